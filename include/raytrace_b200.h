@@ -1,0 +1,187 @@
+/*
+ * raytrace_b200.h — C ABI of libraytrace_b200.so
+ *
+ * The drop-in boundary for ONE hot path of gonewest818/raytrace-clj: the per-pixel
+ * path-tracing loop.  The reference has no FFI of its own; the seam is the render
+ * block of `-main` (reference src/raytrace_clj/core.clj:99-108): input
+ * (nx ny nr camera world), output every pixel's [ir ig ib] written at
+ * (i, ny-1-j).  Everything the reference computes inside that block — `pixel`
+ * (core.clj:43-57), `color` (core.clj:17-41), `get-ray` (camera.clj:8-16,35-48),
+ * `hit?` on Sphere / UVSphere / MovingSphere and the brute-force closest-hit
+ * reduce (hitable.clj:15-26,141-259), `scatter`/`emitted` of Lambertian / Metal /
+ * Dielectric / DiffuseLight (shader.clj:6-119), `sample` of Constant / UVGradient
+ * / Checkerboard (texture.clj:14-50) and the vec3 helpers (util.clj:5-52) — runs
+ * on the GPU behind these entry points.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer, the
+ *     library copies during the call and keeps no host pointer after return;
+ *   - every function returns RT_OK (0) or a negative rt_status; the message of
+ *     the last failure on a context is `rt_last_error(ctx)`;
+ *   - one rt_ctx may be used by one thread at a time (calls are serialised by a
+ *     mutex inside the context);
+ *   - there is NO CPU fallback: without a usable CUDA device rt_create fails.
+ *
+ * The JVM-side binding (JNA) a maintainer would add to the reference is shown in
+ * INTEGRATION.md and shipped as source under clojure/.
+ */
+#ifndef RAYTRACE_B200_H
+#define RAYTRACE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+typedef struct rt_ctx rt_ctx;
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_ARG = -1,          /* bad argument (null pointer, negative size, bad id …)   */
+    RT_ERR_UNSUPPORTED = -2,  /* object / material / texture type outside the hot path  */
+    RT_ERR_CUDA = -3,         /* CUDA runtime error; rt_last_error has the CUDA string  */
+    RT_ERR_STATE = -4,        /* call order: render before set_scene / set_camera       */
+    RT_ERR_NODEVICE = -5      /* no usable CUDA device (there is no CPU fallback)       */
+} rt_status;
+
+/* sphere_flags bits */
+#define RT_SPHERE_UV      1u  /* UVSphere (hitable.clj:141-172): uv from get-sphere-uv (hitable.clj:128-139) */
+#define RT_SPHERE_MOVING  2u  /* MovingSphere (hitable.clj:224-259): centre lerped by ray time                */
+
+/* material types (shader.clj) */
+#define RT_MAT_LAMBERTIAN    0  /* shader.clj:29-36   tex = albedo                    */
+#define RT_MAT_METAL         1  /* shader.clj:46-59   tex = albedo, param = fuzz      */
+#define RT_MAT_DIELECTRIC    2  /* shader.clj:76-104  param = ri                      */
+#define RT_MAT_DIFFUSE_LIGHT 3  /* shader.clj:114-119 tex = emission                  */
+
+/* texture types (texture.clj) */
+#define RT_TEX_CONSTANT      0  /* texture.clj:14-16  params[0..2] = colour                                  */
+#define RT_TEX_UV_GRADIENT   1  /* texture.clj:26-34  params = co[3] cu[3] cv[3] cuv[3]                       */
+#define RT_TEX_CHECKERBOARD  2  /* texture.clj:44-50  params[0] = scale, children = {tex0, tex1}              */
+
+/* camera types (camera.clj) */
+#define RT_CAM_PINHOLE    0     /* camera.clj:8-16   uses origin, lleft, horiz, vert; ray time 0, no RNG draws */
+#define RT_CAM_THIN_LENS  1     /* camera.clj:35-48  all 24 floats                                             */
+
+/* render variants */
+#define RT_VARIANT_MEGAKERNEL 0 /* persistent megakernel with per-lane path regeneration */
+#define RT_VARIANT_WAVEFRONT  1 /* persistent wavefront: generate / intersect / shade / compact queues */
+
+/*
+ * Scene = the flattened leaves of the reference's `world` (hitable.clj:97-123 bvh-node
+ * tree walked left to right, de-duplicated), as structure-of-arrays host buffers.
+ * Replaces: the Hitable / Shader / Texture record graph reachable from `world`
+ * (core.clj:90).  float32 on the wire; the reference holds doubles.
+ */
+typedef struct rt_scene_desc {
+    int32_t n_spheres;
+    const float* center0_r;        /* 4*n: cx cy cz radius            (Sphere/UVSphere centre, MovingSphere centre0) */
+    const float* center1;          /* 4*n: c1x c1y c1z pad, or NULL   (MovingSphere centre1; ignored if not moving)  */
+    const float* t0t1;             /* 2*n: t0 t1, or NULL             (MovingSphere t0 t1)                           */
+    const uint32_t* sphere_flags;  /* n: RT_SPHERE_* bits                                                            */
+    const int32_t* material_id;    /* n: index into the material table                                               */
+    int32_t n_materials;
+    const int32_t* mat_type;       /* m: RT_MAT_*                                                                    */
+    const float* mat_param;        /* m: fuzz (metal) | ri (dielectric) | unused                                     */
+    const int32_t* mat_tex;        /* m: texture id (albedo / emission) or -1                                        */
+    int32_t n_textures;
+    const int32_t* tex_type;       /* t: RT_TEX_*                                                                    */
+    const float* tex_params;       /* 12*t                                                                           */
+    const int32_t* tex_children;   /* 2*t: child texture ids (checkerboard) or -1                                    */
+} rt_scene_desc;
+
+/*
+ * Camera record (camera.clj:35 ThinLensCamera / camera.clj:8 PinholeCamera):
+ * cam[0..20] = origin lleft horiz vert u v w (3 floats each), cam[21] = aperture,
+ * cam[22] = t0, cam[23] = t1.
+ */
+
+/* counters filled by rt_get_counters (the reference's metrics.clj:7-9 counters, on device) */
+enum {
+    RT_CTR_RAYS = 0,         /* hit?(world) calls  == `total-rays` (core.clj:24)                  */
+    RT_CTR_SPHERE_TESTS,     /* ray-sphere discriminant evaluations == rays * n_spheres           */
+    RT_CTR_SAMPLES,          /* top-level `color` calls (core.clj:51)                             */
+    RT_CTR_TERM_LIGHT,       /* paths ended on a non-scattering material (DiffuseLight)           */
+    RT_CTR_TERM_ABSORB,      /* paths ended by Metal.scatter returning nil (shader.clj:54)        */
+    RT_CTR_TERM_DEPTH,       /* paths ended by the depth cutoff (core.clj:26)                     */
+    RT_CTR_TERM_MISS,        /* paths ended by a miss (core.clj:40-41)                            */
+    RT_CTR_KERNEL_NS,        /* device time of the last render's kernels, ns (CUDA events)        */
+    RT_CTR_CANDIDATES,       /* (ray, sphere) pairs that passed the FP32 cull and were refined    */
+    RT_CTR_COUNT = 16
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+
+/* Create a context on `n_devices` CUDA devices (ids in device_ids; NULL => device 0).
+ * n_devices > 1 renders sample slices on every device from this one process and combines
+ * the per-device float sums on device_ids[0] over NVLink peer access.                        */
+int rt_create(rt_ctx** out, const int* device_ids, int n_devices);
+void rt_destroy(rt_ctx* ctx);
+const char* rt_last_error(const rt_ctx* ctx);   /* ctx may be NULL: last rt_create failure */
+int rt_abi_version(void);
+
+/* ---- scene / camera (replace the record graph built at core.clj:82-90) ---------------- */
+int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* scene);
+int rt_set_camera(rt_ctx* ctx, int cam_type, const float cam[24]);
+
+/* ---- the hot path (replaces core.clj:99-108) ------------------------------------------ */
+
+/* Render nsamples per pixel, depth cutoff max_depth (reference: 50, core.clj:20,45).
+ * out_linear_rgb: nx*ny*3 float, per-pixel SUM over samples / nsamples (before gamma),
+ *                 pixel (i, j) at ((j*nx)+i)*3, j = 0 is the BOTTOM row (reference's j); may be NULL.
+ * out_rgb8:       nx*ny*3 bytes after sqrt, *255.99, min, truncate (core.clj:52-57), row 0 = TOP
+ *                 (reference writes row ny-1-j, core.clj:105); may be NULL.                      */
+int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t seed,
+              int variant, float* out_linear_rgb, uint8_t* out_rgb8);
+
+/* Same render, device-resident: accumulate samples [sample_begin, sample_begin+sample_count)
+ * of every pixel whose row j satisfies j % row_stride == row_offset into d_sum (DEVICE pointer on
+ * the context's first device, nx*ny*3 float, += semantics; caller zeroes it).  This is the
+ * per-GPU leg of a sharded render: the caller reduces d_sum across ranks (NCCL) and then calls
+ * rt_resolve_device.  Launches on `stream` (a cudaStream_t cast to void*, NULL = default).
+ * Returns after the kernels are enqueued if `sync` is 0.                                       */
+int rt_render_accumulate_device(rt_ctx* ctx, int nx, int ny, int sample_begin, int sample_count,
+                                int row_offset, int row_stride, int max_depth, uint64_t seed,
+                                int variant, float* d_sum, void* stream, int sync);
+
+/* core.clj:52-57 on the device: out = int(min(255.99, 255.99*sqrt(sum/nsamples_total))), y-flipped.
+ * d_rgb8 is a DEVICE pointer (nx*ny*3 bytes).                                                   */
+int rt_resolve_device(rt_ctx* ctx, int nx, int ny, int nsamples_total, const float* d_sum,
+                      uint8_t* d_rgb8, void* stream, int sync);
+
+/* ---- diagnostics used by the parity tests ---------------------------------------------- */
+
+/* Closest hit of n caller-given rays against the scene = Hitlist.hit? (hitable.clj:15-26)
+ * over the flattened leaves: out_t[i] (double), out_id[i] = sphere index or -1.                */
+int rt_trace_primary(rt_ctx* ctx, int n, const float* origins /*3n*/, const float* dirs /*3n*/,
+                     const float* times /*n or NULL*/, float tmin, float tmax,
+                     double* out_t, int32_t* out_id);
+
+/* Camera rays exactly as the render kernels generate them for (pixel i, j, sample s):
+ * out_origin/out_dir 3n floats, out_time n floats; ij is 2n int32 (i, j), s is n int32.        */
+int rt_generate_rays(rt_ctx* ctx, int n, int nx, int ny, const int32_t* ij, const int32_t* s,
+                     uint64_t seed, float* out_origin, float* out_dir, float* out_time);
+
+/* One scatter + emitted evaluation per ray with CALLER-GIVEN random inputs instead of the
+ * Philox stream (shader.clj:29-119 with `rand-in-unit-sphere` = ball[3i..], `rand` = u01[i]):
+ * given ray (o, d, time), hit sphere id and t, writes scattered origin/dir (3n each),
+ * attenuation (3n), emitted (3n) and flags[i] = 1 if scattered, 0 if the path ends.            */
+int rt_shade_batch(rt_ctx* ctx, int n, const float* origins, const float* dirs, const float* times,
+                   const int32_t* hit_id, const double* hit_t, const float* ball, const float* u01,
+                   float* out_origin, float* out_dir, float* out_atten, float* out_emitted,
+                   int32_t* out_flags);
+
+/* FP32 FFMA-chain peak of device 0 of the context, in TFLOP/s (2 flop per FFMA), plus the
+ * packed FFMA2 figure; used as the measured roofline denominator by bench.py.                  */
+int rt_measure_fp32_peak(rt_ctx* ctx, double* out_ffma_tflops, double* out_ffma2_tflops);
+
+int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]);
+int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, char name[64]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYTRACE_B200_H */
