@@ -155,15 +155,18 @@ int rt_resolve_device(rt_ctx* ctx, int nx, int ny, int nsamples_total, const flo
 /* ---- diagnostics used by the parity tests ---------------------------------------------- */
 
 /* Closest hit of n caller-given rays against the scene = Hitlist.hit? (hitable.clj:15-26)
- * over the flattened leaves: out_t[i] (double), out_id[i] = sphere index or -1.                */
+ * over the flattened leaves: out_t[i] (double, +inf on a miss), out_id[i] = sphere index or -1.  */
 int rt_trace_primary(rt_ctx* ctx, int n, const float* origins /*3n*/, const float* dirs /*3n*/,
-                     const float* times /*n or NULL*/, float tmin, float tmax,
+                     const float* times /*n or NULL*/, double tmin, double tmax,
                      double* out_t, int32_t* out_id);
 
 /* Camera rays exactly as the render kernels generate them for (pixel i, j, sample s):
- * out_origin/out_dir 3n floats, out_time n floats; ij is 2n int32 (i, j), s is n int32.        */
+ * out_origin/out_dir 3n floats, out_time n floats; ij is 2n int32 (i, j), s is n int32.
+ * out_rand (5n floats or NULL) receives the uniforms the ray was built from:
+ * (pixel jitter u, pixel jitter v, lens disk x, lens disk y, shutter time u).                   */
 int rt_generate_rays(rt_ctx* ctx, int n, int nx, int ny, const int32_t* ij, const int32_t* s,
-                     uint64_t seed, float* out_origin, float* out_dir, float* out_time);
+                     uint64_t seed, float* out_origin, float* out_dir, float* out_time,
+                     float* out_rand);
 
 /* One scatter + emitted evaluation per ray with CALLER-GIVEN random inputs instead of the
  * Philox stream (shader.clj:29-119 with `rand-in-unit-sphere` = ball[3i..], `rand` = u01[i]):
@@ -178,7 +181,9 @@ int rt_shade_batch(rt_ctx* ctx, int n, const float* origins, const float* dirs, 
  * packed FFMA2 figure; used as the measured roofline denominator by bench.py.                  */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* out_ffma_tflops, double* out_ffma2_tflops);
 
+/* Counters accumulate over renders until reset. */
 int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]);
+int rt_reset_counters(rt_ctx* ctx);
 int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, char name[64]);
 
 #ifdef __cplusplus

@@ -1,0 +1,747 @@
+// rt_api.cu — host side of libraytrace_b200.so: the C ABI of include/raytrace_b200.h.
+//
+// One rt_ctx owns, per CUDA device: the scene in "cull order" SoA buffers, a float sum buffer,
+// an 8-bit image buffer, counters and a stream.  There is no CPU rendering path anywhere in
+// this file: every entry point that produces results launches sm_100a kernels.
+#include "../../include/raytrace_b200.h"
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rt_kernels.cuh"
+
+using namespace rt;
+
+namespace {
+
+constexpr int kR = 4;          // rays (path slots) per thread
+constexpr int kK = 8;          // candidate list depth per ray before an in-loop flush
+constexpr int kBlock = 256;
+constexpr int kMinBlocks = 2;
+constexpr int kTileCap = 4096; // float4 slots of the shared-memory sphere tile when the scene is tiled
+constexpr double kMoverRange = 8.0;  // cull tolerance sized for (time - t0)/(t1 - t0) in [-8, 9]
+
+thread_local std::string g_create_error;
+
+struct DeviceBuffers {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    // scene
+    void* scene_blob = nullptr;
+    DevScene sc{};
+    // frame
+    float* d_sum = nullptr;
+    float* d_mean = nullptr;
+    uint8_t* d_rgb8 = nullptr;
+    size_t frame_px = 0;
+    unsigned long long* d_counters = nullptr;   // DC_COUNT + 1 (last = work counter)
+    // scratch for diagnostics
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int sm_count = 0, clock_khz = 0;
+    char name[64] = {0};
+    float last_ms = 0.f;
+    bool timed = false;
+};
+
+}  // namespace
+
+struct rt_ctx {
+    std::mutex mu;
+    std::string err;
+    std::vector<DeviceBuffers> devs;
+    bool has_scene = false, has_cam = false;
+    int n_spheres = 0;
+    int cull_cap = 0, preloaded = 0;
+    double time_lo = -INFINITY, time_hi = INFINITY;   // ray times the mover cull tolerance covers
+    DevCamera cam{};
+    uint64_t counters[RT_CTR_COUNT] = {0};
+    std::vector<bool> peer_ok;
+};
+
+namespace {
+
+int fail(rt_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define RT_CUDA(ctx, expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(ctx, RT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+    } while (0)
+
+int ensure_scratch(rt_ctx* ctx, DeviceBuffers& d, size_t bytes) {
+    if (d.scratch_bytes >= bytes) return RT_OK;
+    if (d.scratch) cudaFree(d.scratch);
+    d.scratch = nullptr;
+    d.scratch_bytes = 0;
+    RT_CUDA(ctx, cudaMalloc(&d.scratch, bytes));
+    d.scratch_bytes = bytes;
+    return RT_OK;
+}
+
+int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
+    if (d.frame_px >= px) return RT_OK;
+    if (d.d_sum) cudaFree(d.d_sum);
+    if (d.d_mean) cudaFree(d.d_mean);
+    if (d.d_rgb8) cudaFree(d.d_rgb8);
+    d.d_sum = d.d_mean = nullptr;
+    d.d_rgb8 = nullptr;
+    d.frame_px = 0;
+    RT_CUDA(ctx, cudaMalloc(&d.d_sum, px * 3 * sizeof(float)));
+    RT_CUDA(ctx, cudaMalloc(&d.d_mean, px * 3 * sizeof(float)));
+    RT_CUDA(ctx, cudaMalloc(&d.d_rgb8, px * 3));
+    d.frame_px = px;
+    return RT_OK;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+float round_up_f32(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+size_t mega_smem_bytes(int cull_cap) { return (size_t)cull_cap * sizeof(float4) + (size_t)kR * kK * kBlock * sizeof(uint32_t); }
+
+template <typename Kern>
+int configure_kernel(rt_ctx* ctx, Kern kern, size_t smem, int* blocks_per_sm) {
+    RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int b = 0;
+    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kBlock, smem));
+    if (b < 1) return fail(ctx, RT_ERR_CUDA, "kernel does not fit on an SM");
+    *blocks_per_sm = b;
+    return RT_OK;
+}
+
+// Launch the render kernels for one device's share of the work (async on d.stream).
+int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begin, int sample_count, int row_offset,
+                  int row_stride, int max_depth, uint64_t seed, int variant, float* d_sum, cudaStream_t stream) {
+    if (variant != RT_VARIANT_MEGAKERNEL && variant != RT_VARIANT_WAVEFRONT)
+        return fail(ctx, RT_ERR_ARG, "unknown render variant");
+    if (variant == RT_VARIANT_WAVEFRONT) return fail(ctx, RT_ERR_UNSUPPORTED, "wavefront variant not built yet");
+    RenderParams P{};
+    P.sc = d.sc;
+    P.cam = ctx->cam;
+    P.nx = nx;
+    P.ny = ny;
+    P.sample_begin = sample_begin;
+    P.sample_count = sample_count;
+    P.row_offset = row_offset;
+    P.row_stride = row_stride;
+    P.rows_in_shard = (ny - row_offset + row_stride - 1) / row_stride;
+    P.max_depth = max_depth;
+    P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    P.sum = d_sum;
+    P.counters = d.d_counters;
+    P.work_counter = d.d_counters + DC_COUNT;
+    P.total_work = (unsigned long long)sample_count * (unsigned long long)nx * (unsigned long long)P.rows_in_shard;
+    P.cull_cap = ctx->cull_cap;
+    P.preloaded = ctx->preloaded;
+    RT_CUDA(ctx, cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long), stream));
+    if (P.total_work == 0) return RT_OK;
+    auto kern = mega_kernel<kR, kK, kBlock, kMinBlocks>;
+    size_t smem = mega_smem_bytes(ctx->cull_cap);
+    int bps = 0;
+    int rc = configure_kernel(ctx, kern, smem, &bps);
+    if (rc) return rc;
+    unsigned long long want = (P.total_work + (unsigned long long)kBlock * kR - 1) / ((unsigned long long)kBlock * kR);
+    int grid = (int)std::min<unsigned long long>((unsigned long long)d.sm_count * bps, want);
+    if (grid < 1) grid = 1;
+    kern<<<grid, kBlock, smem, stream>>>(P);
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
+}
+
+int check_ready(rt_ctx* ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_set_scene has not been called");
+    return RT_OK;
+}
+
+int check_camera_times(rt_ctx* ctx) {
+    if (!ctx->has_cam) return fail(ctx, RT_ERR_STATE, "rt_set_camera has not been called");
+    if (ctx->cam.type == CAM_THIN_LENS) {
+        double lo = std::min(ctx->cam.t0, ctx->cam.t1), hi = std::max(ctx->cam.t0, ctx->cam.t1);
+        if (lo < ctx->time_lo || hi > ctx->time_hi)
+            return fail(ctx, RT_ERR_UNSUPPORTED, "camera shutter interval is far outside a moving sphere's [t0, t1]");
+    } else if (0.0 < ctx->time_lo || 0.0 > ctx->time_hi) {
+        return fail(ctx, RT_ERR_UNSUPPORTED, "ray time 0 is far outside a moving sphere's [t0, t1]");
+    }
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
+    if (!out) return fail(nullptr, RT_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n_devices < 0 || n_devices > 8) return fail(nullptr, RT_ERR_ARG, "n_devices must be in [1, 8]");
+    if (n_devices == 0 || !device_ids) n_devices = 1;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RT_ERR_NODEVICE,
+                    std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    rt_ctx* ctx = new rt_ctx();
+    ctx->devs.resize(n_devices);
+    ctx->peer_ok.assign(n_devices, false);
+    for (int i = 0; i < n_devices; ++i) {
+        DeviceBuffers& d = ctx->devs[i];
+        d.dev = device_ids ? device_ids[i] : 0;
+        if (d.dev < 0 || d.dev >= count) {
+            g_create_error = "device id out of range";
+            delete ctx;
+            return RT_ERR_ARG;
+        }
+        cudaDeviceProp prop;
+        if ((e = cudaSetDevice(d.dev)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, d.dev)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.ev0)) != cudaSuccess || (e = cudaEventCreate(&d.ev1)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaMalloc(&d.d_counters, (DC_COUNT + 1) * sizeof(unsigned long long))) != cudaSuccess ||
+            (e = cudaMemset(d.d_counters, 0, (DC_COUNT + 1) * sizeof(unsigned long long))) != cudaSuccess) {
+            g_create_error = std::string("device init: ") + cudaGetErrorString(e);
+            rt_destroy(ctx);
+            return RT_ERR_CUDA;
+        }
+        if (prop.major < 10) {
+            g_create_error = std::string("device ") + prop.name + " is not sm_100-class; this library is sm_100a only";
+            rt_destroy(ctx);
+            return RT_ERR_NODEVICE;
+        }
+        d.sm_count = prop.multiProcessorCount;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d.dev);
+        d.clock_khz = khz;
+        snprintf(d.name, sizeof(d.name), "%s", prop.name);
+    }
+    // peer access from the root device to every other device (NVLink loads in the reduce kernel)
+    for (int i = 1; i < n_devices; ++i) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->devs[0].dev, ctx->devs[i].dev);
+        if (can) {
+            cudaSetDevice(ctx->devs[0].dev);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->devs[i].dev, 0);
+            if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) ctx->peer_ok[i] = true;
+            cudaGetLastError();
+        }
+    }
+    cudaSetDevice(ctx->devs[0].dev);
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_destroy(rt_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.dev);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.scene_blob) cudaFree(d.scene_blob);
+        if (d.d_sum) cudaFree(d.d_sum);
+        if (d.d_mean) cudaFree(d.d_mean);
+        if (d.d_rgb8) cudaFree(d.d_rgb8);
+        if (d.d_counters) cudaFree(d.d_counters);
+        if (d.scratch) cudaFree(d.scratch);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.ev_done) cudaEventDestroy(d.ev_done);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, char name[64]) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (sm_count) *sm_count = ctx->devs[0].sm_count;
+    if (clock_khz) *clock_khz = ctx->devs[0].clock_khz;
+    if (name) memcpy(name, ctx->devs[0].name, 64);
+    return RT_OK;
+}
+
+// Upload: validate, reorder to cull order (static spheres, then moving), build the FP32 cull
+// records with their conservative inflation, and copy one blob per device.
+int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!s) return fail(ctx, RT_ERR_ARG, "scene is null");
+    const int n = s->n_spheres, nm_ = s->n_materials, nt = s->n_textures;
+    if (n <= 0 || !s->center0_r || !s->material_id) return fail(ctx, RT_ERR_ARG, "scene needs at least one sphere");
+    if (nm_ <= 0 || !s->mat_type || !s->mat_param || !s->mat_tex) return fail(ctx, RT_ERR_ARG, "material table missing");
+    if (nt < 0 || (nt > 0 && (!s->tex_type || !s->tex_params || !s->tex_children)))
+        return fail(ctx, RT_ERR_ARG, "texture table missing");
+    for (int t = 0; t < nt; ++t) {
+        int ty = s->tex_type[t];
+        if (ty != RT_TEX_CONSTANT && ty != RT_TEX_UV_GRADIENT && ty != RT_TEX_CHECKERBOARD)
+            return fail(ctx, RT_ERR_UNSUPPORTED, "texture type outside the accelerated path (texture.clj:60-138)");
+        if (ty == RT_TEX_CHECKERBOARD)
+            for (int c = 0; c < 2; ++c) {
+                int ch = s->tex_children[2 * t + c];
+                if (ch < 0 || ch >= t) return fail(ctx, RT_ERR_ARG, "checkerboard child must be an earlier texture id");
+            }
+    }
+    for (int m = 0; m < nm_; ++m) {
+        int ty = s->mat_type[m];
+        if (ty < RT_MAT_LAMBERTIAN || ty > RT_MAT_DIFFUSE_LIGHT)
+            return fail(ctx, RT_ERR_UNSUPPORTED, "material type outside the accelerated path (shader.clj:129-143)");
+        if (ty != RT_MAT_DIELECTRIC && (s->mat_tex[m] < 0 || s->mat_tex[m] >= nt))
+            return fail(ctx, RT_ERR_ARG, "material texture id out of range");
+    }
+    std::vector<int> order;
+    order.reserve(n);
+    int n_static = 0;
+    double time_lo = -INFINITY, time_hi = INFINITY;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < n; ++i) {
+            unsigned fl = s->sphere_flags ? s->sphere_flags[i] : 0u;
+            bool moving = (fl & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
+            if ((int)moving == pass) order.push_back(i);
+            if (pass == 0) {
+                if (fl & ~(RT_SPHERE_UV | RT_SPHERE_MOVING)) return fail(ctx, RT_ERR_UNSUPPORTED, "unknown sphere flag");
+                if (s->material_id[i] < 0 || s->material_id[i] >= nm_) return fail(ctx, RT_ERR_ARG, "material id out of range");
+                if (!moving) n_static++;
+                else {
+                    double t0 = s->t0t1[2 * i], t1 = s->t0t1[2 * i + 1];
+                    if (!(t1 != t0)) return fail(ctx, RT_ERR_ARG, "moving sphere with t1 == t0");
+                    double dt = std::fabs(t1 - t0);
+                    time_lo = std::max(time_lo, std::min(t0, t1) - kMoverRange * dt);
+                    time_hi = std::min(time_hi, std::max(t0, t1) + kMoverRange * dt);
+                }
+            }
+        }
+    const int n_moving = n - n_static;
+
+    // blob layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_cull_a = take((size_t)n * 16), o_cull_b = take((size_t)std::max(n_moving, 1) * 16);
+    size_t o_c0r = take((size_t)n * 16), o_c1 = take((size_t)n * 16), o_t0t1 = take((size_t)n * 8);
+    size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n * 4), o_mat = take((size_t)n * 4);
+    size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);
+    size_t o_ttype = take((size_t)std::max(nt, 1) * 4), o_tparam = take((size_t)std::max(nt, 1) * 48), o_tchild = take((size_t)std::max(nt, 1) * 8);
+    std::vector<unsigned char> blob(off, 0);
+    float* cull_a = (float*)(blob.data() + o_cull_a);
+    float* cull_b = (float*)(blob.data() + o_cull_b);
+    float* c0r = (float*)(blob.data() + o_c0r);
+    float* c1 = (float*)(blob.data() + o_c1);
+    float* t0t1 = (float*)(blob.data() + o_t0t1);
+    int* orig = (int*)(blob.data() + o_orig);
+    int* cull_of = (int*)(blob.data() + o_cull_of);
+    unsigned* flags = (unsigned*)(blob.data() + o_flags);
+    int* mat = (int*)(blob.data() + o_mat);
+    const double eps = (double)CULL_EPS;
+    for (int k = 0; k < n; ++k) {
+        int i = order[k];
+        bool moving = k >= n_static;
+        orig[k] = i;
+        cull_of[i] = k;
+        flags[k] = (s->sphere_flags ? s->sphere_flags[i] : 0u) & (moving ? ~0u : ~RT_SPHERE_MOVING);
+        mat[k] = s->material_id[i];
+        for (int c = 0; c < 4; ++c) c0r[4 * k + c] = s->center0_r[4 * i + c];
+        double r = std::fabs((double)s->center0_r[4 * i + 3]);
+        if (!moving) {
+            for (int c = 0; c < 3; ++c) c1[4 * k + c] = s->center0_r[4 * i + c];
+            t0t1[2 * k] = 0.f;
+            t0t1[2 * k + 1] = 1.f;
+            for (int c = 0; c < 3; ++c) cull_a[4 * k + c] = s->center0_r[4 * i + c];
+            cull_a[4 * k + 3] = round_up_f32(r * r * (1.0 + eps));
+        } else {
+            for (int c = 0; c < 3; ++c) c1[4 * k + c] = s->center1[4 * i + c];
+            double t0 = s->t0t1[2 * i], t1 = s->t0t1[2 * i + 1];
+            t0t1[2 * k] = (float)t0;
+            t0t1[2 * k + 1] = (float)t1;
+            double amax = 0, bmax = 0, c0max = 0, dmax = 0;
+            int km = k - n_static;
+            for (int c = 0; c < 3; ++c) {
+                double p0 = s->center0_r[4 * i + c], p1 = s->center1[4 * i + c];
+                double B = (p1 - p0) / (t1 - t0);
+                double A = p0 - t0 * B;
+                cull_a[4 * k + c] = (float)A;
+                cull_b[4 * km + c] = (float)B;
+                amax = std::max(amax, std::fabs(A));
+                bmax = std::max(bmax, std::fabs(B));
+                c0max = std::max(c0max, std::max(std::fabs(p0), std::fabs(p1)));
+                dmax = std::max(dmax, std::fabs(p1 - p0));
+            }
+            // FP32 centre error bound for (time - t0)/(t1 - t0) in [-kMoverRange, 1 + kMoverRange]
+            double tmax_abs = std::max(std::fabs(t0), std::fabs(t1)) + kMoverRange * std::fabs(t1 - t0);
+            double e_c = std::ldexp(1.0, -21) * (amax + tmax_abs * bmax + c0max + (kMoverRange + 1.0) * dmax + r);
+            double re = r + e_c;
+            cull_a[4 * k + 3] = round_up_f32(re * re * (1.0 + eps));
+        }
+    }
+    memcpy(blob.data() + o_mtype, s->mat_type, (size_t)nm_ * 4);
+    memcpy(blob.data() + o_mparam, s->mat_param, (size_t)nm_ * 4);
+    memcpy(blob.data() + o_mtex, s->mat_tex, (size_t)nm_ * 4);
+    if (nt > 0) {
+        memcpy(blob.data() + o_ttype, s->tex_type, (size_t)nt * 4);
+        memcpy(blob.data() + o_tparam, s->tex_params, (size_t)nt * 48);
+        memcpy(blob.data() + o_tchild, s->tex_children, (size_t)nt * 8);
+    }
+    for (auto& d : ctx->devs) {
+        RT_CUDA(ctx, cudaSetDevice(d.dev));
+        RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        if (d.scene_blob) cudaFree(d.scene_blob);
+        d.scene_blob = nullptr;
+        RT_CUDA(ctx, cudaMalloc(&d.scene_blob, blob.size()));
+        RT_CUDA(ctx, cudaMemcpyAsync(d.scene_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, d.stream));
+        RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        char* b = (char*)d.scene_blob;
+        DevScene& sc = d.sc;
+        sc.n = n; sc.n_static = n_static; sc.n_moving = n_moving;
+        sc.cull_a = (const float4*)(b + o_cull_a); sc.cull_b = (const float4*)(b + o_cull_b);
+        sc.ex_c0r = (const float4*)(b + o_c0r); sc.ex_c1 = (const float4*)(b + o_c1); sc.ex_t0t1 = (const float2*)(b + o_t0t1);
+        sc.orig_id = (const int*)(b + o_orig); sc.cull_of_orig = (const int*)(b + o_cull_of);
+        sc.flags = (const unsigned*)(b + o_flags); sc.mat_id = (const int*)(b + o_mat);
+        sc.mat_type = (const int*)(b + o_mtype); sc.mat_param = (const float*)(b + o_mparam); sc.mat_tex = (const int*)(b + o_mtex);
+        sc.tex_type = (const int*)(b + o_ttype); sc.tex_params = (const float*)(b + o_tparam); sc.tex_child = (const int*)(b + o_tchild);
+    }
+    cudaSetDevice(ctx->devs[0].dev);
+    ctx->n_spheres = n;
+    if (n + n_moving <= kTileCap) {
+        ctx->preloaded = 1;
+        ctx->cull_cap = (int)align_up((size_t)(n + n_moving), 8);
+    } else {
+        ctx->preloaded = 0;
+        ctx->cull_cap = kTileCap;
+    }
+    ctx->time_lo = time_lo;
+    ctx->time_hi = time_hi;
+    ctx->has_scene = true;
+    return RT_OK;
+}
+
+int rt_set_camera(rt_ctx* ctx, int cam_type, const float cam[24]) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!cam) return fail(ctx, RT_ERR_ARG, "cam is null");
+    if (cam_type != RT_CAM_PINHOLE && cam_type != RT_CAM_THIN_LENS) return fail(ctx, RT_ERR_UNSUPPORTED, "unknown camera type");
+    DevCamera& c = ctx->cam;
+    c.type = cam_type;
+    auto g = [&](int k) { return make_float3(cam[3 * k], cam[3 * k + 1], cam[3 * k + 2]); };
+    c.origin = g(0); c.lleft = g(1); c.horiz = g(2); c.vert = g(3); c.u = g(4); c.v = g(5); c.w = g(6);
+    c.lens_radius = cam[21] / 2.0f;   // camera.clj:38
+    c.t0 = cam[22];
+    c.t1 = cam[23];
+    ctx->has_cam = true;
+    return RT_OK;
+}
+
+int rt_render_accumulate_device(rt_ctx* ctx, int nx, int ny, int sample_begin, int sample_count, int row_offset,
+                                int row_stride, int max_depth, uint64_t seed, int variant, float* d_sum, void* stream,
+                                int sync) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = check_camera_times(ctx))) return rc;
+    if (nx <= 0 || ny <= 0 || sample_count < 0 || sample_begin < 0 || max_depth < 0 || !d_sum || row_stride < 1 ||
+        row_offset < 0 || row_offset >= row_stride)
+        return fail(ctx, RT_ERR_ARG, "bad render arguments");
+    if ((long long)nx * ny > 0x7fffffffLL / 3) return fail(ctx, RT_ERR_ARG, "image too large");
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    RT_CUDA(ctx, cudaEventRecord(d.ev0, st));
+    rc = launch_render(ctx, d, nx, ny, sample_begin, sample_count, row_offset, row_stride, max_depth, seed, variant, d_sum, st);
+    if (rc) return rc;
+    RT_CUDA(ctx, cudaEventRecord(d.ev1, st));
+    d.timed = true;
+    if (sync) RT_CUDA(ctx, cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+int rt_resolve_device(rt_ctx* ctx, int nx, int ny, int nsamples_total, const float* d_sum, uint8_t* d_rgb8, void* stream,
+                      int sync) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nx <= 0 || ny <= 0 || nsamples_total <= 0 || !d_sum || !d_rgb8) return fail(ctx, RT_ERR_ARG, "bad resolve arguments");
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    ResolveParams P{};
+    P.sum = d_sum; P.n_peers = 0; P.nx = nx; P.ny = ny; P.nr = nsamples_total; P.rgb8 = d_rgb8; P.mean = nullptr; P.sum_out = nullptr;
+    int total = nx * ny * 3;
+    cudaStream_t st = (cudaStream_t)stream;
+    resolve_kernel<<<(total + 255) / 256, 256, 0, st>>>(P);
+    RT_CUDA(ctx, cudaGetLastError());
+    if (sync) RT_CUDA(ctx, cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t seed, int variant, float* out_linear_rgb,
+              uint8_t* out_rgb8) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = check_camera_times(ctx))) return rc;
+    if (nx <= 0 || ny <= 0 || nsamples <= 0 || max_depth < 0) return fail(ctx, RT_ERR_ARG, "bad render arguments");
+    if ((long long)nx * ny > 0x7fffffffLL / 3) return fail(ctx, RT_ERR_ARG, "image too large");
+    const size_t px = (size_t)nx * ny;
+    const int G = (int)ctx->devs.size();
+    // sample slices: device g renders samples [g*S/G, (g+1)*S/G) of every pixel
+    for (int g = 0; g < G; ++g) {
+        DeviceBuffers& d = ctx->devs[g];
+        RT_CUDA(ctx, cudaSetDevice(d.dev));
+        if ((rc = ensure_frame(ctx, d, px))) return rc;
+        int s0 = (int)((long long)nsamples * g / G), s1 = (int)((long long)nsamples * (g + 1) / G);
+        RT_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+        RT_CUDA(ctx, cudaMemsetAsync(d.d_sum, 0, px * 3 * sizeof(float), d.stream));
+        if ((rc = launch_render(ctx, d, nx, ny, s0, s1 - s0, 0, 1, max_depth, seed, variant, d.d_sum, d.stream))) return rc;
+        RT_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+        RT_CUDA(ctx, cudaEventRecord(d.ev_done, d.stream));
+        d.timed = true;
+    }
+    // combine on the root device: the resolve kernel reads the peers' sums over NVLink
+    DeviceBuffers& root = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(root.dev));
+    ResolveParams P{};
+    P.sum = root.d_sum; P.n_peers = 0; P.nx = nx; P.ny = ny; P.nr = nsamples;
+    P.rgb8 = out_rgb8 ? root.d_rgb8 : nullptr;
+    P.mean = out_linear_rgb ? root.d_mean : nullptr;
+    P.sum_out = nullptr;
+    for (int g = 1; g < G; ++g) {
+        DeviceBuffers& d = ctx->devs[g];
+        RT_CUDA(ctx, cudaStreamWaitEvent(root.stream, d.ev_done, 0));
+        if (ctx->peer_ok[g]) {
+            P.peers[P.n_peers++] = d.d_sum;
+        } else {   // no peer mapping: stage through a copy, then add
+            if ((rc = ensure_scratch(ctx, root, (size_t)(G - 1) * px * 3 * sizeof(float)))) return rc;
+            float* stage = (float*)root.scratch + (size_t)(g - 1) * px * 3;
+            RT_CUDA(ctx, cudaMemcpyPeerAsync(stage, root.dev, d.d_sum, d.dev, px * 3 * sizeof(float), root.stream));
+            P.peers[P.n_peers++] = stage;
+        }
+    }
+    int total = nx * ny * 3;
+    resolve_kernel<<<(total + 255) / 256, 256, 0, root.stream>>>(P);
+    RT_CUDA(ctx, cudaGetLastError());
+    if (out_linear_rgb)
+        RT_CUDA(ctx, cudaMemcpyAsync(out_linear_rgb, root.d_mean, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
+    if (out_rgb8) RT_CUDA(ctx, cudaMemcpyAsync(out_rgb8, root.d_rgb8, px * 3, cudaMemcpyDeviceToHost, root.stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(root.stream));
+    for (int g = 1; g < G; ++g) {
+        RT_CUDA(ctx, cudaSetDevice(ctx->devs[g].dev));
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->devs[g].stream));
+    }
+    cudaSetDevice(root.dev);
+    return RT_OK;
+}
+
+int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs, const float* times, double tmin,
+                     double tmax, double* out_t, int32_t* out_id) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && (!origins || !dirs || !out_t || !out_id))) return fail(ctx, RT_ERR_ARG, "bad trace arguments");
+    if (n == 0) return RT_OK;
+    if (times)
+        for (int i = 0; i < n; ++i)
+            if (!(times[i] >= ctx->time_lo && times[i] <= ctx->time_hi))
+                return fail(ctx, RT_ERR_UNSUPPORTED, "ray time far outside a moving sphere's [t0, t1]");
+    if (!times && !(0.0 >= ctx->time_lo && 0.0 <= ctx->time_hi))
+        return fail(ctx, RT_ERR_UNSUPPORTED, "ray time 0 far outside a moving sphere's [t0, t1]");
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    size_t b_o = align_up((size_t)n * 12, 256), b_t = align_up((size_t)n * 4, 256), b_ot = align_up((size_t)n * 8, 256);
+    if ((rc = ensure_scratch(ctx, d, 2 * b_o + 2 * b_t + b_ot))) return rc;
+    char* base = (char*)d.scratch;
+    float* d_o = (float*)base;
+    float* d_d = (float*)(base + b_o);
+    float* d_tm = (float*)(base + 2 * b_o);
+    int* d_id = (int*)(base + 2 * b_o + b_t);
+    double* d_t = (double*)(base + 2 * b_o + 2 * b_t);
+    RT_CUDA(ctx, cudaMemcpyAsync(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
+    if (times) RT_CUDA(ctx, cudaMemcpyAsync(d_tm, times, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
+    TraceParams P{};
+    P.sc = d.sc; P.n = n; P.origins = d_o; P.dirs = d_d; P.times = times ? d_tm : nullptr;
+    P.tmin = tmin; P.tmax = tmax; P.out_t = d_t; P.out_id = d_id; P.cull_cap = ctx->cull_cap; P.preloaded = ctx->preloaded;
+    auto kern = trace_kernel<kR, kK, kBlock>;
+    size_t smem = mega_smem_bytes(ctx->cull_cap);
+    int bps = 0;
+    if ((rc = configure_kernel(ctx, kern, smem, &bps))) return rc;
+    int want = (int)(((long long)n + kBlock * kR - 1) / (kBlock * kR));
+    int grid = std::max(1, std::min(d.sm_count * bps, want));
+    kern<<<grid, kBlock, smem, d.stream>>>(P);
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaMemcpyAsync(out_t, d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(out_id, d_id, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return RT_OK;
+}
+
+int rt_generate_rays(rt_ctx* ctx, int n, int nx, int ny, const int32_t* ij, const int32_t* s, uint64_t seed,
+                     float* out_origin, float* out_dir, float* out_time, float* out_rand) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_cam) return fail(ctx, RT_ERR_STATE, "rt_set_camera has not been called");
+    if (n < 0 || nx <= 0 || ny <= 0 || (n > 0 && (!ij || !s || !out_origin || !out_dir || !out_time)))
+        return fail(ctx, RT_ERR_ARG, "bad generate_rays arguments");
+    if (n == 0) return RT_OK;
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    size_t b_ij = align_up((size_t)n * 8, 256), b_s = align_up((size_t)n * 4, 256), b_v = align_up((size_t)n * 12, 256),
+           b_r = align_up((size_t)n * 20, 256);
+    int rc;
+    if ((rc = ensure_scratch(ctx, d, b_ij + 2 * b_s + 2 * b_v + b_r))) return rc;
+    char* base = (char*)d.scratch;
+    int* d_ij = (int*)base;
+    int* d_s = (int*)(base + b_ij);
+    float* d_o = (float*)(base + b_ij + b_s);
+    float* d_d = (float*)(base + b_ij + b_s + b_v);
+    float* d_t = (float*)(base + b_ij + b_s + 2 * b_v);
+    float* d_r = (float*)(base + b_ij + 2 * b_s + 2 * b_v);
+    RT_CUDA(ctx, cudaMemcpyAsync(d_ij, ij, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_s, s, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
+    genrays_kernel<<<(n + 255) / 256, 256, 0, d.stream>>>(ctx->cam, n, nx, ny, d_ij, d_s,
+                                                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), d_o, d_d, d_t,
+                                                         out_rand ? d_r : nullptr);
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaMemcpyAsync(out_origin, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(out_dir, d_d, (size_t)n * 12, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(out_time, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
+    if (out_rand) RT_CUDA(ctx, cudaMemcpyAsync(out_rand, d_r, (size_t)n * 20, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return RT_OK;
+}
+
+int rt_shade_batch(rt_ctx* ctx, int n, const float* origins, const float* dirs, const float* times, const int32_t* hit_id,
+                   const double* hit_t, const float* ball, const float* u01v, float* out_origin, float* out_dir,
+                   float* out_atten, float* out_emitted, int32_t* out_flags) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && (!origins || !dirs || !hit_id || !hit_t || !ball || !u01v || !out_origin || !out_dir ||
+                            !out_atten || !out_emitted || !out_flags)))
+        return fail(ctx, RT_ERR_ARG, "bad shade_batch arguments");
+    if (n == 0) return RT_OK;
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    size_t b3 = align_up((size_t)n * 12, 256), b1 = align_up((size_t)n * 4, 256), b8 = align_up((size_t)n * 8, 256);
+    if ((rc = ensure_scratch(ctx, d, 7 * b3 + 4 * b1 + b8))) return rc;
+    char* p = (char*)d.scratch;
+    float* d_o = (float*)p; p += b3;
+    float* d_d = (float*)p; p += b3;
+    float* d_ball = (float*)p; p += b3;
+    float* d_oo = (float*)p; p += b3;
+    float* d_od = (float*)p; p += b3;
+    float* d_oa = (float*)p; p += b3;
+    float* d_oe = (float*)p; p += b3;
+    float* d_tm = (float*)p; p += b1;
+    float* d_u = (float*)p; p += b1;
+    int* d_id = (int*)p; p += b1;
+    int* d_fl = (int*)p; p += b1;
+    double* d_ht = (double*)p;
+    RT_CUDA(ctx, cudaMemcpyAsync(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_ball, ball, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
+    if (times) RT_CUDA(ctx, cudaMemcpyAsync(d_tm, times, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_u, u01v, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_id, hit_id, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_ht, hit_t, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream));
+    shade_kernel<<<(n + 255) / 256, 256, 0, d.stream>>>(d.sc, n, d_o, d_d, times ? d_tm : nullptr, d_id, d_ht, d_ball, d_u,
+                                                       d_oo, d_od, d_oa, d_oe, d_fl);
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaMemcpyAsync(out_origin, d_oo, (size_t)n * 12, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(out_dir, d_od, (size_t)n * 12, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(out_atten, d_oa, (size_t)n * 12, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(out_emitted, d_oe, (size_t)n * 12, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(out_flags, d_fl, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return RT_OK;
+}
+
+int rt_measure_fp32_peak(rt_ctx* ctx, double* out_ffma_tflops, double* out_ffma2_tflops) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    const int blocks = d.sm_count * 8, threads = 256, iters = 1 << 15;
+    int rc;
+    if ((rc = ensure_scratch(ctx, d, (size_t)blocks * threads * 4))) return rc;
+    float* out = (float*)d.scratch;
+    double best[2] = {0, 0};
+    for (int variant = 0; variant < 2; ++variant) {
+        for (int rep = 0; rep < 4; ++rep) {
+            RT_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+            if (variant == 0) ffma_peak_kernel<false><<<blocks, threads, 0, d.stream>>>(out, iters, 1.0000001f, 1e-7f);
+            else ffma_peak_kernel<true><<<blocks, threads, 0, d.stream>>>(out, iters, 1.0000001f, 1e-7f);
+            RT_CUDA(ctx, cudaGetLastError());
+            RT_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+            RT_CUDA(ctx, cudaEventSynchronize(d.ev1));
+            float ms = 0;
+            RT_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+            double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;   // 16 FMA per thread per iter either way
+            if (rep > 0) best[variant] = std::max(best[variant], flops / (ms * 1e-3) / 1e12);
+        }
+    }
+    if (out_ffma_tflops) *out_ffma_tflops = best[0];
+    if (out_ffma2_tflops) *out_ffma2_tflops = best[1];
+    d.timed = false;
+    return RT_OK;
+}
+
+int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]) {
+    if (!ctx || !out) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    unsigned long long dc[DC_COUNT];
+    uint64_t total[DC_COUNT] = {0};
+    float max_ms = 0.f;
+    for (auto& d : ctx->devs) {
+        RT_CUDA(ctx, cudaSetDevice(d.dev));
+        RT_CUDA(ctx, cudaDeviceSynchronize());
+        RT_CUDA(ctx, cudaMemcpy(dc, d.d_counters, sizeof(dc), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < DC_COUNT; ++i) total[i] += dc[i];
+        if (d.timed) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, d.ev0, d.ev1) == cudaSuccess) d.last_ms = ms;
+            cudaGetLastError();
+        }
+        max_ms = std::max(max_ms, d.last_ms);
+    }
+    cudaSetDevice(ctx->devs[0].dev);
+    memset(out, 0, sizeof(uint64_t) * RT_CTR_COUNT);
+    out[RT_CTR_RAYS] = total[DC_RAYS];
+    out[RT_CTR_SPHERE_TESTS] = total[DC_RAYS] * (uint64_t)ctx->n_spheres;
+    out[RT_CTR_SAMPLES] = total[DC_SAMPLES];
+    out[RT_CTR_TERM_LIGHT] = total[DC_TERM_LIGHT];
+    out[RT_CTR_TERM_ABSORB] = total[DC_TERM_ABSORB];
+    out[RT_CTR_TERM_DEPTH] = total[DC_TERM_DEPTH];
+    out[RT_CTR_TERM_MISS] = total[DC_TERM_MISS];
+    out[RT_CTR_KERNEL_NS] = (uint64_t)((double)max_ms * 1e6);
+    out[RT_CTR_CANDIDATES] = total[DC_CANDIDATES];
+    return RT_OK;
+}
+
+int rt_reset_counters(rt_ctx* ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& d : ctx->devs) {
+        RT_CUDA(ctx, cudaSetDevice(d.dev));
+        RT_CUDA(ctx, cudaDeviceSynchronize());
+        RT_CUDA(ctx, cudaMemset(d.d_counters, 0, (DC_COUNT + 1) * sizeof(unsigned long long)));
+    }
+    cudaSetDevice(ctx->devs[0].dev);
+    return RT_OK;
+}
+
+}  // extern "C"

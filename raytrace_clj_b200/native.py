@@ -204,7 +204,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_set_scene", "rt_set_camera", "rt_render",
     "rt_render_accumulate_device", "rt_resolve_device", "rt_trace_primary", "rt_generate_rays", "rt_shade_batch",
-    "rt_measure_fp32_peak", "rt_get_counters", "rt_device_info",
+    "rt_measure_fp32_peak", "rt_get_counters", "rt_reset_counters", "rt_device_info",
 ]
 
 _lib = None
@@ -231,9 +231,10 @@ def load_library():
                                               C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.rt_resolve_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int]
-    L.rt_trace_primary.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f64p, _i32p]
+    L.rt_trace_primary.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, C.c_double, C.c_double, _f64p, _i32p]
     L.rt_generate_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_uint64, _f32p, _f32p,
-                                   _f32p]
+                                   _f32p, _f32p]
+    L.rt_reset_counters.argtypes = [C.c_void_p]
     L.rt_shade_batch.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _i32p, _f64p, _f32p, _f32p, _f32p, _f32p,
                                  _f32p, _f32p, _i32p]
     L.rt_measure_fp32_peak.argtypes = [C.c_void_p, _f64p, _f64p]
@@ -328,8 +329,8 @@ class Renderer:
         tm = None if times is None else np.ascontiguousarray(times, np.float32)
         t = np.empty(n, np.float64)
         ids = np.empty(n, np.int32)
-        self._check(self.L.rt_trace_primary(self.h, n, _p(o, _f32p), _p(d, _f32p), _p(tm, _f32p), C.c_float(t_min),
-                                            C.c_float(t_max), _p(t, _f64p), _p(ids, _i32p)), "rt_trace_primary")
+        self._check(self.L.rt_trace_primary(self.h, n, _p(o, _f32p), _p(d, _f32p), _p(tm, _f32p), C.c_double(t_min),
+                                            C.c_double(t_max), _p(t, _f64p), _p(ids, _i32p)), "rt_trace_primary")
         return t, ids
 
     def generate_rays(self, nx, ny, ij, s, seed=1):
@@ -337,9 +338,11 @@ class Renderer:
         s = np.ascontiguousarray(s, np.int32)
         n = ij.shape[0]
         o = np.empty((n, 3), np.float32); d = np.empty((n, 3), np.float32); t = np.empty(n, np.float32)
+        rnd = np.empty((n, 5), np.float32)
         self._check(self.L.rt_generate_rays(self.h, n, nx, ny, _p(ij, _i32p), _p(s, _i32p), C.c_uint64(seed),
-                                            _p(o, _f32p), _p(d, _f32p), _p(t, _f32p)), "rt_generate_rays")
-        return o, d, t
+                                            _p(o, _f32p), _p(d, _f32p), _p(t, _f32p), _p(rnd, _f32p)),
+                    "rt_generate_rays")
+        return o, d, t, rnd
 
     def shade_batch(self, origins, dirs, times, hit_id, hit_t, ball, u01):
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
@@ -367,6 +370,9 @@ class Renderer:
         out = np.zeros(RT_CTR_COUNT, np.uint64)
         self._check(self.L.rt_get_counters(self.h, _p(out, _u64p)), "rt_get_counters")
         return {k: int(v) for k, v in zip(COUNTER_NAMES, out)}
+
+    def reset_counters(self):
+        self._check(self.L.rt_reset_counters(self.h), "rt_reset_counters")
 
     def device_info(self):
         sm = C.c_int32(); clk = C.c_int32(); name = C.create_string_buffer(64)
