@@ -23,7 +23,6 @@ using namespace rt;
 namespace {
 
 constexpr int kR = 4;          // rays (path slots) per thread
-constexpr int kK = 8;          // candidate list depth per ray before an in-loop flush
 constexpr int kBlock = 256;
 constexpr int kMinBlocks = 2;
 constexpr int kTileCap = 4096; // float4 slots of the shared-memory sphere tile when the scene is tiled
@@ -116,7 +115,7 @@ float round_up_f32(double x) {
     return f;
 }
 
-size_t mega_smem_bytes(int cull_cap) { return (size_t)cull_cap * sizeof(float4) + (size_t)kR * kK * kBlock * sizeof(uint32_t); }
+size_t mega_smem_bytes(int cull_cap) { return (size_t)cull_cap * sizeof(float4) + (size_t)LIST_K * kBlock * sizeof(uint16_t); }
 
 template <typename Kern>
 int configure_kernel(rt_ctx* ctx, Kern kern, size_t smem, int* blocks_per_sm) {
@@ -154,7 +153,7 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
     P.preloaded = ctx->preloaded;
     RT_CUDA(ctx, cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long), stream));
     if (P.total_work == 0) return RT_OK;
-    auto kern = mega_kernel<kR, kK, kBlock, kMinBlocks>;
+    auto kern = mega_kernel<kR, kBlock, kMinBlocks>;
     size_t smem = mega_smem_bytes(ctx->cull_cap);
     int bps = 0;
     int rc = configure_kernel(ctx, kern, smem, &bps);
@@ -364,7 +363,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
             for (int c = 0; c < 3; ++c) c1[4 * k + c] = s->center0_r[4 * i + c];
             t0t1[2 * k] = 0.f;
             t0t1[2 * k + 1] = 1.f;
-            for (int c = 0; c < 3; ++c) cull_a[4 * k + c] = s->center0_r[4 * i + c];
+            for (int c = 0; c < 3; ++c) cull_a[4 * k + c] = -s->center0_r[4 * i + c];   // negated: f = o + (-c)
             cull_a[4 * k + 3] = round_up_f32(r * r * (1.0 + eps));
         } else {
             for (int c = 0; c < 3; ++c) c1[4 * k + c] = s->center1[4 * i + c];
@@ -377,8 +376,8 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
                 double p0 = s->center0_r[4 * i + c], p1 = s->center1[4 * i + c];
                 double B = (p1 - p0) / (t1 - t0);
                 double A = p0 - t0 * B;
-                cull_a[4 * k + c] = (float)A;
-                cull_b[4 * km + c] = (float)B;
+                cull_a[4 * k + c] = (float)(-A);   // negated: f = o + nA + time * nB
+                cull_b[4 * km + c] = (float)(-B);
                 amax = std::max(amax, std::fabs(A));
                 bmax = std::max(bmax, std::fabs(B));
                 c0max = std::max(c0max, std::max(std::fabs(p0), std::fabs(p1)));
@@ -575,7 +574,7 @@ int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs
     TraceParams P{};
     P.sc = d.sc; P.n = n; P.origins = d_o; P.dirs = d_d; P.times = times ? d_tm : nullptr;
     P.tmin = tmin; P.tmax = tmax; P.out_t = d_t; P.out_id = d_id; P.cull_cap = ctx->cull_cap; P.preloaded = ctx->preloaded;
-    auto kern = trace_kernel<kR, kK, kBlock>;
+    auto kern = trace_kernel<kR, kBlock>;
     size_t smem = mega_smem_bytes(ctx->cull_cap);
     int bps = 0;
     if ((rc = configure_kernel(ctx, kern, smem, &bps))) return rc;

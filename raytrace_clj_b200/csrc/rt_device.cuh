@@ -41,8 +41,8 @@ enum { DC_RAYS = 0, DC_SAMPLES, DC_TERM_LIGHT, DC_TERM_ABSORB, DC_TERM_DEPTH, DC
 // Scene in HBM, "cull order": static spheres first [0, n_static), then moving [n_static, n).
 struct DevScene {
     int n, n_static, n_moving;
-    const float4* cull_a;     // [n]        static: (cx, cy, cz, r2_inflated); moving: (Ax, Ay, Az, r2_inflated)
-    const float4* cull_b;     // [n_moving] moving: (Bx, By, Bz, 0)   centre(time) = A + time * B
+    const float4* cull_a;     // [n]        static: (-cx, -cy, -cz, r2_inflated); moving: (-Ax, -Ay, -Az, r2_inflated)
+    const float4* cull_b;     // [n_moving] moving: (-Bx, -By, -Bz, 0)   centre(time) = A + time * B
     const float4* ex_c0r;     // [n] exact centre0 + radius   (float32 as marshalled)
     const float4* ex_c1;      // [n] exact centre1
     const float2* ex_t0t1;    // [n]

