@@ -25,6 +25,7 @@ namespace {
 constexpr int kR = 4;          // rays (path slots) per thread
 constexpr int kBlock = 256;
 constexpr int kMinBlocks = 2;
+constexpr int kWaveBatchesPerWarp = 4;  // wavefront queue capacity per CTA = kBlock * kR * this
 constexpr int kTileCap = 4096; // float4 slots of the shared-memory sphere tile when the scene is tiled
 constexpr double kMoverRange = 8.0;  // cull tolerance sized for (time - t0)/(t1 - t0) in [-8, 9]
 
@@ -43,6 +44,10 @@ struct DeviceBuffers {
     uint8_t* d_rgb8 = nullptr;
     size_t frame_px = 0;
     unsigned long long* d_counters = nullptr;   // DC_COUNT + 1 (last = work counter)
+    // wavefront queues
+    float4* wave_queue = nullptr;
+    float2* wave_hits = nullptr;
+    size_t wave_entries = 0;      // total entries allocated (ctas * capacity)
     // scratch for diagnostics
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -107,6 +112,19 @@ int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
     return RT_OK;
 }
 
+int ensure_wave(rt_ctx* ctx, DeviceBuffers& d, size_t entries) {
+    if (d.wave_entries >= entries) return RT_OK;
+    if (d.wave_queue) cudaFree(d.wave_queue);
+    if (d.wave_hits) cudaFree(d.wave_hits);
+    d.wave_queue = nullptr;
+    d.wave_hits = nullptr;
+    d.wave_entries = 0;
+    RT_CUDA(ctx, cudaMalloc(&d.wave_queue, entries * 2 * 3 * sizeof(float4)));
+    RT_CUDA(ctx, cudaMalloc(&d.wave_hits, entries * sizeof(float2)));
+    d.wave_entries = entries;
+    return RT_OK;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 float round_up_f32(double x) {
@@ -132,7 +150,8 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
                   int row_stride, int max_depth, uint64_t seed, int variant, float* d_sum, cudaStream_t stream) {
     if (variant != RT_VARIANT_MEGAKERNEL && variant != RT_VARIANT_WAVEFRONT)
         return fail(ctx, RT_ERR_ARG, "unknown render variant");
-    if (variant == RT_VARIANT_WAVEFRONT) return fail(ctx, RT_ERR_UNSUPPORTED, "wavefront variant not built yet");
+    if (variant == RT_VARIANT_WAVEFRONT && max_depth > 255)
+        return fail(ctx, RT_ERR_ARG, "the wavefront variant packs the depth in 8 bits: max_depth <= 255");
     RenderParams P{};
     P.sc = d.sc;
     P.cam = ctx->cam;
@@ -153,15 +172,34 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
     P.preloaded = ctx->preloaded;
     RT_CUDA(ctx, cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long), stream));
     if (P.total_work == 0) return RT_OK;
-    auto kern = mega_kernel<kR, kBlock, kMinBlocks>;
+    if ((sample_begin + sample_count) >= (1 << 24)) return fail(ctx, RT_ERR_ARG, "sample index must stay below 2^24");
     size_t smem = mega_smem_bytes(ctx->cull_cap);
+    unsigned long long want = (P.total_work + (unsigned long long)kBlock * kR - 1) / ((unsigned long long)kBlock * kR);
     int bps = 0;
+    if (variant == RT_VARIANT_MEGAKERNEL) {
+        auto kern = mega_kernel<kR, kBlock, kMinBlocks>;
+        int rc = configure_kernel(ctx, kern, smem, &bps);
+        if (rc) return rc;
+        int grid = (int)std::min<unsigned long long>((unsigned long long)d.sm_count * bps, want);
+        if (grid < 1) grid = 1;
+        kern<<<grid, kBlock, smem, stream>>>(P);
+        RT_CUDA(ctx, cudaGetLastError());
+        return RT_OK;
+    }
+    // persistent wavefront: every CTA is an independent engine with its own queues
+    auto kern = wave_kernel<kR, kBlock, kMinBlocks>;
     int rc = configure_kernel(ctx, kern, smem, &bps);
     if (rc) return rc;
-    unsigned long long want = (P.total_work + (unsigned long long)kBlock * kR - 1) / ((unsigned long long)kBlock * kR);
     int grid = (int)std::min<unsigned long long>((unsigned long long)d.sm_count * bps, want);
     if (grid < 1) grid = 1;
-    kern<<<grid, kBlock, smem, stream>>>(P);
+    const int capacity = kBlock * kR * kWaveBatchesPerWarp;
+    if ((rc = ensure_wave(ctx, d, (size_t)d.sm_count * bps * capacity))) return rc;
+    WaveParams W{};
+    W.base = P;
+    W.queue = d.wave_queue;
+    W.hits = d.wave_hits;
+    W.capacity = capacity;
+    kern<<<grid, kBlock, smem, stream>>>(W);
     RT_CUDA(ctx, cudaGetLastError());
     return RT_OK;
 }
@@ -262,6 +300,8 @@ void rt_destroy(rt_ctx* ctx) {
         if (d.d_rgb8) cudaFree(d.d_rgb8);
         if (d.d_counters) cudaFree(d.d_counters);
         if (d.scratch) cudaFree(d.scratch);
+        if (d.wave_queue) cudaFree(d.wave_queue);
+        if (d.wave_hits) cudaFree(d.wave_hits);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_done) cudaEventDestroy(d.ev_done);

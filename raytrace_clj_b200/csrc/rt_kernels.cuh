@@ -52,11 +52,12 @@ struct RenderParams {
 // the end of each sphere class.
 // ------------------------------------------------------------------------------------------
 constexpr int LIST_K = 32;       // entries per thread
-constexpr int LIST_GUARD = 4;    // spheres between two overflow checks (= unroll group)
+constexpr int LIST_GUARD = 2;    // spheres between two overflow checks (= unroll group; small bodies stay in the L0 I-cache)
 
 template <int R, int BLOCK>
 struct Intersect {
-    static_assert(R == 4, "entry layout holds 4 sign bits");
+    static_assert(R == 1 || R == 2 || R == 4, "entry layout holds up to 4 sign bits");
+    static constexpr unsigned SIGN_MASK = (1u << R) - 1u;
     float ox[R], oy[R], oz[R];     // origin
     float hx[R], hy[R], hz[R];     // cull direction: d * sqrt(1 + eps) / |d|
     float dx[R], dy[R], dz[R];     // direction as given (un-normalised, util.clj:13-16)
@@ -86,40 +87,49 @@ struct Intersect {
         tm[r] = 0.f;
     }
 
-    template <int RR>
-    __device__ __forceinline__ void refine_one(const DevScene& sc, int k) {
-        double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, ox[RR], oy[RR], oz[RR], dx[RR], dy[RR],
-                                    dz[RR], tm[RR], tmin, tmax);
-        if (t <= best_t[RR] && t < CUDART_INF) {   // exact ties go to the lower caller index (hitable.clj:17-26)
-            int orig = __ldg(&sc.orig_id[k]);
-            if (t < best_t[RR] || orig < best_orig[RR]) {
-                best_t[RR] = t;
-                best_k[RR] = k;
-                best_orig[RR] = orig;
-            }
-        }
-        ncand++;
-    }
-
     // The list pointer is a byte address in the shared window (one LEA less per sphere than indexing).
     static __device__ __forceinline__ void push_entry(unsigned& ptr, unsigned acc) {
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(ptr), "h"((unsigned short)acc) : "memory");
-        if ((~acc) & 15u) ptr += BLOCK * 2;   // some ray's key has a clear sign bit: keep the entry
+        if ((~acc) & SIGN_MASK) ptr += BLOCK * 2;   // some ray's key has a clear sign bit: keep the entry
     }
     static __device__ __forceinline__ unsigned list_begin(const uint16_t* list) {
         return (unsigned)__cvta_generic_to_shared(list + threadIdx.x);
     }
 
-    // refine every listed survivor; entries are (k_local << 4 | sign bits), ray r at bit R-1-r
+    // Refine every listed survivor in FP64.  Entries are (k_local << R | sign bits), ray r at bit R-1-r.
+    // Each lane walks its own (ray, sphere) pairs, ONE refine call site: the warp runs
+    // max-over-lanes(#pairs) iterations instead of (#entries x R) sparsely populated calls.
     __device__ __forceinline__ void flush(const DevScene& sc, const uint16_t* list, unsigned& ptr, int kbase) {
         const int count = (int)(ptr - list_begin(list)) / (BLOCK * 2);
-        for (int i = 0; i < count; ++i) {
-            unsigned e = list[i * BLOCK + threadIdx.x];
-            int k = kbase + (int)(e >> 4);
-            if (!(e & 8u)) refine_one<0>(sc, k);
-            if (!(e & 4u)) refine_one<1>(sc, k);
-            if (!(e & 2u)) refine_one<2>(sc, k);
-            if (!(e & 1u)) refine_one<3>(sc, k);
+        int i = 0;
+        unsigned e = 0, pend = 0;   // pend: rays of the current entry still to refine (bit r = ray r)
+        for (;;) {
+            while (pend == 0 && i < count) {
+                e = list[i * BLOCK + threadIdx.x];
+                ++i;
+                pend = (~__brev(e) >> (32 - R)) & SIGN_MASK;   // bit R-1-r of e -> bit r, inverted: 1 = survivor
+            }
+            if (pend == 0) break;
+            const int r = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const int k = kbase + (int)(e >> R);
+            float sox = ox[0], soy = oy[0], soz = oz[0], sdx = dx[0], sdy = dy[0], sdz = dz[0], stm = tm[0];
+#pragma unroll
+            for (int q = 1; q < R; ++q)
+                if (r == q) { sox = ox[q]; soy = oy[q]; soz = oz[q]; sdx = dx[q]; sdy = dy[q]; sdz = dz[q]; stm = tm[q]; }
+            const double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, sox, soy, soz, sdx, sdy, sdz,
+                                              stm, tmin, tmax);
+            ncand++;
+            if (t < CUDART_INF) {
+                const int orig = __ldg(&sc.orig_id[k]);
+#pragma unroll
+                for (int q = 0; q < R; ++q)   // exact ties go to the lower caller index (hitable.clj:17-26)
+                    if (r == q && (t < best_t[q] || (t == best_t[q] && orig < best_orig[q]))) {
+                        best_t[q] = t;
+                        best_k[q] = k;
+                        best_orig[q] = orig;
+                    }
+            }
         }
         ptr = list_begin(list);
     }
@@ -184,32 +194,36 @@ struct Intersect {
     }
 
     // Whole scene.  In tiled mode every thread of the CTA must call it (tile loads use __syncthreads).
+    // One copy of each hot loop: a preloaded scene is a single resident tile (statics at s_cull[0, ns),
+    // movers' A at s_cull + ns, B at s_cull + ns + nm); a tiled scene streams tiles of `cap` float4 slots.
     __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint16_t* list) {
         begin();
         unsigned ptr = list_begin(list);
         const int ns = sc.n_static, nm = sc.n_moving;
-        if (preloaded) {
-            cull_static(sc, s_cull, ns, 0, list, ptr);
-            cull_moving(sc, s_cull + ns, s_cull + ns + nm, nm, ns, list, ptr);
-        } else {
-            for (int base = 0; base < ns; base += cap) {
-                int count = min(cap, ns - base);
+        for (int base = 0; base < ns; base += cap) {
+            int count = min(cap, ns - base);
+            if (!preloaded) {
                 __syncthreads();
                 for (int i = threadIdx.x; i < count; i += BLOCK) s_cull[i] = __ldg(&sc.cull_a[base + i]);
                 __syncthreads();
-                cull_static(sc, s_cull, count, base, list, ptr);
             }
-            const int half = cap / 2;
-            for (int base = 0; base < nm; base += half) {
-                int count = min(half, nm - base);
+            cull_static(sc, s_cull, count, base, list, ptr);
+        }
+        const int half = cap / 2;
+        const float4* sa = preloaded ? s_cull + ns : s_cull;
+        const float4* sb = preloaded ? s_cull + ns + nm : s_cull + half;
+        const int step = preloaded ? max(nm, 1) : half;
+        for (int base = 0; base < nm; base += step) {
+            int count = min(step, nm - base);
+            if (!preloaded) {
                 __syncthreads();
                 for (int i = threadIdx.x; i < count; i += BLOCK) {
                     s_cull[i] = __ldg(&sc.cull_a[ns + base + i]);
                     s_cull[half + i] = __ldg(&sc.cull_b[base + i]);
                 }
                 __syncthreads();
-                cull_moving(sc, s_cull, s_cull + half, count, ns + base, list, ptr);
             }
+            cull_moving(sc, sa, sb, count, ns + base, list, ptr);
         }
     }
 };
@@ -333,6 +347,225 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
     atomicAdd(&s_ctr[DC_RAYS], n_rays);
     atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
     atomicAdd(&s_ctr[DC_CANDIDATES], I.ncand);
+    __syncthreads();
+    if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent wavefront path tracer: every CTA is an independent wavefront engine.
+//
+//   queue record (3 x float4 per path, AoS so one thread moves a path with 3 LDG/STG.128):
+//       a = (ox, oy, oz, time)   b = (dx, dy, dz, pixel index)   c = (atten r, g, b, sample << 8 | depth)
+//   Each CTA owns two ping-pong queues and a hit buffer of `capacity` entries in HBM/L2 and loops
+//       G  generate   fill the queue with camera rays; (sample, pixel) work items are claimed from
+//                     one global counter, one atomic per warp (ballot + popc prefix)
+//       A  intersect  warps claim batches of 32*R queue entries from a shared-memory counter, run the
+//                     brute-force cull + FP64 refine (4 rays per thread), write (t, k) per entry;
+//                     a nearly empty queue (tail) switches to the 1-ray-per-thread loop
+//       B  shade + regenerate + compact   one path per thread: shade the hit; surviving paths and
+//                     fresh camera rays are appended to the NEXT queue at positions claimed with
+//                     warp ballot + prefix popc + one shared-memory atomic per warp
+//   with __syncthreads between phases.  All warps of a CTA therefore execute the same small code
+//   region at the same time (an asynchronous megakernel loses ~45 % of its issue slots to
+//   instruction-cache misses, profiles/), intersect always runs on a dense compacted queue, and
+//   there is no chip-wide barrier (a grid.sync version spent 41 % of its warp-time waiting):
+//   two CTAs per SM hide each other's barrier and shade phases.
+// ------------------------------------------------------------------------------------------
+struct WaveParams {
+    RenderParams base;
+    float4* queue;             // gridDim.x * 2 * 3 * capacity float4
+    float2* hits;              // gridDim.x * capacity: (t as float, k as int bits)
+    int capacity;              // entries per CTA queue (multiple of 32)
+};
+
+// claim consecutive slots for the lanes whose predicate is set; returns this lane's slot
+__device__ __forceinline__ unsigned warp_claim_shared(unsigned* counter, bool pred, unsigned lane) {
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    unsigned base = 0;
+    if (m) {
+        int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+    }
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// pull one (sample, pixel) work item for every lane with `want`; returns false when the work ran out
+__device__ __forceinline__ bool fetch_and_generate(const RenderParams& P, bool want, unsigned lane, float4& a, float4& b,
+                                                   float4& c) {
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return false;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    unsigned long long w = base + __popc(m & ((1u << lane) - 1u));
+    if (!want || w >= P.total_work) return false;
+    const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
+    unsigned s_local = (unsigned)(w / pshard);
+    unsigned q = (unsigned)(w - (unsigned long long)s_local * pshard);
+    int row_local = (int)(q / (unsigned)P.nx);
+    int i = (int)(q - (unsigned)row_local * (unsigned)P.nx);
+    int j = P.row_offset + row_local * P.row_stride;
+    uint32_t pix = (uint32_t)j * (uint32_t)P.nx + (uint32_t)i;
+    uint32_t smp = (uint32_t)(P.sample_begin + (int)s_local);
+    float3 o, d;
+    float tmv;
+    generate_ray(P.cam, P.nx, P.ny, i, j, pix, smp, P.key, o, d, tmv, nullptr);
+    a = make_float4(o.x, o.y, o.z, tmv);
+    b = make_float4(d.x, d.y, d.z, __uint_as_float(pix));
+    c = make_float4(1.f, 1.f, 1.f, __uint_as_float((smp << 8) | (uint32_t)P.max_depth));
+    return true;
+}
+
+// phase A for one CTA: batches of 32*R entries claimed dynamically (preloaded scene) or walked in
+// CTA-uniform order (tiled scene: the tile loads inside Intersect::run need every thread)
+template <int R, int BLOCK>
+__device__ __forceinline__ void wave_intersect(const RenderParams& P, const float4* qc, float2* hits, unsigned n,
+                                               float4* s_cull, uint16_t* s_list, unsigned* s_batch, unsigned& n_cand) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
+    const unsigned n_batches = (n + 32 * R - 1) / (32 * R);
+    Intersect<R, BLOCK> I;
+    I.tmin = 0.001;               // core.clj:25
+    I.tmax = (double)FLT_MAX;     // Float/MAX_VALUE
+    I.ncand = 0;
+    unsigned batch = warp;
+    const unsigned uniform_end = (n_batches + warps - 1) / warps * warps;
+    for (;;) {
+        if (P.preloaded) {
+            unsigned b = 0;
+            if (lane == 0) b = atomicAdd(s_batch, 1u);
+            batch = __shfl_sync(0xffffffffu, b, 0);
+            if (batch >= n_batches) break;
+        } else {
+            if (batch >= uniform_end) break;
+        }
+        const unsigned wbase = batch * (32 * R) + lane;     // ray r of this lane = entry wbase + 32 r
+        RT_FOR_R {
+            unsigned idx = wbase + 32 * r;
+            if (idx < n) {
+                float4 a = qc[3 * (size_t)idx], b = qc[3 * (size_t)idx + 1];
+                I.ox[r] = a.x; I.oy[r] = a.y; I.oz[r] = a.z; I.tm[r] = a.w;
+                I.dx[r] = b.x; I.dy[r] = b.y; I.dz[r] = b.z;
+            } else {
+                I.kill(r);
+            }
+        }
+        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list);
+        RT_FOR_R {
+            unsigned idx = wbase + 32 * r;
+            if (idx < n) hits[idx] = make_float2((float)I.best_t[r], __int_as_float(I.best_k[r]));
+        }
+        batch += warps;
+    }
+    n_cand += I.ncand;
+}
+
+template <int R, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) wave_kernel(const WaveParams W) {
+    const RenderParams& P = W.base;
+    extern __shared__ float4 smem_f4[];
+    float4* s_cull = smem_f4;
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
+    __shared__ unsigned s_ctr[DC_COUNT];
+    __shared__ unsigned s_qcount[2];
+    __shared__ unsigned s_batch;
+    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_qcount[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_batch = 0;
+    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned cap = (unsigned)W.capacity;
+    float4* q0 = W.queue + (size_t)blockIdx.x * 2 * 3 * cap;
+    float4* queue[2] = {q0, q0 + 3 * (size_t)cap};
+    float2* hits = W.hits + (size_t)blockIdx.x * cap;
+    unsigned n_rays = 0, n_samples = 0, n_cand = 0;
+
+    // ---- phase G: fill queue 0 -------------------------------------------------------------------
+    for (unsigned idx = threadIdx.x; idx < cap; idx += BLOCK) {
+        float4 a, b, c;
+        bool ok = fetch_and_generate(P, true, lane, a, b, c);
+        unsigned slot = warp_claim_shared(&s_qcount[0], ok, lane);
+        if (ok) {
+            float4* q = queue[0] + 3 * (size_t)slot;
+            q[0] = a; q[1] = b; q[2] = c;
+            n_samples++;
+        }
+        if (!__any_sync(0xffffffffu, ok)) break;          // work ran out
+    }
+    __syncthreads();
+
+    int cur = 0;
+    for (;;) {
+        const unsigned n = s_qcount[cur];
+        if (n == 0) break;
+        const float4* qc = queue[cur];
+        if (threadIdx.x == 0) n_rays += n;
+
+        // ---- phase A: intersect ----------------------------------------------------------------------
+        if (n > BLOCK) wave_intersect<R, BLOCK>(P, qc, hits, n, s_cull, s_list, &s_batch, n_cand);
+        else           wave_intersect<1, BLOCK>(P, qc, hits, n, s_cull, s_list, &s_batch, n_cand);   // tail: 1 ray/thread
+        __syncthreads();
+        if (threadIdx.x == 0) { s_batch = 0; s_qcount[cur] = 0; }
+
+        // ---- phase B: shade, compact survivors into the next queue, regenerate -------------------
+        float4* qn = queue[cur ^ 1];
+        for (unsigned idx0 = threadIdx.x - lane; idx0 < n; idx0 += BLOCK) {   // warp-uniform trip count
+            const unsigned idx = idx0 + lane;
+            bool have = idx < n;
+            bool cont = false;
+            float4 a, b, c;
+            if (have) {
+                a = qc[3 * (size_t)idx]; b = qc[3 * (size_t)idx + 1]; c = qc[3 * (size_t)idx + 2];
+                float2 h = hits[idx];
+                int k = __float_as_int(h.y);
+                uint32_t pix = __float_as_uint(b.w), sd = __float_as_uint(c.w);
+                uint32_t smp = sd >> 8;
+                int depth = (int)(sd & 255u);
+                if (k < 0) {                                        // core.clj:40-41 miss -> accum (black)
+                    atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
+                } else {
+                    float3 o = f3(a.x, a.y, a.z), d = f3(b.x, b.y, b.z);
+                    float3 att, em;
+                    int reason = TERM_NONE;
+                    ScatterRng rng{P.key, pix, smp, (uint32_t)(P.max_depth - depth + 1), nullptr, nullptr};
+                    cont = shade_hit(P.sc, k, h.x, o, d, a.w, depth > 0, rng, att, em, reason);
+                    if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
+                        float* dst = P.sum + (size_t)pix * 3;
+                        atomicAdd(dst + 0, c.x * em.x);
+                        atomicAdd(dst + 1, c.y * em.y);
+                        atomicAdd(dst + 2, c.z * em.z);
+                    }
+                    if (cont) {
+                        a = make_float4(o.x, o.y, o.z, a.w);
+                        b = make_float4(d.x, d.y, d.z, b.w);
+                        c = make_float4(c.x * att.x, c.y * att.y, c.z * att.z, __uint_as_float((smp << 8) | (uint32_t)(depth - 1)));
+                    } else {
+                        atomicAdd(&s_ctr[reason == TERM_LIGHT ? DC_TERM_LIGHT
+                                         : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
+                    }
+                }
+            }
+            // a finished path frees its lane for the next (sample, pixel)
+            if (fetch_and_generate(P, have && !cont, lane, a, b, c)) {
+                cont = true;
+                n_samples++;
+            }
+            unsigned slot = warp_claim_shared(&s_qcount[cur ^ 1], cont, lane);
+            if (cont) {
+                float4* q = qn + 3 * (size_t)slot;
+                q[0] = a; q[1] = b; q[2] = c;
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+
+    atomicAdd(&s_ctr[DC_RAYS], n_rays);
+    atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
+    atomicAdd(&s_ctr[DC_CANDIDATES], n_cand);
     __syncthreads();
     if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
 }

@@ -273,7 +273,7 @@ def test_shade_batch_matches_oracle(renderer, scene_c2):
         assert len(att_ok) == 0 or att_ok.mean() > 0.999, (mt, att_ok.mean())
     # checkerboard ground: both colours are produced and agree with the oracle
     ground = same & (ids == int(np.nonzero((flat.center0_r[:, 3] == 1000) & (flat.sphere_flags == 0))[0][0]))
-    cols = {tuple(np.round(c, 3)) for c in g["atten"][ground][:2000]}
+    cols = {tuple(round(float(x), 3) for x in c) for c in g["atten"][ground][:2000]}
     assert (0.2, 0.3, 0.1) in cols and (0.9, 0.9, 0.9) in cols
 
 
@@ -307,7 +307,7 @@ def _render_parity(renderer, flat, cam_type, cam, nx, ny, ns, depth=50, variant=
     return g1
 
 
-@pytest.mark.parametrize("variant", [0])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_render_matches_oracle_random_scene(renderer, scene_c2, variant):
     """BASELINE config 1 stand-in: make-random-scene 200x100, 100 spp (the `lein run out.ppm 200 100 100` shape)."""
     flat, cam_type, cam, _ = scene_c2
@@ -316,7 +316,7 @@ def test_render_matches_oracle_random_scene(renderer, scene_c2, variant):
     _render_parity(renderer, flat, cam_type, cam, 200, 100, 100, variant=variant)
 
 
-@pytest.mark.parametrize("variant", [0])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_render_matches_oracle_material_stress(renderer, variant):
     """BASELINE config 4: metal/glass-heavy mix, depth 50 (long paths, absorbed rays, TIR)."""
     sc = rt.scene.make_material_stress_scene(160, 96, 11, random.Random(4))
@@ -325,7 +325,7 @@ def test_render_matches_oracle_material_stress(renderer, variant):
     _render_parity(renderer, flat, cam_type, cam, 160, 96, 96, variant=variant)
 
 
-@pytest.mark.parametrize("variant", [0])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_render_matches_oracle_two_spheres_and_depth_cutoff(renderer, variant):
     """make-two-spheres (scene.clj:9-49: UVGradient on a Lambertian UVSphere) and a depth cutoff of 2."""
     sc = rt.scene.make_two_spheres(120, 80)
@@ -340,14 +340,15 @@ def test_render_matches_oracle_two_spheres_and_depth_cutoff(renderer, variant):
     assert _rmse(lin, ref) < 0.05 and abs(lin.mean() - ref.mean()) < 5e-3
 
 
-def test_counters_define_the_metric(renderer, scene_c2):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_counters_define_the_metric(renderer, scene_c2, variant):
     """samples == nx*ny*ns; tests == rays * N (brute force, counted on device); every path ends once."""
     flat, cam_type, cam, S = scene_c2
     renderer.set_scene(flat)
     renderer.set_camera(cam_type, cam)
     renderer.reset_counters()
     nx, ny, ns = 150, 100, 8
-    renderer.render(nx, ny, ns, 50, seed=5)
+    renderer.render(nx, ny, ns, 50, seed=5, variant=variant)
     c = renderer.counters()
     assert c["samples"] == nx * ny * ns
     assert c["sphere_tests"] == c["rays"] * flat.n_spheres
@@ -358,7 +359,8 @@ def test_counters_define_the_metric(renderer, scene_c2):
     assert abs(c["term_light"] - oc["term_light"]) < 0.01 * c["samples"]
 
 
-def test_resolve_bit_exact_and_sharding(renderer, scene_c2):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_resolve_bit_exact_and_sharding(renderer, scene_c2, variant):
     """rt_render_accumulate_device + rt_resolve_device on caller-owned device buffers (the per-GPU leg of the
     sharded render): sample slices and interleaved rows add up to the unsharded sums; the 8-bit resolve is
     bit-identical to core.clj:52-57 evaluated by the oracle on the same float sums."""
@@ -370,16 +372,21 @@ def test_resolve_bit_exact_and_sharding(renderer, scene_c2):
     nx, ny, ns = 160, 90, 8
     dev = torch.device("cuda:0")
     full = torch.zeros(ny, nx, 3, device=dev)
-    renderer.render_accumulate_device(nx, ny, 0, ns, full.data_ptr(), seed=77)
+    renderer.render_accumulate_device(nx, ny, 0, ns, full.data_ptr(), seed=77, variant=variant)
     parts = torch.zeros(ny, nx, 3, device=dev)
-    renderer.render_accumulate_device(nx, ny, 0, 3, parts.data_ptr(), seed=77)          # samples [0,3)
-    renderer.render_accumulate_device(nx, ny, 3, 5, parts.data_ptr(), seed=77)          # samples [3,8)
+    renderer.render_accumulate_device(nx, ny, 0, 3, parts.data_ptr(), seed=77, variant=variant)   # samples [0,3)
+    renderer.render_accumulate_device(nx, ny, 3, 5, parts.data_ptr(), seed=77, variant=variant)   # samples [3,8)
     rows = torch.zeros(ny, nx, 3, device=dev)
     for g in range(3):                                                                   # rows j = g (mod 3)
-        renderer.render_accumulate_device(nx, ny, 0, ns, rows.data_ptr(), row_offset=g, row_stride=3, seed=77)
+        renderer.render_accumulate_device(nx, ny, 0, ns, rows.data_ptr(), row_offset=g, row_stride=3, seed=77,
+                                          variant=variant)
     torch.cuda.synchronize()
     f, p, r = full.cpu().numpy(), parts.cpu().numpy(), rows.cpu().numpy()
-    assert np.allclose(f, p, rtol=1e-5, atol=1e-5) and np.allclose(f, r, rtol=1e-5, atol=1e-5)
+    assert np.isfinite(f).all() and np.isfinite(p).all() and np.isfinite(r).all()
+    # same paths, different float summation order (atomics): equal up to rounding of ~8 addends
+    for other in (p, r):
+        err = np.abs(f - other) / np.maximum(1.0, np.abs(f))
+        assert err.max() < 1e-5, (float(err.max()), np.unravel_index(err.argmax(), err.shape))
     assert f.sum() > 0
     rgb = torch.zeros(ny, nx, 3, dtype=torch.uint8, device=dev)
     renderer.resolve_device(nx, ny, ns, full.data_ptr(), rgb.data_ptr())
@@ -391,7 +398,7 @@ def test_resolve_bit_exact_and_sharding(renderer, scene_c2):
     renderer.resolve_device(1, 1, ns, special.data_ptr(), out.data_ptr())
     assert out.cpu().numpy().tolist() == [[[0, 255, 127]]]
     # rt_render (host buffers) returns the same image as the device path
-    lin, img = renderer.render(nx, ny, ns, 50, seed=77)
+    lin, img = renderer.render(nx, ny, ns, 50, seed=77, variant=variant)
     assert np.allclose(lin * ns, f, rtol=1e-5, atol=1e-5)
     assert (img != rgb.cpu().numpy()).mean() < 1e-3     # float summation order may flip a rare 8-bit boundary
 
