@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,9 +26,7 @@ namespace {
 constexpr int kR = 4;          // rays (path slots) per thread
 constexpr int kBlock = 256;
 constexpr int kMinBlocks = 2;
-constexpr int kWaveBatchesPerWarp = 4;  // wavefront queue capacity per CTA = kBlock * kR * this
 constexpr int kTileCap = 4096; // float4 slots of the shared-memory sphere tile when the scene is tiled
-constexpr double kMoverRange = 8.0;  // cull tolerance sized for (time - t0)/(t1 - t0) in [-8, 9]
 
 thread_local std::string g_create_error;
 
@@ -45,9 +44,14 @@ struct DeviceBuffers {
     size_t frame_px = 0;
     unsigned long long* d_counters = nullptr;   // DC_COUNT + 1 (last = work counter)
     // wavefront queues
-    float4* wave_queue = nullptr;
-    float2* wave_hits = nullptr;
-    size_t wave_entries = 0;      // total entries allocated (ctas * capacity)
+    float4* wave_queue = nullptr;            // 2 * 3 * wave_entries float4
+    unsigned long long* wave_best = nullptr; // 2 * wave_entries
+    uint2* wave_pairs = nullptr;
+    double* wave_pair_t = nullptr;
+    WaveState* wave_state = nullptr;
+    WaveState* h_wave_state = nullptr;       // pinned, 2 snapshots
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+    size_t wave_entries = 0;
     // scratch for diagnostics
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -66,7 +70,11 @@ struct rt_ctx {
     bool has_scene = false, has_cam = false;
     int n_spheres = 0;
     int cull_cap = 0, preloaded = 0;
-    double time_lo = -INFINITY, time_hi = INFINITY;   // ray times the mover cull tolerance covers
+    // time window [win_lo, win_hi] the movers' bounding spheres cover; grown (and the cull records rebuilt)
+    // when a camera shutter interval or a traced ray's time falls outside
+    double win_lo = 0.0, win_hi = 0.0;
+    std::vector<float> h_c0r, h_c1, h_t0t1;
+    std::vector<unsigned> h_flags;
     DevCamera cam{};
     uint64_t counters[RT_CTR_COUNT] = {0};
     std::vector<bool> peer_ok;
@@ -112,15 +120,31 @@ int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
     return RT_OK;
 }
 
-int ensure_wave(rt_ctx* ctx, DeviceBuffers& d, size_t entries) {
-    if (d.wave_entries >= entries) return RT_OK;
+constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 2.6)
+constexpr size_t kWaveCapacity = 1u << 21;  // paths in flight per device
+constexpr int kWaveChunk = 4;           // iterations enqueued between two polls of the queue count
+
+void free_wave(DeviceBuffers& d) {
     if (d.wave_queue) cudaFree(d.wave_queue);
-    if (d.wave_hits) cudaFree(d.wave_hits);
-    d.wave_queue = nullptr;
-    d.wave_hits = nullptr;
+    if (d.wave_best) cudaFree(d.wave_best);
+    if (d.wave_pairs) cudaFree(d.wave_pairs);
+    if (d.wave_pair_t) cudaFree(d.wave_pair_t);
+    d.wave_queue = nullptr; d.wave_best = nullptr; d.wave_pairs = nullptr; d.wave_pair_t = nullptr;
     d.wave_entries = 0;
+}
+
+int ensure_wave(rt_ctx* ctx, DeviceBuffers& d, size_t entries) {
+    if (!d.wave_state) {
+        RT_CUDA(ctx, cudaMalloc(&d.wave_state, sizeof(WaveState)));
+        RT_CUDA(ctx, cudaHostAlloc(&d.h_wave_state, 2 * sizeof(WaveState), cudaHostAllocDefault));
+        for (int i = 0; i < 2; ++i) RT_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_poll[i], cudaEventDisableTiming));
+    }
+    if (d.wave_entries >= entries) return RT_OK;
+    free_wave(d);
     RT_CUDA(ctx, cudaMalloc(&d.wave_queue, entries * 2 * 3 * sizeof(float4)));
-    RT_CUDA(ctx, cudaMalloc(&d.wave_hits, entries * sizeof(float2)));
+    RT_CUDA(ctx, cudaMalloc(&d.wave_best, entries * 2 * sizeof(unsigned long long)));
+    RT_CUDA(ctx, cudaMalloc(&d.wave_pairs, entries * kPairsPerEntry * sizeof(uint2)));
+    RT_CUDA(ctx, cudaMalloc(&d.wave_pair_t, entries * kPairsPerEntry * sizeof(double)));
     d.wave_entries = entries;
     return RT_OK;
 }
@@ -142,6 +166,77 @@ int configure_kernel(rt_ctx* ctx, Kern kern, size_t smem, int* blocks_per_sm) {
     RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kBlock, smem));
     if (b < 1) return fail(ctx, RT_ERR_CUDA, "kernel does not fit on an SM");
     *blocks_per_sm = b;
+    return RT_OK;
+}
+
+// tuning knobs (environment, read once): RT_WAVE_BLOCK = 128 | 256 threads per CTA, RT_WAVE_M = queue
+// capacity in 32*R-entry batches per warp
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Wavefront render of one device's share: enqueue iterations (cull, refine, tie-break, shade) ahead of the
+// GPU and poll the queue count every kWaveChunk iterations; returns when the queue has drained (the last
+// polled chunk may still be finishing its empty kernels).
+template <int BLOCK, int MINB>
+int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WaveParams)) {
+    *kern = wf_cull<kR, BLOCK, MINB>;
+    *smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * BLOCK * sizeof(uint16_t);
+    RT_CUDA(ctx, cudaFuncSetAttribute(*kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, *kern, BLOCK, *smem));
+    if (*bps < 1) return fail(ctx, RT_ERR_CUDA, "cull kernel does not fit on an SM");
+    return RT_OK;
+}
+
+int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned long long, cudaStream_t stream) {
+    // CTA shape of the cull kernel: 256 threads x 3 CTAs/SM (80 registers, 24 warps/SM) by default;
+    // RT_CULL_SHAPE = "256x2" | "256x3" | "128x5" | "128x6" for experiments
+    static const std::string shape = getenv("RT_CULL_SHAPE") ? getenv("RT_CULL_SHAPE") : "256x3";
+    void (*cull)(const WaveParams) = nullptr;
+    size_t smem = 0;
+    int bps = 0, cull_block = 256, rc;
+    if (shape == "256x2") rc = cull_config<256, 2>(ctx, &smem, &bps, &cull);
+    else if (shape == "128x5") { rc = cull_config<128, 5>(ctx, &smem, &bps, &cull); cull_block = 128; }
+    else if (shape == "128x6") { rc = cull_config<128, 6>(ctx, &smem, &bps, &cull); cull_block = 128; }
+    else rc = cull_config<256, 3>(ctx, &smem, &bps, &cull);
+    if (rc) return rc;
+    static const size_t cap_env = (size_t)std::max(1, env_int("RT_WAVE_CAPACITY", (int)kWaveCapacity));
+    const size_t capacity = align_up((size_t)std::min<unsigned long long>(cap_env, P.total_work), 32);
+    if ((rc = ensure_wave(ctx, d, capacity))) return rc;
+    WaveParams W{};
+    W.base = P;
+    W.queue[0] = d.wave_queue;
+    W.queue[1] = d.wave_queue + 3 * capacity;
+    W.best_t = d.wave_best;
+    W.best_key = d.wave_best + capacity;
+    W.pairs = d.wave_pairs;
+    W.pair_t = d.wave_pair_t;
+    W.st = d.wave_state;
+    W.capacity = (int)capacity;
+    W.pair_cap = (unsigned)std::min<size_t>(capacity * kPairsPerEntry, 0xfffffff0u);
+    W.cur = 0;
+    const unsigned count0 = (unsigned)std::min<unsigned long long>(capacity, P.total_work);
+    const int light_grid = d.sm_count * 8;
+    wf_generate<<<std::max(1, std::min(light_grid, (int)((count0 + 255) / 256))), 256, 0, stream>>>(W, count0);
+    RT_CUDA(ctx, cudaGetLastError());
+    const int cull_grid = d.sm_count * bps;
+    for (int chunk = 0;; ++chunk) {
+        for (int it = 0; it < kWaveChunk; ++it) {
+            cull<<<cull_grid, cull_block, smem, stream>>>(W);
+            wf_refine<<<light_grid, 256, 0, stream>>>(W);
+            wf_tiebreak<<<light_grid, 256, 0, stream>>>(W);
+            wf_shade<<<light_grid, 256, 0, stream>>>(W);
+            W.cur ^= 1;
+        }
+        RT_CUDA(ctx, cudaGetLastError());
+        RT_CUDA(ctx, cudaMemcpyAsync(&d.h_wave_state[chunk & 1], d.wave_state, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
+        RT_CUDA(ctx, cudaEventRecord(d.ev_poll[chunk & 1], stream));
+        if (chunk > 0) {   // look at the PREVIOUS chunk's snapshot: the GPU always has one chunk queued
+            RT_CUDA(ctx, cudaEventSynchronize(d.ev_poll[(chunk - 1) & 1]));
+            if (d.h_wave_state[(chunk - 1) & 1].qcount[W.cur] == 0) break;   // kWaveChunk is even: same parity
+        }
+    }
     return RT_OK;
 }
 
@@ -187,20 +282,57 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
         return RT_OK;
     }
     // persistent wavefront: every CTA is an independent engine with its own queues
-    auto kern = wave_kernel<kR, kBlock, kMinBlocks>;
-    int rc = configure_kernel(ctx, kern, smem, &bps);
-    if (rc) return rc;
-    int grid = (int)std::min<unsigned long long>((unsigned long long)d.sm_count * bps, want);
-    if (grid < 1) grid = 1;
-    const int capacity = kBlock * kR * kWaveBatchesPerWarp;
-    if ((rc = ensure_wave(ctx, d, (size_t)d.sm_count * bps * capacity))) return rc;
-    WaveParams W{};
-    W.base = P;
-    W.queue = d.wave_queue;
-    W.hits = d.wave_hits;
-    W.capacity = capacity;
-    kern<<<grid, kBlock, smem, stream>>>(W);
-    RT_CUDA(ctx, cudaGetLastError());
+    return launch_wave(ctx, d, P, want, stream);
+}
+
+// FP32 cull record per sphere: (-cx, -cy, -cz, r^2 inflated).  A moving sphere (hitable.clj:224-259) is
+// represented by the bounding sphere of its swept volume over [win_lo, win_hi]: centre = midpoint of
+// centre(win_lo), centre(win_hi), radius = r + half the travelled distance.  Inflation covers float rounding
+// of the record itself plus the cull's own rounding (CULL_EPS), so the cull only ever over-reports.
+void build_cull_records(const rt_ctx* ctx, int n, double win_lo, double win_hi, float* cull_a) {
+    const double eps = (double)CULL_EPS;
+    for (int i = 0; i < n; ++i) {
+        double r = std::fabs((double)ctx->h_c0r[4 * i + 3]);
+        double mid[3], half2 = 0.0, cmax = 0.0;
+        const bool moving = (ctx->h_flags[i] & RT_SPHERE_MOVING) != 0;
+        for (int c = 0; c < 3; ++c) {
+            double p0 = ctx->h_c0r[4 * i + c];
+            if (moving) {
+                double p1 = ctx->h_c1[4 * i + c], t0 = ctx->h_t0t1[2 * i], t1 = ctx->h_t0t1[2 * i + 1];
+                double fa = (win_lo - t0) / (t1 - t0), fb = (win_hi - t0) / (t1 - t0);
+                double pa = p0 * (1.0 - fa) + p1 * fa, pb = p0 * (1.0 - fb) + p1 * fb;
+                mid[c] = 0.5 * (pa + pb);
+                half2 += 0.25 * (pb - pa) * (pb - pa);
+            } else {
+                mid[c] = p0;
+            }
+            cmax = std::max(cmax, std::fabs(mid[c]));
+        }
+        double rb = r + std::sqrt(half2);
+        double e = moving ? std::ldexp(1.0, -21) * (cmax + rb) : 0.0;   // float rounding of the midpoint (+ margin)
+        for (int c = 0; c < 3; ++c) cull_a[4 * i + c] = (float)(-mid[c]);   // negated: f = o + (-c)
+        double re = rb + e;
+        cull_a[4 * i + 3] = round_up_f32(re * re * (1.0 + eps));
+    }
+}
+
+// make sure the movers' bounding spheres cover ray times in [lo, hi]
+int ensure_window(rt_ctx* ctx, double lo, double hi) {
+    if (lo >= ctx->win_lo && hi <= ctx->win_hi) return RT_OK;
+    if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) return fail(ctx, RT_ERR_ARG, "ray time is not finite");
+    ctx->win_lo = std::min(ctx->win_lo, lo);
+    ctx->win_hi = std::max(ctx->win_hi, hi);
+    bool any_moving = false;
+    for (unsigned f : ctx->h_flags) any_moving |= (f & RT_SPHERE_MOVING) != 0;
+    if (!any_moving) return RT_OK;
+    std::vector<float> cull((size_t)ctx->n_spheres * 4);
+    build_cull_records(ctx, ctx->n_spheres, ctx->win_lo, ctx->win_hi, cull.data());
+    for (auto& d : ctx->devs) {
+        RT_CUDA(ctx, cudaSetDevice(d.dev));
+        RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        RT_CUDA(ctx, cudaMemcpy((void*)d.sc.cull_a, cull.data(), cull.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    cudaSetDevice(ctx->devs[0].dev);
     return RT_OK;
 }
 
@@ -212,14 +344,9 @@ int check_ready(rt_ctx* ctx) {
 
 int check_camera_times(rt_ctx* ctx) {
     if (!ctx->has_cam) return fail(ctx, RT_ERR_STATE, "rt_set_camera has not been called");
-    if (ctx->cam.type == CAM_THIN_LENS) {
-        double lo = std::min(ctx->cam.t0, ctx->cam.t1), hi = std::max(ctx->cam.t0, ctx->cam.t1);
-        if (lo < ctx->time_lo || hi > ctx->time_hi)
-            return fail(ctx, RT_ERR_UNSUPPORTED, "camera shutter interval is far outside a moving sphere's [t0, t1]");
-    } else if (0.0 < ctx->time_lo || 0.0 > ctx->time_hi) {
-        return fail(ctx, RT_ERR_UNSUPPORTED, "ray time 0 is far outside a moving sphere's [t0, t1]");
-    }
-    return RT_OK;
+    if (ctx->cam.type == CAM_THIN_LENS)
+        return ensure_window(ctx, std::min(ctx->cam.t0, ctx->cam.t1), std::max(ctx->cam.t0, ctx->cam.t1));
+    return ensure_window(ctx, 0.0, 0.0);
 }
 
 }  // namespace
@@ -300,8 +427,11 @@ void rt_destroy(rt_ctx* ctx) {
         if (d.d_rgb8) cudaFree(d.d_rgb8);
         if (d.d_counters) cudaFree(d.d_counters);
         if (d.scratch) cudaFree(d.scratch);
-        if (d.wave_queue) cudaFree(d.wave_queue);
-        if (d.wave_hits) cudaFree(d.wave_hits);
+        free_wave(d);
+        if (d.wave_state) cudaFree(d.wave_state);
+        if (d.h_wave_state) cudaFreeHost(d.h_wave_state);
+        for (int i = 0; i < 2; ++i)
+            if (d.ev_poll[i]) cudaEventDestroy(d.ev_poll[i]);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_done) cudaEventDestroy(d.ev_done);
@@ -347,89 +477,59 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         if (ty != RT_MAT_DIELECTRIC && (s->mat_tex[m] < 0 || s->mat_tex[m] >= nt))
             return fail(ctx, RT_ERR_ARG, "material texture id out of range");
     }
-    std::vector<int> order;
-    order.reserve(n);
-    int n_static = 0;
-    double time_lo = -INFINITY, time_hi = INFINITY;
-    for (int pass = 0; pass < 2; ++pass)
-        for (int i = 0; i < n; ++i) {
-            unsigned fl = s->sphere_flags ? s->sphere_flags[i] : 0u;
-            bool moving = (fl & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
-            if ((int)moving == pass) order.push_back(i);
-            if (pass == 0) {
-                if (fl & ~(RT_SPHERE_UV | RT_SPHERE_MOVING)) return fail(ctx, RT_ERR_UNSUPPORTED, "unknown sphere flag");
-                if (s->material_id[i] < 0 || s->material_id[i] >= nm_) return fail(ctx, RT_ERR_ARG, "material id out of range");
-                if (!moving) n_static++;
-                else {
-                    double t0 = s->t0t1[2 * i], t1 = s->t0t1[2 * i + 1];
-                    if (!(t1 != t0)) return fail(ctx, RT_ERR_ARG, "moving sphere with t1 == t0");
-                    double dt = std::fabs(t1 - t0);
-                    time_lo = std::max(time_lo, std::min(t0, t1) - kMoverRange * dt);
-                    time_hi = std::min(time_hi, std::max(t0, t1) + kMoverRange * dt);
-                }
-            }
+    double win_lo = INFINITY, win_hi = -INFINITY;
+    for (int i = 0; i < n; ++i) {
+        unsigned fl = s->sphere_flags ? s->sphere_flags[i] : 0u;
+        bool moving = (fl & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
+        if (fl & ~(RT_SPHERE_UV | RT_SPHERE_MOVING)) return fail(ctx, RT_ERR_UNSUPPORTED, "unknown sphere flag");
+        if (s->material_id[i] < 0 || s->material_id[i] >= nm_) return fail(ctx, RT_ERR_ARG, "material id out of range");
+        if (moving) {
+            double t0 = s->t0t1[2 * i], t1 = s->t0t1[2 * i + 1];
+            if (!(t1 != t0)) return fail(ctx, RT_ERR_ARG, "moving sphere with t1 == t0");
+            win_lo = std::min(win_lo, std::min(t0, t1));
+            win_hi = std::max(win_hi, std::max(t0, t1));
         }
-    const int n_moving = n - n_static;
+    }
+    if (!(win_lo <= win_hi)) { win_lo = 0.0; win_hi = 0.0; }   // no movers
+    if (ctx->has_cam) {                                           // cover the shutter interval already set
+        double lo = ctx->cam.type == CAM_THIN_LENS ? std::min(ctx->cam.t0, ctx->cam.t1) : 0.0;
+        double hi = ctx->cam.type == CAM_THIN_LENS ? std::max(ctx->cam.t0, ctx->cam.t1) : 0.0;
+        win_lo = std::min(win_lo, lo);
+        win_hi = std::max(win_hi, hi);
+    }
+
+    // host copy of the geometry: the cull records are rebuilt when the time window has to grow
+    ctx->h_c0r.assign(s->center0_r, s->center0_r + 4 * (size_t)n);
+    ctx->h_c1.assign(4 * (size_t)n, 0.f);
+    ctx->h_t0t1.assign(2 * (size_t)n, 0.f);
+    ctx->h_flags.assign((size_t)n, 0u);
+    for (int i = 0; i < n; ++i) {
+        unsigned fl = s->sphere_flags ? s->sphere_flags[i] : 0u;
+        bool moving = (fl & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
+        ctx->h_flags[i] = moving ? fl : (fl & ~RT_SPHERE_MOVING);
+        for (int c = 0; c < 3; ++c) ctx->h_c1[4 * i + c] = moving ? s->center1[4 * i + c] : s->center0_r[4 * i + c];
+        ctx->h_t0t1[2 * i] = moving ? s->t0t1[2 * i] : 0.f;
+        ctx->h_t0t1[2 * i + 1] = moving ? s->t0t1[2 * i + 1] : 1.f;
+    }
 
     // blob layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_cull_a = take((size_t)n * 16), o_cull_b = take((size_t)std::max(n_moving, 1) * 16);
+    size_t o_cull_a = take((size_t)n * 16);
     size_t o_c0r = take((size_t)n * 16), o_c1 = take((size_t)n * 16), o_t0t1 = take((size_t)n * 8);
     size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n * 4), o_mat = take((size_t)n * 4);
     size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);
     size_t o_ttype = take((size_t)std::max(nt, 1) * 4), o_tparam = take((size_t)std::max(nt, 1) * 48), o_tchild = take((size_t)std::max(nt, 1) * 8);
     std::vector<unsigned char> blob(off, 0);
-    float* cull_a = (float*)(blob.data() + o_cull_a);
-    float* cull_b = (float*)(blob.data() + o_cull_b);
-    float* c0r = (float*)(blob.data() + o_c0r);
-    float* c1 = (float*)(blob.data() + o_c1);
-    float* t0t1 = (float*)(blob.data() + o_t0t1);
+    build_cull_records(ctx, n, win_lo, win_hi, (float*)(blob.data() + o_cull_a));
+    memcpy(blob.data() + o_c0r, ctx->h_c0r.data(), (size_t)n * 16);
+    memcpy(blob.data() + o_c1, ctx->h_c1.data(), (size_t)n * 16);
+    memcpy(blob.data() + o_t0t1, ctx->h_t0t1.data(), (size_t)n * 8);
+    memcpy(blob.data() + o_flags, ctx->h_flags.data(), (size_t)n * 4);
     int* orig = (int*)(blob.data() + o_orig);
     int* cull_of = (int*)(blob.data() + o_cull_of);
-    unsigned* flags = (unsigned*)(blob.data() + o_flags);
-    int* mat = (int*)(blob.data() + o_mat);
-    const double eps = (double)CULL_EPS;
-    for (int k = 0; k < n; ++k) {
-        int i = order[k];
-        bool moving = k >= n_static;
-        orig[k] = i;
-        cull_of[i] = k;
-        flags[k] = (s->sphere_flags ? s->sphere_flags[i] : 0u) & (moving ? ~0u : ~RT_SPHERE_MOVING);
-        mat[k] = s->material_id[i];
-        for (int c = 0; c < 4; ++c) c0r[4 * k + c] = s->center0_r[4 * i + c];
-        double r = std::fabs((double)s->center0_r[4 * i + 3]);
-        if (!moving) {
-            for (int c = 0; c < 3; ++c) c1[4 * k + c] = s->center0_r[4 * i + c];
-            t0t1[2 * k] = 0.f;
-            t0t1[2 * k + 1] = 1.f;
-            for (int c = 0; c < 3; ++c) cull_a[4 * k + c] = -s->center0_r[4 * i + c];   // negated: f = o + (-c)
-            cull_a[4 * k + 3] = round_up_f32(r * r * (1.0 + eps));
-        } else {
-            for (int c = 0; c < 3; ++c) c1[4 * k + c] = s->center1[4 * i + c];
-            double t0 = s->t0t1[2 * i], t1 = s->t0t1[2 * i + 1];
-            t0t1[2 * k] = (float)t0;
-            t0t1[2 * k + 1] = (float)t1;
-            double amax = 0, bmax = 0, c0max = 0, dmax = 0;
-            int km = k - n_static;
-            for (int c = 0; c < 3; ++c) {
-                double p0 = s->center0_r[4 * i + c], p1 = s->center1[4 * i + c];
-                double B = (p1 - p0) / (t1 - t0);
-                double A = p0 - t0 * B;
-                cull_a[4 * k + c] = (float)(-A);   // negated: f = o + nA + time * nB
-                cull_b[4 * km + c] = (float)(-B);
-                amax = std::max(amax, std::fabs(A));
-                bmax = std::max(bmax, std::fabs(B));
-                c0max = std::max(c0max, std::max(std::fabs(p0), std::fabs(p1)));
-                dmax = std::max(dmax, std::fabs(p1 - p0));
-            }
-            // FP32 centre error bound for (time - t0)/(t1 - t0) in [-kMoverRange, 1 + kMoverRange]
-            double tmax_abs = std::max(std::fabs(t0), std::fabs(t1)) + kMoverRange * std::fabs(t1 - t0);
-            double e_c = std::ldexp(1.0, -21) * (amax + tmax_abs * bmax + c0max + (kMoverRange + 1.0) * dmax + r);
-            double re = r + e_c;
-            cull_a[4 * k + 3] = round_up_f32(re * re * (1.0 + eps));
-        }
-    }
+    for (int k = 0; k < n; ++k) orig[k] = cull_of[k] = k;   // cull order = caller order
+    memcpy(blob.data() + o_mat, s->material_id, (size_t)n * 4);
     memcpy(blob.data() + o_mtype, s->mat_type, (size_t)nm_ * 4);
     memcpy(blob.data() + o_mparam, s->mat_param, (size_t)nm_ * 4);
     memcpy(blob.data() + o_mtex, s->mat_tex, (size_t)nm_ * 4);
@@ -448,8 +548,8 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
         char* b = (char*)d.scene_blob;
         DevScene& sc = d.sc;
-        sc.n = n; sc.n_static = n_static; sc.n_moving = n_moving;
-        sc.cull_a = (const float4*)(b + o_cull_a); sc.cull_b = (const float4*)(b + o_cull_b);
+        sc.n = n;
+        sc.cull_a = (const float4*)(b + o_cull_a);
         sc.ex_c0r = (const float4*)(b + o_c0r); sc.ex_c1 = (const float4*)(b + o_c1); sc.ex_t0t1 = (const float2*)(b + o_t0t1);
         sc.orig_id = (const int*)(b + o_orig); sc.cull_of_orig = (const int*)(b + o_cull_of);
         sc.flags = (const unsigned*)(b + o_flags); sc.mat_id = (const int*)(b + o_mat);
@@ -458,15 +558,10 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     }
     cudaSetDevice(ctx->devs[0].dev);
     ctx->n_spheres = n;
-    if (n + n_moving <= kTileCap) {
-        ctx->preloaded = 1;
-        ctx->cull_cap = (int)align_up((size_t)(n + n_moving), 8);
-    } else {
-        ctx->preloaded = 0;
-        ctx->cull_cap = kTileCap;
-    }
-    ctx->time_lo = time_lo;
-    ctx->time_hi = time_hi;
+    ctx->preloaded = n <= kTileCap ? 1 : 0;
+    ctx->cull_cap = ctx->preloaded ? (int)align_up((size_t)n, 8) : kTileCap;
+    ctx->win_lo = win_lo;
+    ctx->win_hi = win_hi;
     ctx->has_scene = true;
     return RT_OK;
 }
@@ -592,12 +687,14 @@ int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n < 0 || (n > 0 && (!origins || !dirs || !out_t || !out_id))) return fail(ctx, RT_ERR_ARG, "bad trace arguments");
     if (n == 0) return RT_OK;
-    if (times)
-        for (int i = 0; i < n; ++i)
-            if (!(times[i] >= ctx->time_lo && times[i] <= ctx->time_hi))
-                return fail(ctx, RT_ERR_UNSUPPORTED, "ray time far outside a moving sphere's [t0, t1]");
-    if (!times && !(0.0 >= ctx->time_lo && 0.0 <= ctx->time_hi))
-        return fail(ctx, RT_ERR_UNSUPPORTED, "ray time 0 far outside a moving sphere's [t0, t1]");
+    {
+        double lo = 0.0, hi = 0.0;
+        if (times) {
+            lo = INFINITY; hi = -INFINITY;
+            for (int i = 0; i < n; ++i) { lo = std::min(lo, (double)times[i]); hi = std::max(hi, (double)times[i]); }
+        }
+        if ((rc = ensure_window(ctx, lo, hi))) return rc;
+    }
     DeviceBuffers& d = ctx->devs[0];
     RT_CUDA(ctx, cudaSetDevice(d.dev));
     size_t b_o = align_up((size_t)n * 12, 256), b_t = align_up((size_t)n * 4, 256), b_ot = align_up((size_t)n * 8, 256);

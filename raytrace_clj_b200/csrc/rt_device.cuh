@@ -38,11 +38,12 @@ enum TermReason { TERM_NONE = 0, TERM_LIGHT = 1, TERM_ABSORB = 2, TERM_DEPTH = 3
 // device counter slots (subset of RT_CTR_* that the kernels write)
 enum { DC_RAYS = 0, DC_SAMPLES, DC_TERM_LIGHT, DC_TERM_ABSORB, DC_TERM_DEPTH, DC_TERM_MISS, DC_CANDIDATES, DC_COUNT = 8 };
 
-// Scene in HBM, "cull order": static spheres first [0, n_static), then moving [n_static, n).
+// Scene in HBM.  "Cull order" is the caller's order (orig_id is the identity today; kept so a future
+// reordering, e.g. for locality, does not touch the kernels).
 struct DevScene {
-    int n, n_static, n_moving;
-    const float4* cull_a;     // [n]        static: (-cx, -cy, -cz, r2_inflated); moving: (-Ax, -Ay, -Az, r2_inflated)
-    const float4* cull_b;     // [n_moving] moving: (-Bx, -By, -Bz, 0)   centre(time) = A + time * B
+    int n;
+    const float4* cull_a;     // [n] (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its
+                              //     swept volume over the time window the context covers
     const float4* ex_c0r;     // [n] exact centre0 + radius   (float32 as marshalled)
     const float4* ex_c1;      // [n] exact centre1
     const float2* ex_t0t1;    // [n]

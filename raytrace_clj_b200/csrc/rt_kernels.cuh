@@ -1,15 +1,19 @@
 // rt_kernels.cuh — sm_100a kernels of libraytrace_b200.so.
 //
-//   Intersect<R,K,BLOCK>   brute-force closest hit (Hitlist.hit?, hitable.clj:15-26) for R rays
-//                          per thread: sphere list staged in shared memory as float4 SoA,
-//                          warp-uniform LDS.128 broadcast, FP32 cull (17 flop / test), survivors
-//                          pushed to per-thread shared-memory lists and refined in FP64.
-//   mega_kernel            persistent megakernel with per-lane path regeneration
-//                          (pixel + color, core.clj:17-57).
-//   trace_kernel           closest hit of caller-given rays (rt_trace_primary).
-//   shade_kernel / genrays_kernel   diagnostics for the parity tests.
-//   resolve_kernel         core.clj:52-57 + the y flip of core.clj:105.
-//   ffma_peak_kernel       FP32 roofline denominator measured on the box.
+//   Culler<R,BLOCK>    the hot loop: brute-force FP32 cull of R rays per thread against the sphere
+//                      list staged in shared memory (Hitlist.hit?, hitable.clj:15-26), survivors
+//                      recorded branch-free in per-thread shared-memory lists
+//   RefineSink         survivors refined in FP64 by the owning thread (trace kernel, megakernel)
+//   PairSink           survivors emitted as (ray, sphere) pairs for a pooled, CTA-wide FP64 refine
+//                      (wavefront kernel)
+//   wf_generate / wf_cull / wf_refine / wf_tiebreak / wf_shade
+//                      wavefront path tracer: one global path queue, one kernel per stage
+//                      (pixel + color, core.clj:17-57); wf_cull is the persistent hot-loop kernel
+//   mega_kernel        persistent megakernel with per-lane path regeneration, kept for comparison
+//   trace_kernel       closest hit of caller-given rays (rt_trace_primary)
+//   shade_kernel / genrays_kernel   diagnostics for the parity tests
+//   resolve_kernel     core.clj:52-57 + the y flip of core.clj:105 (+ NVLink peer reduce)
+//   ffma_peak_kernel   FP32 roofline denominator measured on the box
 #pragma once
 
 #include "rt_device.cuh"
@@ -35,56 +39,59 @@ struct RenderParams {
 };
 
 // ------------------------------------------------------------------------------------------
-// Intersect: R = 4 rays per thread against the whole scene.
-//
-// FP32 cull, per (ray, sphere), 11 FP32-pipe instructions = the 17-flop test of SURVEY §8(d)
-// (a = d.d is folded into a per-ray normalised direction h = d * sqrt(1+eps)/|d|):
-//     f   = o + (-c)                      3 FADD   (movers: + 3 FFMA for c(time) = A + time*B)
+// Culler: the FP32 test, per (ray, sphere), 11 FP32-pipe instructions = the 17-flop test of
+// SURVEY §8(d) (a = d.d is folded into a per-ray normalised direction h = d * sqrt(1+eps)/|d|):
+//     f   = o + (-c)                      3 FADD
 //     b   = f . h                         1 FMUL + 2 FFMA
 //     nc  = r2i - f . f                   3 FFMA
 //     key = b * min(b, 0) + nc            1 FMNMX + 1 FFMA
 // key >= 0  <=>  (approaching and discriminant >= 0) or (origin inside the sphere): exactly the
-// set of spheres that can have a root in front of the origin; r2i is inflated and h is scaled
-// up so rounding can only add false positives.  No branch: the sign bits of the R keys are
-// funnel-shifted onto the sphere index, the 16-bit entry (k << 4 | signs) is stored
-// unconditionally to the thread's shared-memory list and the list pointer advances only if some
-// ray survived.  Survivors are refined in FP64 (refine_candidate) when the list fills and at
-// the end of each sphere class.
+// spheres that can have a root in front of the origin; r2i is inflated and h is scaled up so
+// rounding can only add false positives.  No branch: the sign bits of the R keys are funnel-
+// shifted onto the sphere index, the 16-bit entry (k << R | signs) is stored unconditionally to
+// the thread's shared-memory list and the list pointer advances only if some ray survived.
+// The Sink decides what happens to the survivors when the list fills / a sphere class ends.
 // ------------------------------------------------------------------------------------------
+// 128-bit shared-memory load from a 32-bit shared-window address (keeps ptxas from re-deriving the
+// generic->shared base every iteration: S2UR/UMOV/UIADD3/ULEA/LEA per sphere pair in the profile)
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));   // opaque: one register, not rematerialised
+    return a;
+}
+
+// slice `part` of `parts` of [0, n)
+__device__ __forceinline__ int slice_lo(int n, int part, int parts) { return (int)(((long long)n * part) / parts); }
+
 constexpr int LIST_K = 32;       // entries per thread
 constexpr int LIST_GUARD = 2;    // spheres between two overflow checks (= unroll group; small bodies stay in the L0 I-cache)
 
 template <int R, int BLOCK>
-struct Intersect {
+struct Culler {
     static_assert(R == 1 || R == 2 || R == 4, "entry layout holds up to 4 sign bits");
     static constexpr unsigned SIGN_MASK = (1u << R) - 1u;
     float ox[R], oy[R], oz[R];     // origin
     float hx[R], hy[R], hz[R];     // cull direction: d * sqrt(1 + eps) / |d|
-    float dx[R], dy[R], dz[R];     // direction as given (un-normalised, util.clj:13-16)
-    float tm[R];
-    double best_t[R];
-    int best_k[R], best_orig[R];
-    unsigned ncand;
-    double tmin, tmax;
+    float tm[R];                   // kept for the sinks (the cull itself is time-free)
 
-    __device__ __forceinline__ void begin() {
-        RT_FOR_R {
-            float a = fmaf(dz[r], dz[r], fmaf(dy[r], dy[r], dx[r] * dx[r]));
-            float s = rsqrtf(a) * (1.0f + 0.5f * CULL_EPS);
-            hx[r] = dx[r] * s; hy[r] = dy[r] * s; hz[r] = dz[r] * s;
-            // opaque to the optimiser: otherwise ptxas rematerialises h (RSQ + 4 FMUL) per sphere to save registers
-            asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]));
-            best_t[r] = CUDART_INF;
-            best_k[r] = -1;
-            best_orig[r] = 0x7fffffff;
-        }
+    __device__ __forceinline__ void set_ray(int r, float o_x, float o_y, float o_z, float d_x, float d_y, float d_z,
+                                            float time) {
+        ox[r] = o_x; oy[r] = o_y; oz[r] = o_z; tm[r] = time;
+        float a = fmaf(d_z, d_z, fmaf(d_y, d_y, d_x * d_x));
+        float s = rsqrtf(a) * (1.0f + 0.5f * CULL_EPS);
+        hx[r] = d_x * s; hy[r] = d_y * s; hz[r] = d_z * s;
     }
-
     // a dead slot: a ray that can never produce a candidate (b > 0 and far outside everything)
-    __device__ __forceinline__ void kill(int r) {
-        ox[r] = 1e18f; oy[r] = 0.f; oz[r] = 0.f;
-        dx[r] = 1.f; dy[r] = 0.f; dz[r] = 0.f;
-        tm[r] = 0.f;
+    __device__ __forceinline__ void kill(int r) { set_ray(r, 1e18f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f); }
+
+    // opaque to the optimiser: otherwise ptxas rematerialises h (RSQ + 4 FMUL) per sphere to save registers
+    __device__ __forceinline__ void pin() {
+        RT_FOR_R asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]), "+f"(ox[r]), "+f"(oy[r]), "+f"(oz[r]), "+f"(tm[r]));
     }
 
     // The list pointer is a byte address in the shared window (one LEA less per sphere than indexing).
@@ -95,28 +102,124 @@ struct Intersect {
     static __device__ __forceinline__ unsigned list_begin(const uint16_t* list) {
         return (unsigned)__cvta_generic_to_shared(list + threadIdx.x);
     }
+    static __device__ __forceinline__ int list_count(const uint16_t* list, unsigned ptr) {
+        return (int)(ptr - list_begin(list)) / (BLOCK * 2);
+    }
+    // survivors of a list entry: bit r set = ray r passed the cull (entry bit R-1-r is its key's sign)
+    static __device__ __forceinline__ unsigned survivors(unsigned e) { return (~__brev(e) >> (32 - R)) & SIGN_MASK; }
 
-    // Refine every listed survivor in FP64.  Entries are (k_local << R | sign bits), ray r at bit R-1-r.
-    // Each lane walks its own (ray, sphere) pairs, ONE refine call site: the warp runs
-    // max-over-lanes(#pairs) iterations instead of (#entries x R) sparsely populated calls.
-    __device__ __forceinline__ void flush(const DevScene& sc, const uint16_t* list, unsigned& ptr, int kbase) {
-        const int count = (int)(ptr - list_begin(list)) / (BLOCK * 2);
+    __device__ __forceinline__ unsigned key_bits(float fx, float fy, float fz, float r2i, int r) const {
+        float b = fmaf(fz, hz[r], fmaf(fy, hy[r], fx * hx[r]));
+        float nc = fmaf(-fz, fz, fmaf(-fy, fy, fmaf(-fx, fx, r2i)));
+        return __float_as_uint(fmaf(b, fminf(b, 0.f), nc));
+    }
+
+    // s[k] = (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its sweep
+    template <class Sink>
+    __device__ __forceinline__ void cull_static(const DevScene& sc, const float4* __restrict__ s, int count, int kbase,
+                                                uint16_t* list, unsigned& ptr, Sink& sink) {
+        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 2;
+        unsigned sa = smem_addr(s);
+        int k = 0;
+        for (; k + LIST_GUARD <= count; k += LIST_GUARD, sa += 16 * LIST_GUARD) {
+#pragma unroll
+            for (int u = 0; u < LIST_GUARD; ++u) {
+                const float4 S = lds128(sa + 16 * u);
+                unsigned acc = (unsigned)(k + u);
+                RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
+                push_entry(ptr, acc);
+            }
+            if (__any_sync(0xffffffffu, ptr > limit)) {   // warp-uniform: sinks may use warp collectives
+                sink.flush(*this, sc, list, list_count(list, ptr), kbase);
+                ptr = list_begin(list);
+            }
+        }
+        for (; k < count; ++k, sa += 16) {
+            const float4 S = lds128(sa);
+            unsigned acc = (unsigned)k;
+            RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
+            push_entry(ptr, acc);
+        }
+        sink.flush(*this, sc, list, list_count(list, ptr), kbase);
+        ptr = list_begin(list);
+    }
+
+    // Whole scene.  In tiled mode every thread of the CTA must call it (tile loads use __syncthreads).
+    // A preloaded scene is a single resident tile s_cull[0, n); a tiled scene streams tiles of `cap` spheres.
+    // Moving spheres are culled as the static bounding sphere of their swept volume (the FP64 refine
+    // evaluates the exact moving sphere), so there is ONE hot loop.
+    template <class Sink>
+    __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint16_t* list,
+                                        Sink& sink) {
+        pin();
+        unsigned ptr = list_begin(list);
+        for (int base = 0; base < sc.n; base += cap) {
+            int count = min(cap, sc.n - base);
+            if (!preloaded) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < count; i += BLOCK) s_cull[i] = __ldg(&sc.cull_a[base + i]);
+                __syncthreads();
+            }
+            cull_static(sc, s_cull, count, base, list, ptr, sink);
+        }
+    }
+
+    // Preloaded scene only: this warp tests slice `part` of `parts` of the sphere list (a short queue is
+    // spread over more warps by splitting the list; PairSink merges the results).
+    template <class Sink>
+    __device__ __forceinline__ void run_slice(const DevScene& sc, float4* s_cull, uint16_t* list, Sink& sink, int part,
+                                              int parts) {
+        pin();
+        unsigned ptr = list_begin(list);
+        const int s0 = slice_lo(sc.n, part, parts), s1 = slice_lo(sc.n, part + 1, parts);
+        cull_static(sc, s_cull + s0, s1 - s0, s0, list, ptr, sink);
+    }
+};
+
+__device__ __forceinline__ void preload_scene(const DevScene& sc, float4* s_cull, int block) {
+    for (int i = threadIdx.x; i < sc.n; i += block) s_cull[i] = __ldg(&sc.cull_a[i]);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// RefineSink: the owning thread refines its survivors in FP64 and keeps the closest hit in
+// registers.  Each lane walks its own (ray, sphere) pairs through ONE refine call site: the warp
+// runs max-over-lanes(#pairs) iterations instead of (#entries x R) sparsely populated calls.
+// ------------------------------------------------------------------------------------------
+template <int R, int BLOCK>
+struct RefineSink {
+    float dx[R], dy[R], dz[R];     // direction as given (un-normalised, util.clj:13-16)
+    double best_t[R];
+    int best_k[R], best_orig[R];
+    unsigned ncand;
+    double tmin, tmax;
+
+    __device__ __forceinline__ void begin() {
+        RT_FOR_R {
+            best_t[r] = CUDART_INF;
+            best_k[r] = -1;
+            best_orig[r] = 0x7fffffff;
+        }
+    }
+
+    __device__ __forceinline__ void flush(const Culler<R, BLOCK>& C, const DevScene& sc, const uint16_t* list, int count,
+                                          int kbase) {
         int i = 0;
         unsigned e = 0, pend = 0;   // pend: rays of the current entry still to refine (bit r = ray r)
         for (;;) {
             while (pend == 0 && i < count) {
                 e = list[i * BLOCK + threadIdx.x];
                 ++i;
-                pend = (~__brev(e) >> (32 - R)) & SIGN_MASK;   // bit R-1-r of e -> bit r, inverted: 1 = survivor
+                pend = Culler<R, BLOCK>::survivors(e);
             }
             if (pend == 0) break;
             const int r = __ffs(pend) - 1;
             pend &= pend - 1;
             const int k = kbase + (int)(e >> R);
-            float sox = ox[0], soy = oy[0], soz = oz[0], sdx = dx[0], sdy = dy[0], sdz = dz[0], stm = tm[0];
+            float sox = C.ox[0], soy = C.oy[0], soz = C.oz[0], sdx = dx[0], sdy = dy[0], sdz = dz[0], stm = C.tm[0];
 #pragma unroll
             for (int q = 1; q < R; ++q)
-                if (r == q) { sox = ox[q]; soy = oy[q]; soz = oz[q]; sdx = dx[q]; sdy = dy[q]; sdz = dz[q]; stm = tm[q]; }
+                if (r == q) { sox = C.ox[q]; soy = C.oy[q]; soz = C.oz[q]; sdx = dx[q]; sdy = dy[q]; sdz = dz[q]; stm = C.tm[q]; }
             const double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, sox, soy, soz, sdx, sdy, sdz,
                                               stm, tmin, tmax);
             ncand++;
@@ -131,113 +234,361 @@ struct Intersect {
                     }
             }
         }
-        ptr = list_begin(list);
     }
+};
 
-    __device__ __forceinline__ unsigned key_bits(float fx, float fy, float fz, float r2i, int r) const {
-        float b = fmaf(fz, hz[r], fmaf(fy, hy[r], fx * hx[r]));
-        float nc = fmaf(-fz, fz, fmaf(-fy, fy, fmaf(-fx, fx, r2i)));
-        return __float_as_uint(fmaf(b, fminf(b, 0.f), nc));
+// ------------------------------------------------------------------------------------------
+// Wavefront path tracer: one global queue of paths, one kernel per stage, each at its own occupancy.
+//
+//   queue record (3 x float4 per path, AoS so one thread moves a path with 3 LDG/STG.128):
+//       a = (ox, oy, oz, time)   b = (dx, dy, dz, pixel index)   c = (atten r, g, b, sample << 8 | depth)
+//   per bounce ("iteration"), in stream order, all counts on the device:
+//     wf_cull      persistent, 2 CTAs/SM: warps claim batches of 32*R queue entries (one atomic per
+//                  batch) and run the FP32 brute-force loop with the sphere list in shared memory; the
+//                  survivors are only EMITTED as (entry, sphere) pairs — per-lane counts are prefix-
+//                  summed with shuffles, one global atomic per warp flush claims the span.  No FP64, no
+//                  shading state: this kernel is the hot loop and nothing else.  A short queue switches
+//                  to 1 ray per thread and splits the sphere list across warps (the pairs merge later).
+//     wf_refine    one thread per pair: FP64 refine with the reference's exact formula, closest t per
+//                  entry merged with a 64-bit atomicMin on the double's bit pattern
+//     wf_tiebreak  pairs owning the minimum t race with atomicMin on (caller index, k): exact ties go
+//                  to the lower caller index, the Hitlist rule (hitable.clj:17-26)
+//     wf_shade     one thread per entry: scatter / emitted, accumulate, then compact: surviving paths
+//                  and fresh camera rays for finished lanes are appended to the next queue (warp ballot
+//                  + prefix popc + one atomic per warp, same for the (sample, pixel) work counter)
+//   The host enqueues iterations ahead and polls the queue count every few iterations.
+// ------------------------------------------------------------------------------------------
+struct WaveState {
+    unsigned qcount[2];            // entries in queue[i]
+    unsigned batch;                // next batch (wf_cull)
+    unsigned npairs;               // pairs emitted this iteration
+    unsigned pad[4];
+};
+
+struct WaveParams {
+    RenderParams base;
+    float4* queue[2];              // 3 * capacity float4 each
+    unsigned long long* best_t;    // [capacity] closest t (double bits)
+    unsigned long long* best_key;  // [capacity] (caller index + 1) << 32 | k
+    uint2* pairs;                  // [pair_cap] (entry, k)
+    double* pair_t;                // [pair_cap] refined t
+    WaveState* st;
+    int capacity;                  // multiple of 32
+    unsigned pair_cap;
+    int cur;                       // queue read by this iteration
+};
+
+constexpr unsigned long long BEST_T_INIT = 0x7ff0000000000000ull;   // +inf
+constexpr unsigned long long BEST_KEY_MISS = ~0ull;
+constexpr unsigned long long BEST_KEY_OVERFLOW = 0ull;              // survives every atomicMin
+constexpr unsigned PAIR_NULL = 0xffffffffu;
+
+// claim consecutive slots for the lanes whose predicate is set (one atomic per warp); returns this lane's slot
+__device__ __forceinline__ unsigned warp_claim(unsigned* counter, bool pred, unsigned lane) {
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    unsigned base = 0;
+    if (m) {
+        int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
     }
+    return base + __popc(m & ((1u << lane) - 1u));
+}
 
-    // static spheres: s[k] = (-cx, -cy, -cz, r2_inflated)
-    __device__ __forceinline__ void cull_static(const DevScene& sc, const float4* __restrict__ s, int count, int kbase,
-                                                uint16_t* list, unsigned& ptr) {
-        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 2;
-        int k = 0;
-        for (; k + LIST_GUARD <= count; k += LIST_GUARD) {
+// pull one (sample, pixel) work item for every lane with `want` (one atomic per warp); false when the work ran out
+__device__ __forceinline__ bool take_work(const RenderParams& P, bool want, unsigned lane, unsigned long long& w) {
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return false;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    w = base + __popc(m & ((1u << lane) - 1u));
+    return want && w < P.total_work;
+}
+
+// camera ray of work item w as a queue record
+__device__ __forceinline__ void make_path(const RenderParams& P, unsigned long long w, float4& a, float4& b, float4& c) {
+    const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
+    unsigned s_local = (unsigned)(w / pshard);
+    unsigned q = (unsigned)(w - (unsigned long long)s_local * pshard);
+    int row_local = (int)(q / (unsigned)P.nx);
+    int i = (int)(q - (unsigned)row_local * (unsigned)P.nx);
+    int j = P.row_offset + row_local * P.row_stride;
+    uint32_t pix = (uint32_t)j * (uint32_t)P.nx + (uint32_t)i;
+    uint32_t smp = (uint32_t)(P.sample_begin + (int)s_local);
+    float3 o, d;
+    float tmv;
+    generate_ray(P.cam, P.nx, P.ny, i, j, pix, smp, P.key, o, d, tmv, nullptr);
+    a = make_float4(o.x, o.y, o.z, tmv);
+    b = make_float4(d.x, d.y, d.z, __uint_as_float(pix));
+    c = make_float4(1.f, 1.f, 1.f, __uint_as_float((smp << 8) | (uint32_t)P.max_depth));
+}
+
+// first fill of queue 0: work items [0, count) map 1:1 to entries, no atomics
+__global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned count) {
+    const RenderParams& P = W.base;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        float4 a, b, c;
+        make_path(P, i, a, b, c);
+        float4* q = W.queue[0] + 3 * (size_t)i;
+        q[0] = a; q[1] = b; q[2] = c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        W.st->qcount[0] = count;
+        W.st->qcount[1] = 0;
+        W.st->batch = 0;
+        W.st->npairs = 0;
+        *P.work_counter = count;
+        atomicAdd(&P.counters[DC_SAMPLES], (unsigned long long)count);
+    }
+}
+
+// PairSink: survivors leave the cull kernel as (entry, sphere) pairs.  Called warp-converged: per-lane
+// pair counts are prefix-summed with shuffles and ONE global atomic claims the warp's span.
+// A warp whose span does not fit marks its entries OVERFLOW; wf_shade re-intersects those exactly.
+template <int R, int BLOCK>
+struct PairSink {
+    unsigned idx0;                 // queue entry of ray r = idx0 + 32 r
+    unsigned n;                    // live entries in the queue
+    const WaveParams* W;
+
+    __device__ __forceinline__ void flush(const Culler<R, BLOCK>&, const DevScene&, const uint16_t* list, int count,
+                                          int kbase) {
+        const unsigned lane = threadIdx.x & 31u;
+        unsigned np = 0;
+        for (int i = 0; i < count; ++i) np += __popc(Culler<R, BLOCK>::survivors(list[i * BLOCK + threadIdx.x]));
+        unsigned incl = np;
 #pragma unroll
-            for (int u = 0; u < LIST_GUARD; ++u) {
-                const float4 S = s[k + u];
-                unsigned acc = (unsigned)(k + u);
-                RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
-                push_entry(ptr, acc);
-            }
-            if (ptr > limit) flush(sc, list, ptr, kbase);
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
         }
-        for (; k < count; ++k) {
-            const float4 S = s[k];
-            unsigned acc = (unsigned)k;
-            RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
-            push_entry(ptr, acc);
-        }
-        flush(sc, list, ptr, kbase);
-    }
-
-    // moving spheres: -centre(time) = nA + time * nB; sa[k] = (nAx, nAy, nAz, r2_inflated), sb[k] = (nBx, nBy, nBz, 0)
-    __device__ __forceinline__ void cull_moving(const DevScene& sc, const float4* __restrict__ sa,
-                                                const float4* __restrict__ sb, int count, int kbase, uint16_t* list,
-                                                unsigned& ptr) {
-        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 2;
-        int k = 0;
-        for (; k + LIST_GUARD <= count; k += LIST_GUARD) {
-#pragma unroll
-            for (int u = 0; u < LIST_GUARD; ++u) {
-                const float4 A = sa[k + u];
-                const float4 B = sb[k + u];
-                unsigned acc = (unsigned)(k + u);
-                RT_FOR_R acc = __funnelshift_l(key_bits(fmaf(tm[r], B.x, ox[r] + A.x), fmaf(tm[r], B.y, oy[r] + A.y),
-                                                        fmaf(tm[r], B.z, oz[r] + A.z), A.w, r), acc, 1);
-                push_entry(ptr, acc);
-            }
-            if (ptr > limit) flush(sc, list, ptr, kbase);
-        }
-        for (; k < count; ++k) {
-            const float4 A = sa[k];
-            const float4 B = sb[k];
-            unsigned acc = (unsigned)k;
-            RT_FOR_R acc = __funnelshift_l(key_bits(fmaf(tm[r], B.x, ox[r] + A.x), fmaf(tm[r], B.y, oy[r] + A.y),
-                                                    fmaf(tm[r], B.z, oz[r] + A.z), A.w, r), acc, 1);
-            push_entry(ptr, acc);
-        }
-        flush(sc, list, ptr, kbase);
-    }
-
-    // Whole scene.  In tiled mode every thread of the CTA must call it (tile loads use __syncthreads).
-    // One copy of each hot loop: a preloaded scene is a single resident tile (statics at s_cull[0, ns),
-    // movers' A at s_cull + ns, B at s_cull + ns + nm); a tiled scene streams tiles of `cap` float4 slots.
-    __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint16_t* list) {
-        begin();
-        unsigned ptr = list_begin(list);
-        const int ns = sc.n_static, nm = sc.n_moving;
-        for (int base = 0; base < ns; base += cap) {
-            int count = min(cap, ns - base);
-            if (!preloaded) {
-                __syncthreads();
-                for (int i = threadIdx.x; i < count; i += BLOCK) s_cull[i] = __ldg(&sc.cull_a[base + i]);
-                __syncthreads();
-            }
-            cull_static(sc, s_cull, count, base, list, ptr);
-        }
-        const int half = cap / 2;
-        const float4* sa = preloaded ? s_cull + ns : s_cull;
-        const float4* sb = preloaded ? s_cull + ns + nm : s_cull + half;
-        const int step = preloaded ? max(nm, 1) : half;
-        for (int base = 0; base < nm; base += step) {
-            int count = min(step, nm - base);
-            if (!preloaded) {
-                __syncthreads();
-                for (int i = threadIdx.x; i < count; i += BLOCK) {
-                    s_cull[i] = __ldg(&sc.cull_a[ns + base + i]);
-                    s_cull[half + i] = __ldg(&sc.cull_b[base + i]);
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) return;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&W->st->npairs, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const bool fits = base + total <= W->pair_cap;
+        unsigned w = base + incl - np;
+        for (int i = 0; i < count; ++i) {
+            unsigned e = list[i * BLOCK + threadIdx.x];
+            unsigned pend = Culler<R, BLOCK>::survivors(e);
+            const unsigned k = (unsigned)kbase + (e >> R);
+            while (pend) {
+                const int r = __ffs(pend) - 1;
+                pend &= pend - 1;
+                const unsigned idx = idx0 + 32u * (unsigned)r;
+                if (fits) {
+                    W->pairs[w] = make_uint2(idx, k);
+                } else {
+                    if (w < W->pair_cap) W->pairs[w] = make_uint2(PAIR_NULL, 0u);
+                    if (idx < n) W->best_key[idx] = BEST_KEY_OVERFLOW;
                 }
-                __syncthreads();
+                ++w;
             }
-            cull_moving(sc, sa, sb, count, ns + base, list, ptr);
         }
     }
 };
 
-__device__ __forceinline__ void preload_scene(const DevScene& sc, float4* s_cull, int block) {
-    for (int i = threadIdx.x; i < sc.n; i += block) s_cull[i] = __ldg(&sc.cull_a[i]);
-    for (int i = threadIdx.x; i < sc.n_moving; i += block) s_cull[sc.n + i] = __ldg(&sc.cull_b[i]);
+template <int R, int BLOCK>
+__device__ __forceinline__ void wf_cull_batches(const WaveParams& W, unsigned n, int parts, float4* s_cull,
+                                                uint16_t* s_list) {
+    const RenderParams& P = W.base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
+    const unsigned n_batches = (n + 32 * R - 1) / (32 * R);
+    const unsigned n_items = n_batches * (unsigned)parts;          // (batch, sphere slice) work items
+    Culler<R, BLOCK> K;
+    PairSink<R, BLOCK> sink;
+    sink.n = n;
+    sink.W = &W;
+    unsigned item = blockIdx.x * warps + warp;                     // tiled scenes: CTA-uniform static order
+    const unsigned uniform_end = (n_items + warps - 1) / warps * warps;
+    for (;;) {
+        if (P.preloaded) {
+            unsigned b = 0;
+            if (lane == 0) b = atomicAdd(&W.st->batch, 1u);
+            item = __shfl_sync(0xffffffffu, b, 0);
+            if (item >= n_items) break;
+        } else {
+            if (item - warp >= uniform_end) break;
+        }
+        const unsigned batch = item / (unsigned)parts, part = item - batch * (unsigned)parts;
+        sink.idx0 = batch * (32 * R) + lane;     // ray r of this lane = entry idx0 + 32 r
+        RT_FOR_R {
+            unsigned idx = sink.idx0 + 32 * r;
+            if (idx < n && batch < n_batches) {
+                float4 a = W.queue[W.cur][3 * (size_t)idx], b = W.queue[W.cur][3 * (size_t)idx + 1];
+                K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w);
+                if (part == 0) {
+                    W.best_t[idx] = BEST_T_INIT;
+                    W.best_key[idx] = BEST_KEY_MISS;
+                }
+            } else {
+                K.kill(r);
+            }
+        }
+        if (parts > 1) K.run_slice(P.sc, s_cull, s_list, sink, (int)part, parts);
+        else           K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, sink);
+        item += gridDim.x * warps;
+    }
+}
+
+template <int R, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
+    const RenderParams& P = W.base;
+    extern __shared__ float4 smem_f4[];
+    float4* s_cull = smem_f4;
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
+    const unsigned n = W.st->qcount[W.cur];
+    if (n == 0) return;
+    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
+    // queue length decides the shape of the work: full batches of 4 rays per thread while every warp of the
+    // grid gets at least one; below that 1 ray per thread, and below THAT the sphere list is split too
+    const unsigned grid_warps = gridDim.x * (BLOCK / 32);
+    if (n >= grid_warps * 64u || !P.preloaded) {   // >= 2 one-ray batches per warp: the 4-ray loop's lower cost per test wins
+        wf_cull_batches<R, BLOCK>(W, n, 1, s_cull, s_list);
+    } else {
+        const unsigned b1 = (n + 31) / 32;
+        int parts = 1;
+        while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
+        wf_cull_batches<1, BLOCK>(W, n, parts, s_cull, s_list);
+    }
+}
+
+// one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved)
+__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) {
+    const RenderParams& P = W.base;
+    const unsigned n = W.st->qcount[W.cur];
+    const unsigned npairs = min(W.st->npairs, W.pair_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        W.st->batch = 0;               // wf_cull is done with it
+        W.st->qcount[W.cur ^ 1] = 0;   // wf_shade appends to it next
+        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const uint2 pr = W.pairs[i];
+        double t = CUDART_INF;
+        if (pr.x != PAIR_NULL && pr.x < n) {
+            const float4 a = W.queue[W.cur][3 * (size_t)pr.x], b = W.queue[W.cur][3 * (size_t)pr.x + 1];
+            t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, (int)pr.y, a.x, a.y, a.z, b.x, b.y, b.z,
+                                 a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
+            if (t < CUDART_INF) atomicMin(&W.best_t[pr.x], (unsigned long long)__double_as_longlong(t));
+        }
+        W.pair_t[i] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) {
+    const RenderParams& P = W.base;
+    const unsigned npairs = min(W.st->npairs, W.pair_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const double t = W.pair_t[i];
+        if (t < CUDART_INF) {
+            const uint2 pr = W.pairs[i];
+            if ((unsigned long long)__double_as_longlong(t) == W.best_t[pr.x]) {
+                unsigned long long key = (((unsigned long long)(__ldg(&P.sc.orig_id[pr.y]) + 1)) << 32) | pr.y;
+                atomicMin(&W.best_key[pr.x], key);
+            }
+        }
+    }
+}
+
+// exact closest hit of one ray by brute force in FP64 (only for entries whose pairs overflowed the pair buffer)
+__device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, float oy, float oz, float dx, float dy, float dz,
+                                               float tm, double* out_t, int* out_k) {
+    double best = CUDART_INF;
+    int bk = -1, borig = 0x7fffffff;
+    for (int k = 0; k < sc.n; ++k) {
+        double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, ox, oy, oz, dx, dy, dz, tm, 0.001,
+                                    (double)FLT_MAX);
+        if (t < CUDART_INF) {
+            int orig = __ldg(&sc.orig_id[k]);
+            if (t < best || (t == best && orig < borig)) { best = t; bk = k; borig = orig; }
+        }
+    }
+    *out_t = best;
+    *out_k = bk;
+}
+
+__global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
+    const RenderParams& P = W.base;
+    __shared__ unsigned s_ctr[DC_COUNT];
+    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned n = W.st->qcount[W.cur];
+    const unsigned lane = threadIdx.x & 31u;
+    const float4* qc = W.queue[W.cur];
+    float4* qn = W.queue[W.cur ^ 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) W.st->npairs = 0;   // refine and tie-break are done with it
+    unsigned n_samples = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned idx0 = blockIdx.x * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
+        const unsigned idx = idx0 + lane;
+        const bool have = idx < n;
+        bool cont = false;
+        float4 a, b, c;
+        if (have) {
+            a = qc[3 * (size_t)idx]; b = qc[3 * (size_t)idx + 1]; c = qc[3 * (size_t)idx + 2];
+            unsigned long long key = W.best_key[idx];
+            const uint32_t pix = __float_as_uint(b.w), sd = __float_as_uint(c.w);
+            const uint32_t smp = sd >> 8;
+            const int depth = (int)(sd & 255u);
+            int k = (int)(unsigned)key;
+            double td = __longlong_as_double((long long)W.best_t[idx]);
+            if (key == BEST_KEY_OVERFLOW) {
+                exact_closest_hit(P.sc, a.x, a.y, a.z, b.x, b.y, b.z, a.w, &td, &k);
+                key = k < 0 ? BEST_KEY_MISS : 1ull;
+            }
+            if (key == BEST_KEY_MISS) {                     // core.clj:40-41 miss -> accum (black)
+                atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
+            } else {
+                float3 o = f3(a.x, a.y, a.z), d = f3(b.x, b.y, b.z);
+                float3 att, em;
+                int reason = TERM_NONE;
+                ScatterRng rng{P.key, pix, smp, (uint32_t)(P.max_depth - depth + 1), nullptr, nullptr};
+                cont = shade_hit(P.sc, k, (float)td, o, d, a.w, depth > 0, rng, att, em, reason);
+                if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
+                    float* dst = P.sum + (size_t)pix * 3;
+                    atomicAdd(dst + 0, c.x * em.x);
+                    atomicAdd(dst + 1, c.y * em.y);
+                    atomicAdd(dst + 2, c.z * em.z);
+                }
+                if (cont) {
+                    a = make_float4(o.x, o.y, o.z, a.w);
+                    b = make_float4(d.x, d.y, d.z, b.w);
+                    c = make_float4(c.x * att.x, c.y * att.y, c.z * att.z, __uint_as_float((smp << 8) | (uint32_t)(depth - 1)));
+                } else {
+                    atomicAdd(&s_ctr[reason == TERM_LIGHT ? DC_TERM_LIGHT
+                                     : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
+                }
+            }
+        }
+        // a finished path frees its lane for the next (sample, pixel)
+        unsigned long long w;
+        if (take_work(P, have && !cont, lane, w)) {
+            make_path(P, w, a, b, c);
+            cont = true;
+            n_samples++;
+        }
+        unsigned slot = warp_claim(&W.st->qcount[W.cur ^ 1], cont, lane);
+        if (cont) {
+            float4* q = qn + 3 * (size_t)slot;
+            q[0] = a; q[1] = b; q[2] = c;
+        }
+    }
+    atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
+    __syncthreads();
+    if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent megakernel with path regeneration: every thread owns R path slots; a slot whose
-// path ended pulls the next (sample, pixel) work item (warp-aggregated atomic: ballot + prefix
-// popc) so the intersect phase always runs with full lanes until the work runs out.
+// Persistent megakernel with path regeneration (kept for comparison): every thread owns R path
+// slots; a slot whose path ended pulls the next (sample, pixel) work item (warp-aggregated atomic:
+// ballot + prefix popc) so the intersect loop runs with full lanes until the work runs out.
+// Warps run asynchronously through generate / intersect / refine / shade code.
 // ------------------------------------------------------------------------------------------
 template <int R, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P) {
@@ -249,16 +600,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
 
-    Intersect<R, BLOCK> I;
+    Culler<R, BLOCK> K;
+    RefineSink<R, BLOCK> I;
     I.tmin = 0.001;               // core.clj:25
     I.tmax = (double)FLT_MAX;     // Float/MAX_VALUE
     I.ncand = 0;
 
+    float ox[R], oy[R], oz[R], tmv[R];
     float ar[R], ag[R], ab[R];    // attenuation (core.clj:23 `atten`)
     uint32_t pix[R], smp[R];
     int depth[R];
     bool alive[R];
-    RT_FOR_R { alive[r] = false; I.kill(r); }
+    RT_FOR_R { alive[r] = false; ox[r] = oy[r] = oz[r] = tmv[r] = 0.f; I.dx[r] = 1.f; I.dy[r] = I.dz[r] = 0.f; }
     unsigned n_rays = 0, n_samples = 0;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
@@ -282,11 +635,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                     pix[r] = (uint32_t)j * (uint32_t)P.nx + (uint32_t)i;
                     smp[r] = (uint32_t)(P.sample_begin + (int)s_local);
                     float3 o, d;
-                    float tmv;
-                    generate_ray(P.cam, P.nx, P.ny, i, j, pix[r], smp[r], P.key, o, d, tmv, nullptr);
-                    I.ox[r] = o.x; I.oy[r] = o.y; I.oz[r] = o.z;
+                    generate_ray(P.cam, P.nx, P.ny, i, j, pix[r], smp[r], P.key, o, d, tmv[r], nullptr);
+                    ox[r] = o.x; oy[r] = o.y; oz[r] = o.z;
                     I.dx[r] = d.x; I.dy[r] = d.y; I.dz[r] = d.z;
-                    I.tm[r] = tmv;
                     ar[r] = ag[r] = ab[r] = 1.0f;
                     depth[r] = P.max_depth;
                     alive[r] = true;
@@ -305,23 +656,26 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
         }
 
         // ---- intersect ----------------------------------------------------------------------------
-        RT_FOR_R n_rays += alive[r] ? 1u : 0u;
-        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list);
+        RT_FOR_R {
+            if (alive[r]) { K.set_ray(r, ox[r], oy[r], oz[r], I.dx[r], I.dy[r], I.dz[r], tmv[r]); n_rays++; }
+            else K.kill(r);
+        }
+        I.begin();
+        K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, I);
 
         // ---- shade ------------------------------------------------------------------------------
         RT_FOR_R {
             if (alive[r]) {
                 if (I.best_k[r] < 0) {                       // core.clj:40-41 miss -> accum (black)
                     alive[r] = false;
-                    I.kill(r);
                     atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
                 } else {
-                    float3 o = f3(I.ox[r], I.oy[r], I.oz[r]), d = f3(I.dx[r], I.dy[r], I.dz[r]);
+                    float3 o = f3(ox[r], oy[r], oz[r]), d = f3(I.dx[r], I.dy[r], I.dz[r]);
                     float3 att, em;
                     int reason = TERM_NONE;
                     ScatterRng rng{P.key, pix[r], smp[r], (uint32_t)(P.max_depth - depth[r] + 1), nullptr, nullptr};
-                    bool cont = shade_hit(P.sc, I.best_k[r], (float)I.best_t[r], o, d, I.tm[r], depth[r] > 0, rng, att,
-                                          em, reason);
+                    bool cont = shade_hit(P.sc, I.best_k[r], (float)I.best_t[r], o, d, tmv[r], depth[r] > 0, rng, att, em,
+                                          reason);
                     if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
                         float* dst = P.sum + (size_t)pix[r] * 3;
                         atomicAdd(dst + 0, ar[r] * em.x);
@@ -330,12 +684,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                     }
                     if (cont) {
                         ar[r] *= att.x; ag[r] *= att.y; ab[r] *= att.z;     // core.clj:31
-                        I.ox[r] = o.x; I.oy[r] = o.y; I.oz[r] = o.z;
+                        ox[r] = o.x; oy[r] = o.y; oz[r] = o.z;
                         I.dx[r] = d.x; I.dy[r] = d.y; I.dz[r] = d.z;
                         depth[r]--;
                     } else {
                         alive[r] = false;
-                        I.kill(r);
                         atomicAdd(&s_ctr[reason == TERM_LIGHT ? DC_TERM_LIGHT
                                          : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
                     }
@@ -352,226 +705,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent wavefront path tracer: every CTA is an independent wavefront engine.
-//
-//   queue record (3 x float4 per path, AoS so one thread moves a path with 3 LDG/STG.128):
-//       a = (ox, oy, oz, time)   b = (dx, dy, dz, pixel index)   c = (atten r, g, b, sample << 8 | depth)
-//   Each CTA owns two ping-pong queues and a hit buffer of `capacity` entries in HBM/L2 and loops
-//       G  generate   fill the queue with camera rays; (sample, pixel) work items are claimed from
-//                     one global counter, one atomic per warp (ballot + popc prefix)
-//       A  intersect  warps claim batches of 32*R queue entries from a shared-memory counter, run the
-//                     brute-force cull + FP64 refine (4 rays per thread), write (t, k) per entry;
-//                     a nearly empty queue (tail) switches to the 1-ray-per-thread loop
-//       B  shade + regenerate + compact   one path per thread: shade the hit; surviving paths and
-//                     fresh camera rays are appended to the NEXT queue at positions claimed with
-//                     warp ballot + prefix popc + one shared-memory atomic per warp
-//   with __syncthreads between phases.  All warps of a CTA therefore execute the same small code
-//   region at the same time (an asynchronous megakernel loses ~45 % of its issue slots to
-//   instruction-cache misses, profiles/), intersect always runs on a dense compacted queue, and
-//   there is no chip-wide barrier (a grid.sync version spent 41 % of its warp-time waiting):
-//   two CTAs per SM hide each other's barrier and shade phases.
-// ------------------------------------------------------------------------------------------
-struct WaveParams {
-    RenderParams base;
-    float4* queue;             // gridDim.x * 2 * 3 * capacity float4
-    float2* hits;              // gridDim.x * capacity: (t as float, k as int bits)
-    int capacity;              // entries per CTA queue (multiple of 32)
-};
-
-// claim consecutive slots for the lanes whose predicate is set; returns this lane's slot
-__device__ __forceinline__ unsigned warp_claim_shared(unsigned* counter, bool pred, unsigned lane) {
-    unsigned m = __ballot_sync(0xffffffffu, pred);
-    unsigned base = 0;
-    if (m) {
-        int leader = __ffs(m) - 1;
-        if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-    }
-    return base + __popc(m & ((1u << lane) - 1u));
-}
-
-// pull one (sample, pixel) work item for every lane with `want`; returns false when the work ran out
-__device__ __forceinline__ bool fetch_and_generate(const RenderParams& P, bool want, unsigned lane, float4& a, float4& b,
-                                                   float4& c) {
-    unsigned m = __ballot_sync(0xffffffffu, want);
-    if (!m) return false;
-    int leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    unsigned long long w = base + __popc(m & ((1u << lane) - 1u));
-    if (!want || w >= P.total_work) return false;
-    const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
-    unsigned s_local = (unsigned)(w / pshard);
-    unsigned q = (unsigned)(w - (unsigned long long)s_local * pshard);
-    int row_local = (int)(q / (unsigned)P.nx);
-    int i = (int)(q - (unsigned)row_local * (unsigned)P.nx);
-    int j = P.row_offset + row_local * P.row_stride;
-    uint32_t pix = (uint32_t)j * (uint32_t)P.nx + (uint32_t)i;
-    uint32_t smp = (uint32_t)(P.sample_begin + (int)s_local);
-    float3 o, d;
-    float tmv;
-    generate_ray(P.cam, P.nx, P.ny, i, j, pix, smp, P.key, o, d, tmv, nullptr);
-    a = make_float4(o.x, o.y, o.z, tmv);
-    b = make_float4(d.x, d.y, d.z, __uint_as_float(pix));
-    c = make_float4(1.f, 1.f, 1.f, __uint_as_float((smp << 8) | (uint32_t)P.max_depth));
-    return true;
-}
-
-// phase A for one CTA: batches of 32*R entries claimed dynamically (preloaded scene) or walked in
-// CTA-uniform order (tiled scene: the tile loads inside Intersect::run need every thread)
-template <int R, int BLOCK>
-__device__ __forceinline__ void wave_intersect(const RenderParams& P, const float4* qc, float2* hits, unsigned n,
-                                               float4* s_cull, uint16_t* s_list, unsigned* s_batch, unsigned& n_cand) {
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
-    const unsigned n_batches = (n + 32 * R - 1) / (32 * R);
-    Intersect<R, BLOCK> I;
-    I.tmin = 0.001;               // core.clj:25
-    I.tmax = (double)FLT_MAX;     // Float/MAX_VALUE
-    I.ncand = 0;
-    unsigned batch = warp;
-    const unsigned uniform_end = (n_batches + warps - 1) / warps * warps;
-    for (;;) {
-        if (P.preloaded) {
-            unsigned b = 0;
-            if (lane == 0) b = atomicAdd(s_batch, 1u);
-            batch = __shfl_sync(0xffffffffu, b, 0);
-            if (batch >= n_batches) break;
-        } else {
-            if (batch >= uniform_end) break;
-        }
-        const unsigned wbase = batch * (32 * R) + lane;     // ray r of this lane = entry wbase + 32 r
-        RT_FOR_R {
-            unsigned idx = wbase + 32 * r;
-            if (idx < n) {
-                float4 a = qc[3 * (size_t)idx], b = qc[3 * (size_t)idx + 1];
-                I.ox[r] = a.x; I.oy[r] = a.y; I.oz[r] = a.z; I.tm[r] = a.w;
-                I.dx[r] = b.x; I.dy[r] = b.y; I.dz[r] = b.z;
-            } else {
-                I.kill(r);
-            }
-        }
-        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list);
-        RT_FOR_R {
-            unsigned idx = wbase + 32 * r;
-            if (idx < n) hits[idx] = make_float2((float)I.best_t[r], __int_as_float(I.best_k[r]));
-        }
-        batch += warps;
-    }
-    n_cand += I.ncand;
-}
-
-template <int R, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) wave_kernel(const WaveParams W) {
-    const RenderParams& P = W.base;
-    extern __shared__ float4 smem_f4[];
-    float4* s_cull = smem_f4;
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
-    __shared__ unsigned s_ctr[DC_COUNT];
-    __shared__ unsigned s_qcount[2];
-    __shared__ unsigned s_batch;
-    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
-    if (threadIdx.x < 2) s_qcount[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_batch = 0;
-    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
-    __syncthreads();
-
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned cap = (unsigned)W.capacity;
-    float4* q0 = W.queue + (size_t)blockIdx.x * 2 * 3 * cap;
-    float4* queue[2] = {q0, q0 + 3 * (size_t)cap};
-    float2* hits = W.hits + (size_t)blockIdx.x * cap;
-    unsigned n_rays = 0, n_samples = 0, n_cand = 0;
-
-    // ---- phase G: fill queue 0 -------------------------------------------------------------------
-    for (unsigned idx = threadIdx.x; idx < cap; idx += BLOCK) {
-        float4 a, b, c;
-        bool ok = fetch_and_generate(P, true, lane, a, b, c);
-        unsigned slot = warp_claim_shared(&s_qcount[0], ok, lane);
-        if (ok) {
-            float4* q = queue[0] + 3 * (size_t)slot;
-            q[0] = a; q[1] = b; q[2] = c;
-            n_samples++;
-        }
-        if (!__any_sync(0xffffffffu, ok)) break;          // work ran out
-    }
-    __syncthreads();
-
-    int cur = 0;
-    for (;;) {
-        const unsigned n = s_qcount[cur];
-        if (n == 0) break;
-        const float4* qc = queue[cur];
-        if (threadIdx.x == 0) n_rays += n;
-
-        // ---- phase A: intersect ----------------------------------------------------------------------
-        if (n > BLOCK) wave_intersect<R, BLOCK>(P, qc, hits, n, s_cull, s_list, &s_batch, n_cand);
-        else           wave_intersect<1, BLOCK>(P, qc, hits, n, s_cull, s_list, &s_batch, n_cand);   // tail: 1 ray/thread
-        __syncthreads();
-        if (threadIdx.x == 0) { s_batch = 0; s_qcount[cur] = 0; }
-
-        // ---- phase B: shade, compact survivors into the next queue, regenerate -------------------
-        float4* qn = queue[cur ^ 1];
-        for (unsigned idx0 = threadIdx.x - lane; idx0 < n; idx0 += BLOCK) {   // warp-uniform trip count
-            const unsigned idx = idx0 + lane;
-            bool have = idx < n;
-            bool cont = false;
-            float4 a, b, c;
-            if (have) {
-                a = qc[3 * (size_t)idx]; b = qc[3 * (size_t)idx + 1]; c = qc[3 * (size_t)idx + 2];
-                float2 h = hits[idx];
-                int k = __float_as_int(h.y);
-                uint32_t pix = __float_as_uint(b.w), sd = __float_as_uint(c.w);
-                uint32_t smp = sd >> 8;
-                int depth = (int)(sd & 255u);
-                if (k < 0) {                                        // core.clj:40-41 miss -> accum (black)
-                    atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
-                } else {
-                    float3 o = f3(a.x, a.y, a.z), d = f3(b.x, b.y, b.z);
-                    float3 att, em;
-                    int reason = TERM_NONE;
-                    ScatterRng rng{P.key, pix, smp, (uint32_t)(P.max_depth - depth + 1), nullptr, nullptr};
-                    cont = shade_hit(P.sc, k, h.x, o, d, a.w, depth > 0, rng, att, em, reason);
-                    if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
-                        float* dst = P.sum + (size_t)pix * 3;
-                        atomicAdd(dst + 0, c.x * em.x);
-                        atomicAdd(dst + 1, c.y * em.y);
-                        atomicAdd(dst + 2, c.z * em.z);
-                    }
-                    if (cont) {
-                        a = make_float4(o.x, o.y, o.z, a.w);
-                        b = make_float4(d.x, d.y, d.z, b.w);
-                        c = make_float4(c.x * att.x, c.y * att.y, c.z * att.z, __uint_as_float((smp << 8) | (uint32_t)(depth - 1)));
-                    } else {
-                        atomicAdd(&s_ctr[reason == TERM_LIGHT ? DC_TERM_LIGHT
-                                         : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
-                    }
-                }
-            }
-            // a finished path frees its lane for the next (sample, pixel)
-            if (fetch_and_generate(P, have && !cont, lane, a, b, c)) {
-                cont = true;
-                n_samples++;
-            }
-            unsigned slot = warp_claim_shared(&s_qcount[cur ^ 1], cont, lane);
-            if (cont) {
-                float4* q = qn + 3 * (size_t)slot;
-                q[0] = a; q[1] = b; q[2] = c;
-            }
-        }
-        __syncthreads();
-        cur ^= 1;
-    }
-
-    atomicAdd(&s_ctr[DC_RAYS], n_rays);
-    atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
-    atomicAdd(&s_ctr[DC_CANDIDATES], n_cand);
-    __syncthreads();
-    if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
-}
-
-// ------------------------------------------------------------------------------------------
-// rt_trace_primary: closest hit of n caller-given rays (same Intersect as the renderer)
+// rt_trace_primary: closest hit of n caller-given rays (same Culler + FP64 refine as the renderer)
 // ------------------------------------------------------------------------------------------
 struct TraceParams {
     DevScene sc;
@@ -592,7 +726,8 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
-    Intersect<R, BLOCK> I;
+    Culler<R, BLOCK> K;
+    RefineSink<R, BLOCK> I;
     I.tmin = P.tmin;
     I.tmax = P.tmax;
     I.ncand = 0;
@@ -600,14 +735,16 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
         RT_FOR_R {
             long long idx = base + (long long)r * BLOCK + threadIdx.x;
             if (idx < P.n) {
-                I.ox[r] = P.origins[3 * idx]; I.oy[r] = P.origins[3 * idx + 1]; I.oz[r] = P.origins[3 * idx + 2];
                 I.dx[r] = P.dirs[3 * idx]; I.dy[r] = P.dirs[3 * idx + 1]; I.dz[r] = P.dirs[3 * idx + 2];
-                I.tm[r] = P.times ? P.times[idx] : 0.f;
+                K.set_ray(r, P.origins[3 * idx], P.origins[3 * idx + 1], P.origins[3 * idx + 2], I.dx[r], I.dy[r], I.dz[r],
+                          P.times ? P.times[idx] : 0.f);
             } else {
-                I.kill(r);
+                I.dx[r] = 1.f; I.dy[r] = 0.f; I.dz[r] = 0.f;
+                K.kill(r);
             }
         }
-        I.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list);
+        I.begin();
+        K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, I);
         RT_FOR_R {
             long long idx = base + (long long)r * BLOCK + threadIdx.x;
             if (idx < P.n) {
