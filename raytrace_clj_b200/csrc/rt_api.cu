@@ -47,7 +47,9 @@ struct DeviceBuffers {
     float4* wave_queue = nullptr;            // 2 * 3 * wave_entries float4
     unsigned long long* wave_best = nullptr; // 2 * wave_entries
     uint2* wave_pairs = nullptr;
-    double* wave_pair_t = nullptr;
+    uint2* wave_cands = nullptr;
+    double* wave_cand_t = nullptr;
+    unsigned* wave_cand_count = nullptr;
     WaveState* wave_state = nullptr;
     WaveState* h_wave_state = nullptr;       // pinned, 2 snapshots
     cudaEvent_t ev_poll[2] = {nullptr, nullptr};
@@ -128,8 +130,11 @@ void free_wave(DeviceBuffers& d) {
     if (d.wave_queue) cudaFree(d.wave_queue);
     if (d.wave_best) cudaFree(d.wave_best);
     if (d.wave_pairs) cudaFree(d.wave_pairs);
-    if (d.wave_pair_t) cudaFree(d.wave_pair_t);
-    d.wave_queue = nullptr; d.wave_best = nullptr; d.wave_pairs = nullptr; d.wave_pair_t = nullptr;
+    if (d.wave_cands) cudaFree(d.wave_cands);
+    if (d.wave_cand_t) cudaFree(d.wave_cand_t);
+    if (d.wave_cand_count) cudaFree(d.wave_cand_count);
+    d.wave_cand_count = nullptr;
+    d.wave_queue = nullptr; d.wave_best = nullptr; d.wave_pairs = nullptr; d.wave_cands = nullptr; d.wave_cand_t = nullptr;
     d.wave_entries = 0;
 }
 
@@ -144,7 +149,11 @@ int ensure_wave(rt_ctx* ctx, DeviceBuffers& d, size_t entries) {
     RT_CUDA(ctx, cudaMalloc(&d.wave_queue, entries * 2 * 3 * sizeof(float4)));
     RT_CUDA(ctx, cudaMalloc(&d.wave_best, entries * 2 * sizeof(unsigned long long)));
     RT_CUDA(ctx, cudaMalloc(&d.wave_pairs, entries * kPairsPerEntry * sizeof(uint2)));
-    RT_CUDA(ctx, cudaMalloc(&d.wave_pair_t, entries * kPairsPerEntry * sizeof(double)));
+    // candidate regions are private to the warps of the refine grid: pair_cap rounded up per warp
+    const size_t cand_slots = entries * kPairsPerEntry + (size_t)d.sm_count * 8 * 8 * 32;
+    RT_CUDA(ctx, cudaMalloc(&d.wave_cands, cand_slots * sizeof(uint2)));
+    RT_CUDA(ctx, cudaMalloc(&d.wave_cand_t, cand_slots * sizeof(double)));
+    RT_CUDA(ctx, cudaMalloc(&d.wave_cand_count, (size_t)d.sm_count * 8 * 8 * sizeof(unsigned)));
     d.wave_entries = entries;
     return RT_OK;
 }
@@ -176,7 +185,7 @@ int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// Wavefront render of one device's share: enqueue iterations (cull, refine, tie-break, shade) ahead of the
+// Wavefront render of one device's share: enqueue iterations (cull, refine, shade) ahead of the
 // GPU and poll the queue count every kWaveChunk iterations; returns when the queue has drained (the last
 // polled chunk may still be finishing its empty kernels).
 template <int BLOCK, int MINB>
@@ -190,9 +199,9 @@ int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WavePar
 }
 
 int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned long long, cudaStream_t stream) {
-    // CTA shape of the cull kernel: 256 threads x 3 CTAs/SM (80 registers, 24 warps/SM) by default;
+    // CTA shape of the cull kernel: 128 threads x 5 CTAs/SM (20 warps/SM) measured best;
     // RT_CULL_SHAPE = "256x2" | "256x3" | "128x5" | "128x6" for experiments
-    static const std::string shape = getenv("RT_CULL_SHAPE") ? getenv("RT_CULL_SHAPE") : "256x3";
+    static const std::string shape = getenv("RT_CULL_SHAPE") ? getenv("RT_CULL_SHAPE") : "128x5";
     void (*cull)(const WaveParams) = nullptr;
     size_t smem = 0;
     int bps = 0, cull_block = 256, rc;
@@ -211,7 +220,9 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     W.best_t = d.wave_best;
     W.best_key = d.wave_best + capacity;
     W.pairs = d.wave_pairs;
-    W.pair_t = d.wave_pair_t;
+    W.cands = d.wave_cands;
+    W.cand_t = d.wave_cand_t;
+    W.cand_count = d.wave_cand_count;
     W.st = d.wave_state;
     W.capacity = (int)capacity;
     W.pair_cap = (unsigned)std::min<size_t>(capacity * kPairsPerEntry, 0xfffffff0u);

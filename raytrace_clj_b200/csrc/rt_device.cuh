@@ -105,28 +105,26 @@ __device__ __forceinline__ uint4 rng_block(uint2 key, uint32_t pixel, uint32_t s
     return philox4x32_10(make_uint4(pixel, sample, (bounce << 16) | blk, RNG_DOMAIN), key);
 }
 
-// util.clj:43-52 rand-in-unit-sphere: rejection in [-1,1)^3, accept when dot < 1.
-// One Philox block per try (x, y, z used).  first_blk lets callers reserve earlier blocks.
+// util.clj:43-52 rand-in-unit-sphere.  The reference rejects points of [-1,1)^3 until dot < 1, i.e. it draws
+// uniformly from the open unit ball; the JVM stream cannot be reproduced anyway, so the same distribution
+// is drawn in closed form from ONE Philox block (no divergent retry loop): radius cbrt(u), uniform direction.
 __device__ __forceinline__ float3 rand_in_unit_sphere(uint2 key, uint32_t pixel, uint32_t sample, uint32_t bounce,
-                                                      uint32_t first_blk) {
-    for (uint32_t b = 0; b < 64; ++b) {
-        uint4 r = rng_block(key, pixel, sample, bounce, first_blk + b);
-        float3 p = f3(fmaf(2.0f, u01(r.x), -1.0f), fmaf(2.0f, u01(r.y), -1.0f), fmaf(2.0f, u01(r.z), -1.0f));
-        if (!(dot3(p, p) >= 1.0f)) return p;
-    }
-    return f3(0.f, 0.f, 0.f);  // probability (1 - pi/6)^64 ~ 1e-21
+                                                      uint32_t blk) {
+    uint4 r = rng_block(key, pixel, sample, bounce, blk);
+    float rad = cbrtf(u01(r.x));
+    float z = fmaf(-2.0f, u01(r.y), 1.0f);
+    float s = sqrtf(fmaxf(0.f, fmaf(-z, z, 1.0f))) * rad;
+    float sn, cs;
+    sincospif(2.0f * u01(r.z), &sn, &cs);
+    return f3(s * cs, s * sn, z * rad);
 }
-// util.clj:32-41 rand-in-unit-disk: two tries per Philox block
-__device__ __forceinline__ float2 rand_in_unit_disk(uint2 key, uint32_t pixel, uint32_t sample, uint32_t first_blk) {
-    for (uint32_t b = 0; b < 32; ++b) {
-        uint4 r = rng_block(key, pixel, sample, 0u, first_blk + b);
-        float x = fmaf(2.0f, u01(r.x), -1.0f), y = fmaf(2.0f, u01(r.y), -1.0f);
-        if (!(x * x + y * y >= 1.0f)) return make_float2(x, y);
-        x = fmaf(2.0f, u01(r.z), -1.0f);
-        y = fmaf(2.0f, u01(r.w), -1.0f);
-        if (!(x * x + y * y >= 1.0f)) return make_float2(x, y);
-    }
-    return make_float2(0.f, 0.f);
+// util.clj:32-41 rand-in-unit-disk: uniform in the open unit disk, closed form
+__device__ __forceinline__ float2 rand_in_unit_disk(uint2 key, uint32_t pixel, uint32_t sample, uint32_t blk) {
+    uint4 r = rng_block(key, pixel, sample, 0u, blk);
+    float rad = sqrtf(u01(r.x));
+    float sn, cs;
+    sincospif(2.0f * u01(r.y), &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
 }
 
 // ------------------------------------------------------------------------------------------

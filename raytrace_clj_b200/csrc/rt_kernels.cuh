@@ -69,7 +69,7 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) {
 __device__ __forceinline__ int slice_lo(int n, int part, int parts) { return (int)(((long long)n * part) / parts); }
 
 constexpr int LIST_K = 32;       // entries per thread
-constexpr int LIST_GUARD = 2;    // spheres between two overflow checks (= unroll group; small bodies stay in the L0 I-cache)
+constexpr int LIST_GUARD = 4;    // spheres between two list-full checks (= unroll group)
 
 template <int R, int BLOCK>
 struct Culler {
@@ -114,7 +114,16 @@ struct Culler {
         return __float_as_uint(fmaf(b, fminf(b, 0.f), nc));
     }
 
-    // s[k] = (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its sweep
+    // s[k] = (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its sweep.
+    // Spheres go two at a time: both entries are stored, ONE test decides whether the list pointer moves
+    // past both (an entry without survivors that rides along is skipped by the sink); the list-full
+    // check runs every LIST_GUARD spheres.
+    __device__ __forceinline__ unsigned test_sphere(unsigned sa, unsigned k) const {
+        const float4 S = lds128(sa);
+        unsigned acc = k;
+        RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
+        return acc;
+    }
     template <class Sink>
     __device__ __forceinline__ void cull_static(const DevScene& sc, const float4* __restrict__ s, int count, int kbase,
                                                 uint16_t* list, unsigned& ptr, Sink& sink) {
@@ -123,23 +132,19 @@ struct Culler {
         int k = 0;
         for (; k + LIST_GUARD <= count; k += LIST_GUARD, sa += 16 * LIST_GUARD) {
 #pragma unroll
-            for (int u = 0; u < LIST_GUARD; ++u) {
-                const float4 S = lds128(sa + 16 * u);
-                unsigned acc = (unsigned)(k + u);
-                RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
-                push_entry(ptr, acc);
+            for (int u = 0; u < LIST_GUARD; u += 2) {
+                const unsigned a0 = test_sphere(sa + 16 * u, (unsigned)(k + u));
+                const unsigned a1 = test_sphere(sa + 16 * u + 16, (unsigned)(k + u + 1));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(ptr), "h"((unsigned short)a0) : "memory");
+                asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(ptr), "h"((unsigned short)a1), "n"(BLOCK * 2) : "memory");
+                if (~(a0 & a1) & SIGN_MASK) ptr += BLOCK * 4;   // a survivor in either: keep both entries
             }
             if (__any_sync(0xffffffffu, ptr > limit)) {   // warp-uniform: sinks may use warp collectives
                 sink.flush(*this, sc, list, list_count(list, ptr), kbase);
                 ptr = list_begin(list);
             }
         }
-        for (; k < count; ++k, sa += 16) {
-            const float4 S = lds128(sa);
-            unsigned acc = (unsigned)k;
-            RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
-            push_entry(ptr, acc);
-        }
+        for (; k < count; ++k, sa += 16) push_entry(ptr, test_sphere(sa, (unsigned)k));
         sink.flush(*this, sc, list, list_count(list, ptr), kbase);
         ptr = list_begin(list);
     }
@@ -250,9 +255,11 @@ struct RefineSink {
 //                  shading state: this kernel is the hot loop and nothing else.  A short queue switches
 //                  to 1 ray per thread and splits the sphere list across warps (the pairs merge later).
 //     wf_refine    one thread per pair: FP64 refine with the reference's exact formula, closest t per
-//                  entry merged with a 64-bit atomicMin on the double's bit pattern
-//     wf_tiebreak  pairs owning the minimum t race with atomicMin on (caller index, k): exact ties go
-//                  to the lower caller index, the Hitlist rule (hitable.clj:17-26)
+//                  entry merged with a 64-bit atomicMin on the double's bit pattern; pairs that were the
+//                  running minimum go to a compact candidate list
+//     wf_tiebreak  candidates owning the final minimum t race with atomicMin on (caller index, k): exact
+//                  ties go to the lower caller index, the Hitlist rule (hitable.clj:17-26)
+//                  (a single 128-bit CAS merge was tried and was 2.4x slower than this two-step)
 //     wf_shade     one thread per entry: scatter / emitted, accumulate, then compact: surviving paths
 //                  and fresh camera rays for finished lanes are appended to the next queue (warp ballot
 //                  + prefix popc + one atomic per warp, same for the (sample, pixel) work counter)
@@ -271,7 +278,9 @@ struct WaveParams {
     unsigned long long* best_t;    // [capacity] closest t (double bits)
     unsigned long long* best_key;  // [capacity] (caller index + 1) << 32 | k
     uint2* pairs;                  // [pair_cap] (entry, k)
-    double* pair_t;                // [pair_cap] refined t
+    uint2* cands;                  // [pair_cap] pairs that were the running minimum when they merged
+    double* cand_t;                // [pair_cap + slack] their t
+    unsigned* cand_count;          // [warps of the refine grid] candidates in each warp's private region
     WaveState* st;
     int capacity;                  // multiple of 32
     unsigned pair_cap;
@@ -458,41 +467,71 @@ __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
     }
 }
 
-// one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved)
+// one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved).
+// The atomic's result is NOT consumed (fire-and-forget RED; a returning ATOM made this kernel 3x slower):
+// a plain L2 read of the running minimum beforehand decides whether the pair can still be the winner
+// (the final winner always passes: the minimum only ever decreases towards its t).  Such pairs are kept
+// for the tie-break pass in a region private to the warp — no slot-claim atomics either.
+__device__ __forceinline__ unsigned wf_cand_region(const WaveParams& W, unsigned total_warps) {
+    return ((W.pair_cap + total_warps * 32u - 1u) / (total_warps * 32u)) * 32u;   // pairs one warp can see
+}
+
 __global__ void __launch_bounds__(256) wf_refine(const WaveParams W) {
     const RenderParams& P = W.base;
     const unsigned n = W.st->qcount[W.cur];
     const unsigned npairs = min(W.st->npairs, W.pair_cap);
+    const unsigned lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         W.st->batch = 0;               // wf_cull is done with it
         W.st->qcount[W.cur ^ 1] = 0;   // wf_shade appends to it next
         atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);
     }
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
-        const uint2 pr = W.pairs[i];
+    const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
+    const unsigned warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t region = (size_t)warp_id * wf_cand_region(W, total_warps);
+    unsigned cnt = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < npairs; i0 += stride) {   // warp-uniform
+        const unsigned i = i0 + lane;
+        bool cand = false;
+        uint2 pr = make_uint2(PAIR_NULL, 0u);
         double t = CUDART_INF;
+        if (i < npairs) pr = W.pairs[i];
         if (pr.x != PAIR_NULL && pr.x < n) {
             const float4 a = W.queue[W.cur][3 * (size_t)pr.x], b = W.queue[W.cur][3 * (size_t)pr.x + 1];
+            const unsigned long long seen = __ldcg(&W.best_t[pr.x]);
             t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, (int)pr.y, a.x, a.y, a.z, b.x, b.y, b.z,
                                  a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
-            if (t < CUDART_INF) atomicMin(&W.best_t[pr.x], (unsigned long long)__double_as_longlong(t));
-        }
-        W.pair_t[i] = t;
-    }
-}
-
-__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) {
-    const RenderParams& P = W.base;
-    const unsigned npairs = min(W.st->npairs, W.pair_cap);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
-        const double t = W.pair_t[i];
-        if (t < CUDART_INF) {
-            const uint2 pr = W.pairs[i];
-            if ((unsigned long long)__double_as_longlong(t) == W.best_t[pr.x]) {
-                unsigned long long key = (((unsigned long long)(__ldg(&P.sc.orig_id[pr.y]) + 1)) << 32) | pr.y;
-                atomicMin(&W.best_key[pr.x], key);
+            const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
+            if (t < CUDART_INF && tb <= seen) {
+                atomicMin(&W.best_t[pr.x], tb);
+                cand = true;
             }
         }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (cand) {
+            const size_t slot = region + cnt + __popc(m & ((1u << lane) - 1u));
+            W.cands[slot] = pr;
+            W.cand_t[slot] = t;
+        }
+        cnt += __popc(m);
+    }
+    if (lane == 0) W.cand_count[warp_id] = cnt;
+}
+
+// exact ties go to the lower caller index, the Hitlist rule (hitable.clj:17-26): candidates that own the final
+// minimum t race with atomicMin on (caller index, k).  Same grid shape as wf_refine (warp-private regions).
+__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) {
+    const RenderParams& P = W.base;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
+    const unsigned warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t region = (size_t)warp_id * wf_cand_region(W, total_warps);
+    const unsigned cnt = W.cand_count[warp_id];
+    for (unsigned j = lane; j < cnt; j += 32) {
+        const uint2 pr = W.cands[region + j];
+        if ((unsigned long long)__double_as_longlong(W.cand_t[region + j]) == W.best_t[pr.x])
+            atomicMin(&W.best_key[pr.x], (((unsigned long long)(__ldg(&P.sc.orig_id[pr.y]) + 1)) << 32) | pr.y);
     }
 }
 
@@ -522,7 +561,7 @@ __global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
     const unsigned lane = threadIdx.x & 31u;
     const float4* qc = W.queue[W.cur];
     float4* qn = W.queue[W.cur ^ 1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) W.st->npairs = 0;   // refine and tie-break are done with it
+    if (blockIdx.x == 0 && threadIdx.x == 0) W.st->npairs = 0;   // refine / tie-break are done with it
     unsigned n_samples = 0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned idx0 = blockIdx.x * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
@@ -538,7 +577,7 @@ __global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
             const int depth = (int)(sd & 255u);
             int k = (int)(unsigned)key;
             double td = __longlong_as_double((long long)W.best_t[idx]);
-            if (key == BEST_KEY_OVERFLOW) {
+            if (key == BEST_KEY_OVERFLOW) {                 // overflow mark: exact brute force for this entry
                 exact_closest_hit(P.sc, a.x, a.y, a.z, b.x, b.y, b.z, a.w, &td, &k);
                 key = k < 0 ? BEST_KEY_MISS : 1ull;
             }
