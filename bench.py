@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("RT_VARIANT", "0")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("RT_VARIANT", "1")), help="1 wavefront (default), 0 megakernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
     args = ap.parse_args()
@@ -247,6 +247,7 @@ def main():
     my_ms = sum(a.elapsed_time(b) for a, b in ev)
     my_kernel_ms = sum(a.elapsed_time(b) for a, b in kev)
     ctr = r.counters()
+    launches = ctr["kernel_launches"]
     t = torch.tensor([my_ms, my_kernel_ms], device=dev, dtype=torch.float64)
     cnt = torch.tensor([ctr["samples"], ctr["rays"], ctr["sphere_tests"], ctr["candidates"]], device=dev, dtype=torch.float64)
     if world > 1:
@@ -288,8 +289,22 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = (nx * ny * spp * world * e2e_steps) / float(te[0])
 
+    # ---- stage shares: one extra (untimed) step with per-stage CUDA events (rank 0, wavefront only) ------
+    stage = None
+    if rank == 0 and args.variant == 1:
+        r.reset_counters()
+        r.set_profile(True)
+        d_sum.zero_()
+        r.render_accumulate_device(nx, ny, rank * spp, spp, d_sum.data_ptr(), max_depth=depth, seed=1,
+                                   variant=args.variant, stream=stream.cuda_stream, sync=True)
+        r.set_profile(False)
+        pc = r.counters()
+        stage = {k: pc[k + "_ns"] * 1e-6 for k in ("cull", "refine", "tiebreak", "shade")}
+        stage["tests"] = pc["sphere_tests"]
+    barrier()
+
     if rank == 0:
-        achieved_tflops = FLOP_PER_TEST * (tests / world) / (kernel_ms * 1e-3) / 1e12   # per GPU, dominant kernel
+        achieved_tflops = FLOP_PER_TEST * (tests / world) / (kernel_ms * 1e-3) / 1e12   # per GPU, whole render step
         peak_measured = max(fp32_peak)
         line = {
             "metric": "samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -307,7 +322,7 @@ def main():
             "rays_per_sample": rays / samples,
             "cull_survivors_per_ray": cands / rays,
             "kernel_ms_per_step": kernel_ms / args.steps,
-            "gpu_launches": args.steps * (2 if world == 1 else 2),   # mega_kernel + resolve_kernel per step (rank 0)
+            "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tflops, "peak": peak_measured, "unit": "TFLOP/s",
@@ -317,7 +332,15 @@ def main():
                 "peak_ffma_tflops": fp32_peak[0], "peak_ffma2_tflops": fp32_peak[1],
                 "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
                 "flop_per_test": FLOP_PER_TEST, "traffic": None,
-                "note": "non-tensor FP32 pipe; HBM is not the bound (scene in shared memory)",
+                "note": "non-tensor FP32 pipe; HBM is not the bound (scene in shared memory). `achieved` divides the "
+                        "17-flop tests by the time of the WHOLE render step (cull + refine + tie-break + shade kernels)",
+                "dominant_kernel": None if not stage else {
+                    "name": "wf_cull", "ms_per_step": stage["cull"],
+                    "achieved": FLOP_PER_TEST * stage["tests"] / (stage["cull"] * 1e-3) / 1e12,
+                    "frac": FLOP_PER_TEST * stage["tests"] / (stage["cull"] * 1e-3) / 1e12 / peak_measured,
+                    "share_of_step": stage["cull"] / max(1e-9, sum(stage[k] for k in ("cull", "refine", "tiebreak", "shade"))),
+                    "other_stages_ms": {k: stage[k] for k in ("refine", "tiebreak", "shade")},
+                },
             },
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": scene_bytes(flat),
                     "d2h_bytes_per_step": nx * ny * 3, "steps": e2e_steps},

@@ -110,6 +110,11 @@ enum {
     RT_CTR_TERM_MISS,        /* paths ended by a miss (core.clj:40-41)                            */
     RT_CTR_KERNEL_NS,        /* device time of the last render's kernels, ns (CUDA events)        */
     RT_CTR_CANDIDATES,       /* (ray, sphere) pairs that passed the FP32 cull and were refined    */
+    RT_CTR_KERNEL_LAUNCHES,  /* CUDA kernels launched by this context (render + resolve + diagnostics) */
+    RT_CTR_CULL_NS,          /* with rt_set_profile(ctx, 1): device time per wavefront stage, ns  */
+    RT_CTR_REFINE_NS,
+    RT_CTR_TIEBREAK_NS,
+    RT_CTR_SHADE_NS,
     RT_CTR_COUNT = 16
 };
 
@@ -180,6 +185,10 @@ int rt_shade_batch(rt_ctx* ctx, int n, const float* origins, const float* dirs, 
 /* FP32 FFMA-chain peak of device 0 of the context, in TFLOP/s (2 flop per FFMA), plus the
  * packed FFMA2 figure; used as the measured roofline denominator by bench.py.                  */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* out_ffma_tflops, double* out_ffma2_tflops);
+
+/* Stage profiling: when on, the wavefront variant brackets every stage kernel with CUDA events and
+ * accumulates RT_CTR_{CULL,REFINE,TIEBREAK,SHADE}_NS (adds a little launch overhead; off by default). */
+int rt_set_profile(rt_ctx* ctx, int on);
 
 /* Counters accumulate over renders until reset. */
 int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]);

@@ -8,6 +8,6 @@ Package layout (only what the path needs):
              host-side mirror of the reference's front end (records, scene builders, CLI)
 The importable name uses an underscore (a hyphen is not a valid Python identifier).
 """
-from . import camera, core, hitable, native, ppm, scene, shader, texture, util  # noqa: F401
+from . import camera, core, hitable, native, parallel, ppm, scene, shader, texture, util  # noqa: F401
 
-__all__ = ["camera", "core", "hitable", "native", "ppm", "scene", "shader", "texture", "util"]
+__all__ = ["camera", "core", "hitable", "native", "parallel", "ppm", "scene", "shader", "texture", "util"]

@@ -36,7 +36,7 @@ SCENES = {
 }
 
 
-def render(camera, world, nx, ny, nr, *, depth=50, seed=1, variant=native.RT_VARIANT_MEGAKERNEL,
+def render(camera, world, nx, ny, nr, *, depth=50, seed=1, variant=native.RT_VARIANT_WAVEFRONT,
            device_ids=None, renderer=None):
     """core.clj:99-108 replaced: returns (linear float32 [ny,nx,3] bottom-up, rgb8 [ny,nx,3] top-down,
     counters)."""
@@ -56,7 +56,7 @@ def main(argv=None):
     """core.clj:73-115: `[filename] [nx] [ny] [nsamples] [win]`.  Additive, optional knobs come from
     the environment so the 4 documented positional arguments stay byte-for-byte:
     RT_SCENE (random | random-static | two-spheres | stress), RT_SEED, RT_SCENE_SEED,
-    RT_VARIANT (0 megakernel, 1 wavefront), RT_DEVICES (e.g. "0,1,2,3")."""
+    RT_VARIANT (1 wavefront [default], 0 megakernel), RT_DEVICES (e.g. "0,1,2,3")."""
     argv = list(sys.argv[1:] if argv is None else argv)
     tstart = time.time()
     filename = argv[0] if len(argv) > 0 else "render.png"
@@ -70,7 +70,7 @@ def main(argv=None):
     sc = SCENES[scene_name](nx, ny, rng)
     devs = [int(x) for x in os.environ.get("RT_DEVICES", "0").split(",")]
     lin, img, ctr = render(sc["camera"], sc["world"], nx, ny, nr, seed=int(os.environ.get("RT_SEED", "1")),
-                           variant=int(os.environ.get("RT_VARIANT", "0")), device_ids=devs)
+                           variant=int(os.environ.get("RT_VARIANT", "1")), device_ids=devs)
     ppm.save(filename, img)
     dt = time.time() - tstart
     print("%.2fs, 100%%, %d rays, %d ray-sphere tests" % (dt, ctr["rays"], ctr["sphere_tests"]))

@@ -13,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -78,15 +80,22 @@ struct rt_ctx {
     std::vector<float> h_c0r, h_c1, h_t0t1;
     std::vector<unsigned> h_flags;
     DevCamera cam{};
-    uint64_t counters[RT_CTR_COUNT] = {0};
+    std::atomic<uint64_t> n_launches{0};
+    std::mutex err_mu;
+    bool profile = false;
+    double stage_ms[4] = {0, 0, 0, 0};   // cull, refine, tie-break, shade (profile mode)
     std::vector<bool> peer_ok;
 };
 
 namespace {
 
 int fail(rt_ctx* ctx, int code, const std::string& msg) {
-    if (ctx) ctx->err = msg;
-    else g_create_error = msg;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);   // device worker threads may fail concurrently
+        ctx->err = msg;
+    } else {
+        g_create_error = msg;
+    }
     return code;
 }
 
@@ -232,13 +241,24 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     wf_generate<<<std::max(1, std::min(light_grid, (int)((count0 + 255) / 256))), 256, 0, stream>>>(W, count0);
     RT_CUDA(ctx, cudaGetLastError());
     const int cull_grid = d.sm_count * bps;
+    ctx->n_launches += 1;   // wf_generate
+    std::vector<cudaEvent_t> evs;   // profile mode: 5 events per iteration
     for (int chunk = 0;; ++chunk) {
         for (int it = 0; it < kWaveChunk; ++it) {
+            cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            if (ctx->profile)
+                for (auto& x : e) { RT_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
+            if (ctx->profile) cudaEventRecord(e[0], stream);
             cull<<<cull_grid, cull_block, smem, stream>>>(W);
+            if (ctx->profile) cudaEventRecord(e[1], stream);
             wf_refine<<<light_grid, 256, 0, stream>>>(W);
+            if (ctx->profile) cudaEventRecord(e[2], stream);
             wf_tiebreak<<<light_grid, 256, 0, stream>>>(W);
+            if (ctx->profile) cudaEventRecord(e[3], stream);
             wf_shade<<<light_grid, 256, 0, stream>>>(W);
+            if (ctx->profile) cudaEventRecord(e[4], stream);
             W.cur ^= 1;
+            ctx->n_launches += 4;
         }
         RT_CUDA(ctx, cudaGetLastError());
         RT_CUDA(ctx, cudaMemcpyAsync(&d.h_wave_state[chunk & 1], d.wave_state, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
@@ -247,6 +267,15 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
             RT_CUDA(ctx, cudaEventSynchronize(d.ev_poll[(chunk - 1) & 1]));
             if (d.h_wave_state[(chunk - 1) & 1].qcount[W.cur] == 0) break;   // kWaveChunk is even: same parity
         }
+    }
+    if (ctx->profile) {
+        RT_CUDA(ctx, cudaStreamSynchronize(stream));
+        for (size_t i = 0; i + 4 < evs.size(); i += 5)
+            for (int sgi = 0; sgi < 4; ++sgi) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, evs[i + sgi], evs[i + sgi + 1]) == cudaSuccess) ctx->stage_ms[sgi] += ms;
+            }
+        for (auto x : evs) cudaEventDestroy(x);
     }
     return RT_OK;
 }
@@ -290,6 +319,7 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
         if (grid < 1) grid = 1;
         kern<<<grid, kBlock, smem, stream>>>(P);
         RT_CUDA(ctx, cudaGetLastError());
+        ctx->n_launches += 1;
         return RT_OK;
     }
     // persistent wavefront: every CTA is an independent engine with its own queues
@@ -629,6 +659,7 @@ int rt_resolve_device(rt_ctx* ctx, int nx, int ny, int nsamples_total, const flo
     cudaStream_t st = (cudaStream_t)stream;
     resolve_kernel<<<(total + 255) / 256, 256, 0, st>>>(P);
     RT_CUDA(ctx, cudaGetLastError());
+    ctx->n_launches += 1;
     if (sync) RT_CUDA(ctx, cudaStreamSynchronize(st));
     return RT_OK;
 }
@@ -643,18 +674,31 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
     if ((long long)nx * ny > 0x7fffffffLL / 3) return fail(ctx, RT_ERR_ARG, "image too large");
     const size_t px = (size_t)nx * ny;
     const int G = (int)ctx->devs.size();
-    // sample slices: device g renders samples [g*S/G, (g+1)*S/G) of every pixel
-    for (int g = 0; g < G; ++g) {
+    // sample slices: device g renders samples [g*S/G, (g+1)*S/G) of every pixel; one host thread per device
+    // (the wavefront variant polls its queue count from the host, so devices must not be driven serially)
+    auto device_work = [&](int g) -> int {
         DeviceBuffers& d = ctx->devs[g];
         RT_CUDA(ctx, cudaSetDevice(d.dev));
-        if ((rc = ensure_frame(ctx, d, px))) return rc;
+        int r = ensure_frame(ctx, d, px);
+        if (r) return r;
         int s0 = (int)((long long)nsamples * g / G), s1 = (int)((long long)nsamples * (g + 1) / G);
         RT_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
         RT_CUDA(ctx, cudaMemsetAsync(d.d_sum, 0, px * 3 * sizeof(float), d.stream));
-        if ((rc = launch_render(ctx, d, nx, ny, s0, s1 - s0, 0, 1, max_depth, seed, variant, d.d_sum, d.stream))) return rc;
+        if ((r = launch_render(ctx, d, nx, ny, s0, s1 - s0, 0, 1, max_depth, seed, variant, d.d_sum, d.stream))) return r;
         RT_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
         RT_CUDA(ctx, cudaEventRecord(d.ev_done, d.stream));
         d.timed = true;
+        return RT_OK;
+    };
+    if (G == 1) {
+        if ((rc = device_work(0))) return rc;
+    } else {
+        std::vector<int> rcs((size_t)G, RT_OK);
+        std::vector<std::thread> workers;
+        for (int g = 0; g < G; ++g) workers.emplace_back([&, g] { rcs[(size_t)g] = device_work(g); });
+        for (auto& w : workers) w.join();
+        for (int g = 0; g < G; ++g)
+            if (rcs[(size_t)g]) return rcs[(size_t)g];
     }
     // combine on the root device: the resolve kernel reads the peers' sums over NVLink
     DeviceBuffers& root = ctx->devs[0];
@@ -679,6 +723,7 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
     int total = nx * ny * 3;
     resolve_kernel<<<(total + 255) / 256, 256, 0, root.stream>>>(P);
     RT_CUDA(ctx, cudaGetLastError());
+    ctx->n_launches += 1;
     if (out_linear_rgb)
         RT_CUDA(ctx, cudaMemcpyAsync(out_linear_rgb, root.d_mean, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
     if (out_rgb8) RT_CUDA(ctx, cudaMemcpyAsync(out_rgb8, root.d_rgb8, px * 3, cudaMemcpyDeviceToHost, root.stream));
@@ -876,6 +921,11 @@ int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]) {
     out[RT_CTR_TERM_MISS] = total[DC_TERM_MISS];
     out[RT_CTR_KERNEL_NS] = (uint64_t)((double)max_ms * 1e6);
     out[RT_CTR_CANDIDATES] = total[DC_CANDIDATES];
+    out[RT_CTR_KERNEL_LAUNCHES] = ctx->n_launches.load();
+    out[RT_CTR_CULL_NS] = (uint64_t)(ctx->stage_ms[0] * 1e6);
+    out[RT_CTR_REFINE_NS] = (uint64_t)(ctx->stage_ms[1] * 1e6);
+    out[RT_CTR_TIEBREAK_NS] = (uint64_t)(ctx->stage_ms[2] * 1e6);
+    out[RT_CTR_SHADE_NS] = (uint64_t)(ctx->stage_ms[3] * 1e6);
     return RT_OK;
 }
 
@@ -888,6 +938,15 @@ int rt_reset_counters(rt_ctx* ctx) {
         RT_CUDA(ctx, cudaMemset(d.d_counters, 0, (DC_COUNT + 1) * sizeof(unsigned long long)));
     }
     cudaSetDevice(ctx->devs[0].dev);
+    ctx->n_launches = 0;
+    for (double& x : ctx->stage_ms) x = 0.0;
+    return RT_OK;
+}
+
+int rt_set_profile(rt_ctx* ctx, int on) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->profile = on != 0;
     return RT_OK;
 }
 

@@ -26,7 +26,7 @@ RT_CAM_PINHOLE, RT_CAM_THIN_LENS = 0, 1
 RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT = 0, 1
 RT_CTR_COUNT = 16
 COUNTER_NAMES = ["rays", "sphere_tests", "samples", "term_light", "term_absorb", "term_depth", "term_miss",
-                 "kernel_ns", "candidates"]
+                 "kernel_ns", "candidates", "kernel_launches", "cull_ns", "refine_ns", "tiebreak_ns", "shade_ns"]
 
 
 class UnsupportedSceneError(ValueError):
@@ -204,7 +204,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_set_scene", "rt_set_camera", "rt_render",
     "rt_render_accumulate_device", "rt_resolve_device", "rt_trace_primary", "rt_generate_rays", "rt_shade_batch",
-    "rt_measure_fp32_peak", "rt_get_counters", "rt_reset_counters", "rt_device_info",
+    "rt_measure_fp32_peak", "rt_get_counters", "rt_reset_counters", "rt_set_profile", "rt_device_info",
 ]
 
 _lib = None
@@ -235,6 +235,7 @@ def load_library():
     L.rt_generate_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_uint64, _f32p, _f32p,
                                    _f32p, _f32p]
     L.rt_reset_counters.argtypes = [C.c_void_p]
+    L.rt_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.rt_shade_batch.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _i32p, _f64p, _f32p, _f32p, _f32p, _f32p,
                                  _f32p, _f32p, _i32p]
     L.rt_measure_fp32_peak.argtypes = [C.c_void_p, _f64p, _f64p]
@@ -302,7 +303,7 @@ class Renderer:
         assert c.shape == (24,)
         self._check(self.L.rt_set_camera(self.h, C.c_int(cam_type), _p(c, _f32p)), "rt_set_camera")
 
-    def render(self, nx, ny, nsamples, max_depth=50, seed=1, variant=RT_VARIANT_MEGAKERNEL, linear=True, rgb8=True,
+    def render(self, nx, ny, nsamples, max_depth=50, seed=1, variant=RT_VARIANT_WAVEFRONT, linear=True, rgb8=True,
                out_linear=None, out_rgb8=None):
         """rt_render with host buffers.  Returns (linear [ny,nx,3] f32 with j=0 bottom | None, rgb8 [ny,nx,3] | None)."""
         lin = (out_linear if out_linear is not None else np.empty((ny, nx, 3), np.float32)) if linear else None
@@ -312,7 +313,7 @@ class Renderer:
         return lin, img
 
     def render_accumulate_device(self, nx, ny, sample_begin, sample_count, d_sum_ptr, row_offset=0, row_stride=1,
-                                 max_depth=50, seed=1, variant=RT_VARIANT_MEGAKERNEL, stream=None, sync=True):
+                                 max_depth=50, seed=1, variant=RT_VARIANT_WAVEFRONT, stream=None, sync=True):
         self._check(self.L.rt_render_accumulate_device(
             self.h, nx, ny, sample_begin, sample_count, row_offset, row_stride, max_depth, C.c_uint64(seed), variant,
             C.c_void_p(d_sum_ptr), C.c_void_p(stream or 0), 1 if sync else 0), "rt_render_accumulate_device")
@@ -373,6 +374,9 @@ class Renderer:
 
     def reset_counters(self):
         self._check(self.L.rt_reset_counters(self.h), "rt_reset_counters")
+
+    def set_profile(self, on=True):
+        self._check(self.L.rt_set_profile(self.h, 1 if on else 0), "rt_set_profile")
 
     def device_info(self):
         sm = C.c_int32(); clk = C.c_int32(); name = C.create_string_buffer(64)

@@ -428,3 +428,24 @@ def test_error_paths(scene_c2):
         assert lin.shape == (8, 16, 3) and img.shape == (8, 16, 3) and np.isfinite(lin).all()
     with pytest.raises(rt.native.NativeError):
         rt.native.Renderer([99])
+
+
+def test_multi_device_in_library_matches_single(scene_c2):
+    """rt_create with two devices (the single-process path a JVM caller uses): sample slices on each device,
+    per-device float sums combined on device 0 over NVLink peer access inside the resolve kernel."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    flat, cam_type, cam, _ = scene_c2
+    nx, ny, ns = 160, 96, 8
+    with rt.native.Renderer([0]) as r1, rt.native.Renderer([0, 1]) as r2:
+        for r in (r1, r2):
+            r.set_scene(flat)
+            r.set_camera(cam_type, cam)
+        a, img_a = r1.render(nx, ny, ns, 50, seed=11)
+        b, img_b = r2.render(nx, ny, ns, 50, seed=11)
+        c2 = r2.counters()
+    assert np.allclose(a, b, rtol=1e-4, atol=1e-4)          # same paths; float summation order differs
+    assert (img_a != img_b).mean() < 1e-3
+    assert c2["samples"] == nx * ny * ns
