@@ -58,6 +58,13 @@ def build_scene(name, nx, ny, seed):
     return flat, cam_type, cam
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def scene_bytes(flat):
     return int(sum(getattr(flat, k).nbytes for k in flat.__dataclass_fields__)) + 24 * 4
 
@@ -126,13 +133,13 @@ def run_reference(args, world, rank):
     flat, cam_type, cam = build_scene(scene_name, nx, ny, scene_seed)
     S = oracle.Scene(flat)
     step_spp = max(1, min(spp, 2))
-    cores = oracle.max_threads()
+    cores = host_cores()            # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     for w in range(args.warmup):
-        S.render_accumulate(cam_type, cam, nx, ny, 0, 1, depth, seed=w)
+        S.render_accumulate(cam_type, cam, nx, ny, 0, 1, depth, seed=w, n_threads=cores)
     t0 = time.perf_counter()
     samples = tests = 0
     for k in range(args.steps):
-        _, c = S.render_accumulate(cam_type, cam, nx, ny, k * step_spp, step_spp, depth, seed=1)
+        _, c = S.render_accumulate(cam_type, cam, nx, ny, k * step_spp, step_spp, depth, seed=1, n_threads=cores)
         samples += c["samples"]
         tests += c["sphere_tests"]
     dt = time.perf_counter() - t0
@@ -157,7 +164,7 @@ def run_reference(args, world, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -350,11 +357,11 @@ def main():
             import oracle
 
             S = oracle.Scene(flat)
-            cores = oracle.max_threads()
+            cores = host_cores()
             cpu_spp = spp if cores >= 8 else max(1, spp // 4)
-            S.render_accumulate(cam_type, cam, nx, ny, 0, 1, depth, seed=9)          # warm-up
+            S.render_accumulate(cam_type, cam, nx, ny, 0, 1, depth, seed=9, n_threads=cores)          # warm-up
             t0 = time.perf_counter()
-            _, c = S.render_accumulate(cam_type, cam, nx, ny, 0, cpu_spp, depth, seed=1)
+            _, c = S.render_accumulate(cam_type, cam, nx, ny, 0, cpu_spp, depth, seed=1, n_threads=cores)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {
                 "value": c["samples"] / dt, "unit": "samples/s", "cores": cores, "kind": "port",
