@@ -32,6 +32,8 @@ constexpr int kTileCap = 4096; // float4 slots of the shared-memory sphere tile 
 
 thread_local std::string g_create_error;
 
+constexpr int kMaxLanes = 2;
+
 struct DeviceBuffers {
     int dev = 0;
     cudaStream_t stream = nullptr;
@@ -46,16 +48,21 @@ struct DeviceBuffers {
     size_t frame_px = 0;
     unsigned long long* d_counters = nullptr;   // DC_COUNT + 1 (last = work counter)
     // wavefront queues
-    float4* wave_queue = nullptr;            // 2 * 3 * wave_entries float4
-    unsigned long long* wave_best = nullptr; // 2 * wave_entries
-    uint2* wave_pairs = nullptr;
-    uint2* wave_cands = nullptr;
-    double* wave_cand_t = nullptr;
-    unsigned* wave_cand_count = nullptr;
-    WaveState* wave_state = nullptr;
-    WaveState* h_wave_state = nullptr;       // pinned, 2 snapshots
-    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
-    size_t wave_entries = 0;
+    struct WaveLane {
+        float4* queue = nullptr;            // 2 * 3 * entries float4
+        unsigned long long* best = nullptr; // 2 * entries
+        uint2* pairs = nullptr;
+        uint2* cands = nullptr;
+        double* cand_t = nullptr;
+        unsigned* cand_count = nullptr;
+        WaveState* state = nullptr;
+        WaveState* h_state = nullptr;       // pinned, 2 snapshots
+        cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+        cudaEvent_t ev_done = nullptr;
+        cudaStream_t stream = nullptr;      // lane 0 runs on the caller's stream, the others on their own
+        size_t entries = 0;
+    } lanes[kMaxLanes];
+    cudaEvent_t ev_lane_start = nullptr;
     // scratch for diagnostics
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -132,38 +139,57 @@ int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
 }
 
 constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 2.6)
-constexpr size_t kWaveCapacity = 1u << 21;  // paths in flight per device
+constexpr size_t kWaveCapacity = 1u << 22;  // paths in flight per device (all lanes together)
 constexpr int kWaveChunk = 4;           // iterations enqueued between two polls of the queue count
+constexpr unsigned kTailEntries = 1u << 16;   // queue length at which the cooperative tail kernel takes over
 
-void free_wave(DeviceBuffers& d) {
-    if (d.wave_queue) cudaFree(d.wave_queue);
-    if (d.wave_best) cudaFree(d.wave_best);
-    if (d.wave_pairs) cudaFree(d.wave_pairs);
-    if (d.wave_cands) cudaFree(d.wave_cands);
-    if (d.wave_cand_t) cudaFree(d.wave_cand_t);
-    if (d.wave_cand_count) cudaFree(d.wave_cand_count);
-    d.wave_cand_count = nullptr;
-    d.wave_queue = nullptr; d.wave_best = nullptr; d.wave_pairs = nullptr; d.wave_cands = nullptr; d.wave_cand_t = nullptr;
-    d.wave_entries = 0;
+void free_lane(DeviceBuffers::WaveLane& L) {
+    if (L.queue) cudaFree(L.queue);
+    if (L.best) cudaFree(L.best);
+    if (L.pairs) cudaFree(L.pairs);
+    if (L.cands) cudaFree(L.cands);
+    if (L.cand_t) cudaFree(L.cand_t);
+    if (L.cand_count) cudaFree(L.cand_count);
+    L.queue = nullptr; L.best = nullptr; L.pairs = nullptr; L.cands = nullptr; L.cand_t = nullptr; L.cand_count = nullptr;
+    L.entries = 0;
 }
 
-int ensure_wave(rt_ctx* ctx, DeviceBuffers& d, size_t entries) {
-    if (!d.wave_state) {
-        RT_CUDA(ctx, cudaMalloc(&d.wave_state, sizeof(WaveState)));
-        RT_CUDA(ctx, cudaHostAlloc(&d.h_wave_state, 2 * sizeof(WaveState), cudaHostAllocDefault));
-        for (int i = 0; i < 2; ++i) RT_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_poll[i], cudaEventDisableTiming));
+void free_wave(DeviceBuffers& d) {
+    for (auto& L : d.lanes) {
+        free_lane(L);
+        if (L.state) cudaFree(L.state);
+        if (L.h_state) cudaFreeHost(L.h_state);
+        for (auto& e : L.ev_poll)
+            if (e) cudaEventDestroy(e);
+        if (L.ev_done) cudaEventDestroy(L.ev_done);
+        if (L.stream) cudaStreamDestroy(L.stream);
+        L = DeviceBuffers::WaveLane();
     }
-    if (d.wave_entries >= entries) return RT_OK;
-    free_wave(d);
-    RT_CUDA(ctx, cudaMalloc(&d.wave_queue, entries * 2 * 3 * sizeof(float4)));
-    RT_CUDA(ctx, cudaMalloc(&d.wave_best, entries * 2 * sizeof(unsigned long long)));
-    RT_CUDA(ctx, cudaMalloc(&d.wave_pairs, entries * kPairsPerEntry * sizeof(uint2)));
+    if (d.ev_lane_start) cudaEventDestroy(d.ev_lane_start);
+    d.ev_lane_start = nullptr;
+}
+
+int ensure_lane(rt_ctx* ctx, DeviceBuffers& d, int lane, size_t entries) {
+    DeviceBuffers::WaveLane& L = d.lanes[lane];
+    if (!L.state) {
+        RT_CUDA(ctx, cudaMalloc(&L.state, sizeof(WaveState)));
+        RT_CUDA(ctx, cudaHostAlloc(&L.h_state, 2 * sizeof(WaveState), cudaHostAllocDefault));
+        for (auto& e : L.ev_poll) RT_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+        if (lane > 0) RT_CUDA(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        if (!d.ev_lane_start) RT_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_lane_start, cudaEventDisableTiming));
+    }
+    if (L.entries >= entries) return RT_OK;
+    free_lane(L);
+    RT_CUDA(ctx, cudaMalloc(&L.queue, entries * 2 * 3 * sizeof(float4)));
+    RT_CUDA(ctx, cudaMalloc(&L.best, entries * 2 * sizeof(unsigned long long)));
+    RT_CUDA(ctx, cudaMalloc(&L.pairs, entries * kPairsPerEntry * sizeof(uint2)));
     // candidate regions are private to the warps of the refine grid: pair_cap rounded up per warp
     const size_t cand_slots = entries * kPairsPerEntry + (size_t)d.sm_count * 8 * 8 * 32;
-    RT_CUDA(ctx, cudaMalloc(&d.wave_cands, cand_slots * sizeof(uint2)));
-    RT_CUDA(ctx, cudaMalloc(&d.wave_cand_t, cand_slots * sizeof(double)));
-    RT_CUDA(ctx, cudaMalloc(&d.wave_cand_count, (size_t)d.sm_count * 8 * 8 * sizeof(unsigned)));
-    d.wave_entries = entries;
+    RT_CUDA(ctx, cudaMalloc(&L.cands, cand_slots * sizeof(uint2)));
+    RT_CUDA(ctx, cudaMalloc(&L.cand_t, cand_slots * sizeof(double)));
+    RT_CUDA(ctx, cudaMalloc(&L.cand_count, (size_t)d.sm_count * 8 * 8 * sizeof(unsigned)));
+    L.entries = entries;
     return RT_OK;
 }
 
@@ -207,66 +233,136 @@ int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WavePar
     return RT_OK;
 }
 
+// Wavefront render of one device's share.  The path population is split into `lanes` independent halves,
+// each running its own cull -> refine -> tie-break -> shade sequence on its own stream over its own queues
+// (they share only the work counter and the frame, both atomics): one lane's FP32-issue-bound cull kernel
+// co-runs with the other lane's latency-bound refine / shade kernels.  The host enqueues kWaveChunk
+// iterations per lane ahead of the GPU and polls each lane's queue count; when the work counter is
+// exhausted and a lane's queue is short, one cooperative wf_tail launch finishes that lane.
 int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned long long, cudaStream_t stream) {
-    // CTA shape of the cull kernel: 128 threads x 5 CTAs/SM (20 warps/SM) measured best;
-    // RT_CULL_SHAPE = "256x2" | "256x3" | "128x5" | "128x6" for experiments
+    // CTA shape of the cull kernel; RT_CULL_SHAPE = "256x2" | "256x3" | "128x4" | "128x5" | "128x6"
     static const std::string shape = getenv("RT_CULL_SHAPE") ? getenv("RT_CULL_SHAPE") : "128x5";
     void (*cull)(const WaveParams) = nullptr;
     size_t smem = 0;
     int bps = 0, cull_block = 256, rc;
     if (shape == "256x2") rc = cull_config<256, 2>(ctx, &smem, &bps, &cull);
-    else if (shape == "128x5") { rc = cull_config<128, 5>(ctx, &smem, &bps, &cull); cull_block = 128; }
+    else if (shape == "256x3") rc = cull_config<256, 3>(ctx, &smem, &bps, &cull);
+    else if (shape == "128x4") { rc = cull_config<128, 4>(ctx, &smem, &bps, &cull); cull_block = 128; }
     else if (shape == "128x6") { rc = cull_config<128, 6>(ctx, &smem, &bps, &cull); cull_block = 128; }
-    else rc = cull_config<256, 3>(ctx, &smem, &bps, &cull);
+    else { rc = cull_config<128, 5>(ctx, &smem, &bps, &cull); cull_block = 128; }
     if (rc) return rc;
-    static const size_t cap_env = (size_t)std::max(1, env_int("RT_WAVE_CAPACITY", (int)kWaveCapacity));
-    const size_t capacity = align_up((size_t)std::min<unsigned long long>(cap_env, P.total_work), 32);
-    if ((rc = ensure_wave(ctx, d, capacity))) return rc;
-    WaveParams W{};
-    W.base = P;
-    W.queue[0] = d.wave_queue;
-    W.queue[1] = d.wave_queue + 3 * capacity;
-    W.best_t = d.wave_best;
-    W.best_key = d.wave_best + capacity;
-    W.pairs = d.wave_pairs;
-    W.cands = d.wave_cands;
-    W.cand_t = d.wave_cand_t;
-    W.cand_count = d.wave_cand_count;
-    W.st = d.wave_state;
-    W.capacity = (int)capacity;
-    W.pair_cap = (unsigned)std::min<size_t>(capacity * kPairsPerEntry, 0xfffffff0u);
-    W.cur = 0;
-    const unsigned count0 = (unsigned)std::min<unsigned long long>(capacity, P.total_work);
-    const int light_grid = d.sm_count * 8;
-    wf_generate<<<std::max(1, std::min(light_grid, (int)((count0 + 255) / 256))), 256, 0, stream>>>(W, count0);
-    RT_CUDA(ctx, cudaGetLastError());
+    static const int cull_ctas_env = env_int("RT_CULL_CTAS_PER_SM", 4);   // one fewer than the occupancy limit leaves
+    if (cull_ctas_env > 0) bps = std::min(bps, cull_ctas_env);           // room for the other lane's light kernels
+    static const size_t cap_env = (size_t)std::max(64, env_int("RT_WAVE_CAPACITY", (int)kWaveCapacity));
+    static const int lanes_env = std::max(1, std::min(kMaxLanes, env_int("RT_WAVE_LANES", 2)));
+    const int n_lanes = (ctx->profile || P.total_work < 65536) ? 1 : lanes_env;   // stage timing wants one lane
+    const size_t capacity = align_up((size_t)std::min<unsigned long long>(cap_env / n_lanes, (P.total_work + n_lanes - 1) / n_lanes), 32);
+
+    // cooperative tail kernel: every CTA must be resident, also next to the other lane's tail
+    static const unsigned tail_entries = (unsigned)std::max(0, env_int("RT_TAIL_ENTRIES", (int)kTailEntries));
+    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * 256 * sizeof(uint16_t);
+    int tail_bps = 0, coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d.dev);
+    RT_CUDA(ctx, cudaFuncSetAttribute(wf_tail<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_bps, wf_tail<256>, 256, tail_smem));
+    const int tail_grid = d.sm_count * (n_lanes > 1 ? 1 : std::min(tail_bps, 2));
+    const bool tail_ok = coop && tail_bps >= n_lanes && tail_entries > 0 && !ctx->profile;
+
+    static const int light_block = std::max(64, std::min(256, env_int("RT_LIGHT_BLOCK", 256) / 32 * 32));
+    const int light_grid = d.sm_count * 8 * 256 / light_block;
     const int cull_grid = d.sm_count * bps;
-    ctx->n_launches += 1;   // wf_generate
-    std::vector<cudaEvent_t> evs;   // profile mode: 5 events per iteration
+    WaveParams W[kMaxLanes];
+    cudaStream_t st[kMaxLanes];
+    bool done[kMaxLanes];
+    unsigned long long first = 0;
+    for (int l = 0; l < n_lanes; ++l) {
+        if ((rc = ensure_lane(ctx, d, l, capacity))) return rc;
+        DeviceBuffers::WaveLane& L = d.lanes[l];
+        W[l] = WaveParams{};
+        W[l].base = P;
+        W[l].queue[0] = L.queue;
+        W[l].queue[1] = L.queue + 3 * capacity;
+        W[l].best_t = L.best;
+        W[l].best_key = L.best + capacity;
+        W[l].pairs = L.pairs;
+        W[l].cands = L.cands;
+        W[l].cand_t = L.cand_t;
+        W[l].cand_count = L.cand_count;
+        W[l].st = L.state;
+        W[l].capacity = (int)capacity;
+        W[l].pair_cap = (unsigned)std::min<size_t>(capacity * kPairsPerEntry, 0xfffffff0u);
+        W[l].cur = 0;
+        st[l] = l == 0 ? stream : L.stream;
+        done[l] = false;
+    }
+    // the shared work counter starts past every lane's first fill
+    unsigned count0[kMaxLanes];
+    unsigned long long total0 = 0;
+    for (int l = 0; l < n_lanes; ++l) {
+        count0[l] = (unsigned)std::min<unsigned long long>(capacity, P.total_work - total0);
+        total0 += count0[l];
+    }
+    wf_init<<<1, 1, 0, stream>>>(P.work_counter, total0);
+    RT_CUDA(ctx, cudaEventRecord(d.ev_lane_start, stream));
+    for (int l = 0; l < n_lanes; ++l) {
+        if (l > 0) RT_CUDA(ctx, cudaStreamWaitEvent(st[l], d.ev_lane_start, 0));
+        wf_generate<<<std::max(1, std::min(light_grid, (int)((count0[l] + 255) / 256))), 256, 0, st[l]>>>(W[l], first, count0[l]);
+        first += count0[l];
+        ctx->n_launches += 1;
+    }
+    ctx->n_launches += 1;   // wf_init
+    RT_CUDA(ctx, cudaGetLastError());
+
+    std::vector<cudaEvent_t> evs;   // profile mode (one lane): 5 events per iteration
     for (int chunk = 0;; ++chunk) {
-        for (int it = 0; it < kWaveChunk; ++it) {
-            cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-            if (ctx->profile)
-                for (auto& x : e) { RT_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
-            if (ctx->profile) cudaEventRecord(e[0], stream);
-            cull<<<cull_grid, cull_block, smem, stream>>>(W);
-            if (ctx->profile) cudaEventRecord(e[1], stream);
-            wf_refine<<<light_grid, 256, 0, stream>>>(W);
-            if (ctx->profile) cudaEventRecord(e[2], stream);
-            wf_tiebreak<<<light_grid, 256, 0, stream>>>(W);
-            if (ctx->profile) cudaEventRecord(e[3], stream);
-            wf_shade<<<light_grid, 256, 0, stream>>>(W);
-            if (ctx->profile) cudaEventRecord(e[4], stream);
-            W.cur ^= 1;
-            ctx->n_launches += 4;
+        bool all_done = true;
+        for (int l = 0; l < n_lanes; ++l) {
+            if (done[l]) continue;
+            DeviceBuffers::WaveLane& L = d.lanes[l];
+            for (int it = 0; it < kWaveChunk; ++it) {
+                cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+                if (ctx->profile)
+                    for (auto& x : e) { RT_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
+                if (ctx->profile) cudaEventRecord(e[0], st[l]);
+                cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
+                if (ctx->profile) cudaEventRecord(e[1], st[l]);
+                wf_refine<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                if (ctx->profile) cudaEventRecord(e[2], st[l]);
+                wf_tiebreak<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                if (ctx->profile) cudaEventRecord(e[3], st[l]);
+                wf_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                if (ctx->profile) cudaEventRecord(e[4], st[l]);
+                W[l].cur ^= 1;
+                ctx->n_launches += 4;
+            }
+            RT_CUDA(ctx, cudaGetLastError());
+            RT_CUDA(ctx, cudaMemcpyAsync(&L.h_state[chunk & 1], L.state, sizeof(WaveState), cudaMemcpyDeviceToHost, st[l]));
+            RT_CUDA(ctx, cudaEventRecord(L.ev_poll[chunk & 1], st[l]));
         }
-        RT_CUDA(ctx, cudaGetLastError());
-        RT_CUDA(ctx, cudaMemcpyAsync(&d.h_wave_state[chunk & 1], d.wave_state, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
-        RT_CUDA(ctx, cudaEventRecord(d.ev_poll[chunk & 1], stream));
-        if (chunk > 0) {   // look at the PREVIOUS chunk's snapshot: the GPU always has one chunk queued
-            RT_CUDA(ctx, cudaEventSynchronize(d.ev_poll[(chunk - 1) & 1]));
-            if (d.h_wave_state[(chunk - 1) & 1].qcount[W.cur] == 0) break;   // kWaveChunk is even: same parity
+        if (chunk > 0) {   // look at the PREVIOUS chunk's snapshots: every lane always has one chunk queued
+            for (int l = 0; l < n_lanes; ++l) {
+                if (done[l]) continue;
+                DeviceBuffers::WaveLane& L = d.lanes[l];
+                RT_CUDA(ctx, cudaEventSynchronize(L.ev_poll[(chunk - 1) & 1]));
+                const WaveState& snap = L.h_state[(chunk - 1) & 1];
+                if (snap.qcount[W[l].cur] == 0) {   // kWaveChunk is even: same parity
+                    done[l] = true;
+                } else if (tail_ok && snap.exhausted && snap.qcount[W[l].cur] <= tail_entries) {
+                    // no new work can appear and the queue is short: one cooperative launch finishes this lane
+                    void* args[] = {(void*)&W[l]};
+                    RT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)wf_tail<256>, dim3(tail_grid), dim3(256), args, tail_smem, st[l]));
+                    ctx->n_launches += 1;
+                    done[l] = true;
+                }
+            }
         }
+        for (int l = 0; l < n_lanes; ++l) all_done &= done[l];
+        if (all_done) break;
+    }
+    // the caller's stream continues only after every lane has drained
+    for (int l = 1; l < n_lanes; ++l) {
+        RT_CUDA(ctx, cudaEventRecord(d.lanes[l].ev_done, st[l]));
+        RT_CUDA(ctx, cudaStreamWaitEvent(stream, d.lanes[l].ev_done, 0));
     }
     if (ctx->profile) {
         RT_CUDA(ctx, cudaStreamSynchronize(stream));
@@ -469,10 +565,6 @@ void rt_destroy(rt_ctx* ctx) {
         if (d.d_counters) cudaFree(d.d_counters);
         if (d.scratch) cudaFree(d.scratch);
         free_wave(d);
-        if (d.wave_state) cudaFree(d.wave_state);
-        if (d.h_wave_state) cudaFreeHost(d.h_wave_state);
-        for (int i = 0; i < 2; ++i)
-            if (d.ev_poll[i]) cudaEventDestroy(d.ev_poll[i]);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_done) cudaEventDestroy(d.ev_done);

@@ -16,6 +16,8 @@
 //   ffma_peak_kernel   FP32 roofline denominator measured on the box
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "rt_device.cuh"
 
 namespace rt {
@@ -269,7 +271,8 @@ struct WaveState {
     unsigned qcount[2];            // entries in queue[i]
     unsigned batch;                // next batch (wf_cull)
     unsigned npairs;               // pairs emitted this iteration
-    unsigned pad[4];
+    unsigned exhausted;            // the (sample, pixel) work counter has run past the end
+    unsigned pad[3];
 };
 
 struct WaveParams {
@@ -334,12 +337,15 @@ __device__ __forceinline__ void make_path(const RenderParams& P, unsigned long l
     c = make_float4(1.f, 1.f, 1.f, __uint_as_float((smp << 8) | (uint32_t)P.max_depth));
 }
 
-// first fill of queue 0: work items [0, count) map 1:1 to entries, no atomics
-__global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned count) {
+// first fill of a lane's queue 0: work items [first, first + count) map 1:1 to entries, no atomics
+// (the host has already advanced the shared work counter past every lane's first fill: wf_init)
+__global__ void wf_init(unsigned long long* work_counter, unsigned long long value) { *work_counter = value; }
+
+__global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned long long first, unsigned count) {
     const RenderParams& P = W.base;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         float4 a, b, c;
-        make_path(P, i, a, b, c);
+        make_path(P, first + i, a, b, c);
         float4* q = W.queue[0] + 3 * (size_t)i;
         q[0] = a; q[1] = b; q[2] = c;
     }
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned 
         W.st->qcount[1] = 0;
         W.st->batch = 0;
         W.st->npairs = 0;
-        *P.work_counter = count;
+        W.st->exhausted = 0;
         atomicAdd(&P.counters[DC_SAMPLES], (unsigned long long)count);
     }
 }
@@ -401,7 +407,7 @@ struct PairSink {
 };
 
 template <int R, int BLOCK>
-__device__ __forceinline__ void wf_cull_batches(const WaveParams& W, unsigned n, int parts, float4* s_cull,
+__device__ __forceinline__ void wf_cull_batches(const WaveParams& W, int cur, unsigned n, int parts, float4* s_cull,
                                                 uint16_t* s_list) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
@@ -427,7 +433,7 @@ __device__ __forceinline__ void wf_cull_batches(const WaveParams& W, unsigned n,
         RT_FOR_R {
             unsigned idx = sink.idx0 + 32 * r;
             if (idx < n && batch < n_batches) {
-                float4 a = W.queue[W.cur][3 * (size_t)idx], b = W.queue[W.cur][3 * (size_t)idx + 1];
+                float4 a = W.queue[cur][3 * (size_t)idx], b = W.queue[cur][3 * (size_t)idx + 1];
                 K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w);
                 if (part == 0) {
                     W.best_t[idx] = BEST_T_INIT;
@@ -443,6 +449,25 @@ __device__ __forceinline__ void wf_cull_batches(const WaveParams& W, unsigned n,
     }
 }
 
+// queue length decides the shape of the cull work: full batches of R rays per thread while every warp of the
+// grid gets at least two one-ray batches' worth; below that 1 ray per thread, and below THAT the sphere
+// list is split across warps too (the pairs merge in wf_refine).  R = 1 instantiates only the short form.
+template <int R, int BLOCK>
+__device__ __forceinline__ void wf_cull_body(const WaveParams& W, int cur, unsigned n, float4* s_cull, uint16_t* s_list) {
+    const RenderParams& P = W.base;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
+    const unsigned grid_warps = gridDim.x * (BLOCK / 32);
+    if (R > 1 && (n >= grid_warps * 64u || !P.preloaded)) {
+        wf_cull_batches<R, BLOCK>(W, cur, n, 1, s_cull, s_list);
+    } else {
+        const unsigned b1 = (n + 31) / 32;
+        int parts = 1;
+        if (P.preloaded)
+            while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
+        wf_cull_batches<1, BLOCK>(W, cur, n, parts, s_cull, s_list);
+    }
+}
+
 template <int R, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
     const RenderParams& P = W.base;
@@ -453,18 +478,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
     if (n == 0) return;
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
-    // queue length decides the shape of the work: full batches of 4 rays per thread while every warp of the
-    // grid gets at least one; below that 1 ray per thread, and below THAT the sphere list is split too
-    const unsigned grid_warps = gridDim.x * (BLOCK / 32);
-    if (n >= grid_warps * 64u || !P.preloaded) {   // >= 2 one-ray batches per warp: the 4-ray loop's lower cost per test wins
-        wf_cull_batches<R, BLOCK>(W, n, 1, s_cull, s_list);
-    } else {
-        const unsigned b1 = (n + 31) / 32;
-        int parts = 1;
-        while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
-        wf_cull_batches<1, BLOCK>(W, n, parts, s_cull, s_list);
-    }
+    wf_cull_body<R, BLOCK>(W, W.cur, n, s_cull, s_list);
 }
 
 // one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved).
@@ -476,14 +490,14 @@ __device__ __forceinline__ unsigned wf_cand_region(const WaveParams& W, unsigned
     return ((W.pair_cap + total_warps * 32u - 1u) / (total_warps * 32u)) * 32u;   // pairs one warp can see
 }
 
-__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) {
+__device__ __forceinline__ void wf_refine_body(const WaveParams& W, int cur) {
     const RenderParams& P = W.base;
-    const unsigned n = W.st->qcount[W.cur];
+    const unsigned n = W.st->qcount[cur];
     const unsigned npairs = min(W.st->npairs, W.pair_cap);
     const unsigned lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         W.st->batch = 0;               // wf_cull is done with it
-        W.st->qcount[W.cur ^ 1] = 0;   // wf_shade appends to it next
+        W.st->qcount[cur ^ 1] = 0;     // wf_shade appends to it next
         atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);
     }
     const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
@@ -498,7 +512,7 @@ __global__ void __launch_bounds__(256) wf_refine(const WaveParams W) {
         double t = CUDART_INF;
         if (i < npairs) pr = W.pairs[i];
         if (pr.x != PAIR_NULL && pr.x < n) {
-            const float4 a = W.queue[W.cur][3 * (size_t)pr.x], b = W.queue[W.cur][3 * (size_t)pr.x + 1];
+            const float4 a = W.queue[cur][3 * (size_t)pr.x], b = W.queue[cur][3 * (size_t)pr.x + 1];
             const unsigned long long seen = __ldcg(&W.best_t[pr.x]);
             t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, (int)pr.y, a.x, a.y, a.z, b.x, b.y, b.z,
                                  a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
@@ -518,10 +532,11 @@ __global__ void __launch_bounds__(256) wf_refine(const WaveParams W) {
     }
     if (lane == 0) W.cand_count[warp_id] = cnt;
 }
+__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) { wf_refine_body(W, W.cur); }
 
 // exact ties go to the lower caller index, the Hitlist rule (hitable.clj:17-26): candidates that own the final
 // minimum t race with atomicMin on (caller index, k).  Same grid shape as wf_refine (warp-private regions).
-__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) {
+__device__ __forceinline__ void wf_tiebreak_body(const WaveParams& W) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
@@ -534,6 +549,7 @@ __global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) {
             atomicMin(&W.best_key[pr.x], (((unsigned long long)(__ldg(&P.sc.orig_id[pr.y]) + 1)) << 32) | pr.y);
     }
 }
+__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) { wf_tiebreak_body(W); }
 
 // exact closest hit of one ray by brute force in FP64 (only for entries whose pairs overflowed the pair buffer)
 __device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, float oy, float oz, float dx, float dy, float dz,
@@ -552,16 +568,17 @@ __device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, floa
     *out_k = bk;
 }
 
-__global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
+// s_ctr: shared counters of the calling kernel (DC_COUNT slots, zeroed by the caller); returns samples generated
+__device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, int cur, unsigned* s_ctr) {
     const RenderParams& P = W.base;
-    __shared__ unsigned s_ctr[DC_COUNT];
-    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
-    __syncthreads();
-    const unsigned n = W.st->qcount[W.cur];
+    const unsigned n = W.st->qcount[cur];
     const unsigned lane = threadIdx.x & 31u;
-    const float4* qc = W.queue[W.cur];
-    float4* qn = W.queue[W.cur ^ 1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) W.st->npairs = 0;   // refine / tie-break are done with it
+    const float4* qc = W.queue[cur];
+    float4* qn = W.queue[cur ^ 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        W.st->npairs = 0;   // refine / tie-break are done with it
+        W.st->exhausted = (*(volatile unsigned long long*)P.work_counter >= P.total_work) ? 1u : 0u;
+    }
     unsigned n_samples = 0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned idx0 = blockIdx.x * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
@@ -612,16 +629,62 @@ __global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
             cont = true;
             n_samples++;
         }
-        unsigned slot = warp_claim(&W.st->qcount[W.cur ^ 1], cont, lane);
+        unsigned slot = warp_claim(&W.st->qcount[cur ^ 1], cont, lane);
         if (cont) {
             float4* q = qn + 3 * (size_t)slot;
             q[0] = a; q[1] = b; q[2] = c;
         }
     }
+    return n_samples;
+}
+
+__global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
+    const RenderParams& P = W.base;
+    __shared__ unsigned s_ctr[DC_COUNT];
+    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned n_samples = wf_shade_body(W, W.cur, s_ctr);
     atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
     __syncthreads();
     if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
 }
+
+// Tail of a render: the work counter is exhausted and the queue is short.  ONE cooperative launch runs all
+// the remaining bounces (up to the depth cutoff), stages of an iteration separated by grid.sync() instead of
+// kernel boundaries: the sphere list is staged in shared memory once, and a tiny iteration costs a few
+// barrier latencies instead of four kernel-launch floors (~30 us measured per iteration before).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const RenderParams& P = W.base;
+    extern __shared__ float4 smem_f4[];
+    float4* s_cull = smem_f4;
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
+    __shared__ unsigned s_ctr[DC_COUNT];
+    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
+    __syncthreads();
+    unsigned n_samples = 0;
+    int cur = W.cur;
+    for (;;) {
+        const unsigned n = *(volatile unsigned*)&W.st->qcount[cur];
+        if (n == 0) break;
+        wf_cull_body<1, BLOCK>(W, cur, n, s_cull, s_list);
+        grid.sync();
+        wf_refine_body(W, cur);
+        grid.sync();
+        wf_tiebreak_body(W);
+        grid.sync();
+        n_samples += wf_shade_body(W, cur, s_ctr);
+        grid.sync();
+        cur ^= 1;
+    }
+    atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
+    __syncthreads();
+    if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+}
+
 
 // ------------------------------------------------------------------------------------------
 // Persistent megakernel with path regeneration (kept for comparison): every thread owns R path
