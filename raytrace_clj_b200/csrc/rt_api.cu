@@ -201,7 +201,7 @@ float round_up_f32(double x) {
     return f;
 }
 
-size_t mega_smem_bytes(int cull_cap) { return (size_t)cull_cap * sizeof(float4) + (size_t)LIST_K * kBlock * sizeof(uint16_t); }
+size_t mega_smem_bytes(int cull_cap) { return (size_t)cull_cap * sizeof(float4) + (size_t)LIST_K * kBlock * sizeof(uint32_t); }
 
 template <typename Kern>
 int configure_kernel(rt_ctx* ctx, Kern kern, size_t smem, int* blocks_per_sm) {
@@ -226,7 +226,7 @@ int env_int(const char* name, int dflt) {
 template <int BLOCK, int MINB>
 int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WaveParams)) {
     *kern = wf_cull<kR, BLOCK, MINB>;
-    *smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * BLOCK * sizeof(uint16_t);
+    *smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * BLOCK * sizeof(uint32_t);
     RT_CUDA(ctx, cudaFuncSetAttribute(*kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, *kern, BLOCK, *smem));
     if (*bps < 1) return fail(ctx, RT_ERR_CUDA, "cull kernel does not fit on an SM");
@@ -249,6 +249,8 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     else if (shape == "256x3") rc = cull_config<256, 3>(ctx, &smem, &bps, &cull);
     else if (shape == "128x4") { rc = cull_config<128, 4>(ctx, &smem, &bps, &cull); cull_block = 128; }
     else if (shape == "128x6") { rc = cull_config<128, 6>(ctx, &smem, &bps, &cull); cull_block = 128; }
+    else if (shape == "128x7") { rc = cull_config<128, 7>(ctx, &smem, &bps, &cull); cull_block = 128; }
+    else if (shape == "128x8") { rc = cull_config<128, 8>(ctx, &smem, &bps, &cull); cull_block = 128; }
     else { rc = cull_config<128, 5>(ctx, &smem, &bps, &cull); cull_block = 128; }
     if (rc) return rc;
     static const int cull_ctas_env = env_int("RT_CULL_CTAS_PER_SM", 4);   // one fewer than the occupancy limit leaves
@@ -260,7 +262,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
 
     // cooperative tail kernel: every CTA must be resident, also next to the other lane's tail
     static const unsigned tail_entries = (unsigned)std::max(0, env_int("RT_TAIL_ENTRIES", (int)kTailEntries));
-    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * 256 * sizeof(uint16_t);
+    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * 256 * sizeof(uint32_t);
     int tail_bps = 0, coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d.dev);
     RT_CUDA(ctx, cudaFuncSetAttribute(wf_tail<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));

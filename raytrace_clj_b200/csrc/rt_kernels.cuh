@@ -50,7 +50,7 @@ struct RenderParams {
 // key >= 0  <=>  (approaching and discriminant >= 0) or (origin inside the sphere): exactly the
 // spheres that can have a root in front of the origin; r2i is inflated and h is scaled up so
 // rounding can only add false positives.  No branch: the sign bits of the R keys are funnel-
-// shifted onto the sphere index, the 16-bit entry (k << R | signs) is stored unconditionally to
+// shifted onto the sphere index, the 32-bit entry (k << R | signs; one bank per lane) is stored unconditionally to
 // the thread's shared-memory list and the list pointer advances only if some ray survived.
 // The Sink decides what happens to the survivors when the list fills / a sphere class ends.
 // ------------------------------------------------------------------------------------------
@@ -98,14 +98,14 @@ struct Culler {
 
     // The list pointer is a byte address in the shared window (one LEA less per sphere than indexing).
     static __device__ __forceinline__ void push_entry(unsigned& ptr, unsigned acc) {
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(ptr), "h"((unsigned short)acc) : "memory");
-        if ((~acc) & SIGN_MASK) ptr += BLOCK * 2;   // some ray's key has a clear sign bit: keep the entry
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(acc) : "memory");
+        if ((~acc) & SIGN_MASK) ptr += BLOCK * 4;   // some ray's key has a clear sign bit: keep the entry
     }
-    static __device__ __forceinline__ unsigned list_begin(const uint16_t* list) {
+    static __device__ __forceinline__ unsigned list_begin(const uint32_t* list) {
         return (unsigned)__cvta_generic_to_shared(list + threadIdx.x);
     }
-    static __device__ __forceinline__ int list_count(const uint16_t* list, unsigned ptr) {
-        return (int)(ptr - list_begin(list)) / (BLOCK * 2);
+    static __device__ __forceinline__ int list_count(const uint32_t* list, unsigned ptr) {
+        return (int)(ptr - list_begin(list)) / (BLOCK * 4);
     }
     // survivors of a list entry: bit r set = ray r passed the cull (entry bit R-1-r is its key's sign)
     static __device__ __forceinline__ unsigned survivors(unsigned e) { return (~__brev(e) >> (32 - R)) & SIGN_MASK; }
@@ -128,8 +128,8 @@ struct Culler {
     }
     template <class Sink>
     __device__ __forceinline__ void cull_static(const DevScene& sc, const float4* __restrict__ s, int count, int kbase,
-                                                uint16_t* list, unsigned& ptr, Sink& sink) {
-        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 2;
+                                                uint32_t* list, unsigned& ptr, Sink& sink) {
+        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 4;
         unsigned sa = smem_addr(s);
         int k = 0;
         for (; k + LIST_GUARD <= count; k += LIST_GUARD, sa += 16 * LIST_GUARD) {
@@ -137,9 +137,9 @@ struct Culler {
             for (int u = 0; u < LIST_GUARD; u += 2) {
                 const unsigned a0 = test_sphere(sa + 16 * u, (unsigned)(k + u));
                 const unsigned a1 = test_sphere(sa + 16 * u + 16, (unsigned)(k + u + 1));
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(ptr), "h"((unsigned short)a0) : "memory");
-                asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(ptr), "h"((unsigned short)a1), "n"(BLOCK * 2) : "memory");
-                if (~(a0 & a1) & SIGN_MASK) ptr += BLOCK * 4;   // a survivor in either: keep both entries
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(a0) : "memory");
+                asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(ptr), "r"(a1), "n"(BLOCK * 4) : "memory");
+                if (~(a0 & a1) & SIGN_MASK) ptr += BLOCK * 8;   // a survivor in either: keep both entries
             }
             if (__any_sync(0xffffffffu, ptr > limit)) {   // warp-uniform: sinks may use warp collectives
                 sink.flush(*this, sc, list, list_count(list, ptr), kbase);
@@ -156,7 +156,7 @@ struct Culler {
     // Moving spheres are culled as the static bounding sphere of their swept volume (the FP64 refine
     // evaluates the exact moving sphere), so there is ONE hot loop.
     template <class Sink>
-    __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint16_t* list,
+    __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint32_t* list,
                                         Sink& sink) {
         pin();
         unsigned ptr = list_begin(list);
@@ -174,7 +174,7 @@ struct Culler {
     // Preloaded scene only: this warp tests slice `part` of `parts` of the sphere list (a short queue is
     // spread over more warps by splitting the list; PairSink merges the results).
     template <class Sink>
-    __device__ __forceinline__ void run_slice(const DevScene& sc, float4* s_cull, uint16_t* list, Sink& sink, int part,
+    __device__ __forceinline__ void run_slice(const DevScene& sc, float4* s_cull, uint32_t* list, Sink& sink, int part,
                                               int parts) {
         pin();
         unsigned ptr = list_begin(list);
@@ -209,7 +209,7 @@ struct RefineSink {
         }
     }
 
-    __device__ __forceinline__ void flush(const Culler<R, BLOCK>& C, const DevScene& sc, const uint16_t* list, int count,
+    __device__ __forceinline__ void flush(const Culler<R, BLOCK>& C, const DevScene& sc, const uint32_t* list, int count,
                                           int kbase) {
         int i = 0;
         unsigned e = 0, pend = 0;   // pend: rays of the current entry still to refine (bit r = ray r)
@@ -368,7 +368,7 @@ struct PairSink {
     unsigned n;                    // live entries in the queue
     const WaveParams* W;
 
-    __device__ __forceinline__ void flush(const Culler<R, BLOCK>&, const DevScene&, const uint16_t* list, int count,
+    __device__ __forceinline__ void flush(const Culler<R, BLOCK>&, const DevScene&, const uint32_t* list, int count,
                                           int kbase) {
         const unsigned lane = threadIdx.x & 31u;
         unsigned np = 0;
@@ -408,7 +408,7 @@ struct PairSink {
 
 template <int R, int BLOCK>
 __device__ __forceinline__ void wf_cull_batches(const WaveParams& W, int cur, unsigned n, int parts, float4* s_cull,
-                                                uint16_t* s_list) {
+                                                uint32_t* s_list) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
     const unsigned n_batches = (n + 32 * R - 1) / (32 * R);
@@ -453,7 +453,7 @@ __device__ __forceinline__ void wf_cull_batches(const WaveParams& W, int cur, un
 // grid gets at least two one-ray batches' worth; below that 1 ray per thread, and below THAT the sphere
 // list is split across warps too (the pairs merge in wf_refine).  R = 1 instantiates only the short form.
 template <int R, int BLOCK>
-__device__ __forceinline__ void wf_cull_body(const WaveParams& W, int cur, unsigned n, float4* s_cull, uint16_t* s_list) {
+__device__ __forceinline__ void wf_cull_body(const WaveParams& W, int cur, unsigned n, float4* s_cull, uint32_t* s_list) {
     const RenderParams& P = W.base;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
     const unsigned grid_warps = gridDim.x * (BLOCK / 32);
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     const unsigned n = W.st->qcount[W.cur];
     if (n == 0) return;
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     __shared__ unsigned s_ctr[DC_COUNT];
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
@@ -696,7 +696,7 @@ template <int R, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P) {
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     __shared__ unsigned s_ctr[DC_COUNT];
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
@@ -825,7 +825,7 @@ template <int R, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem_f4 + P.cull_cap);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
     Culler<R, BLOCK> K;
