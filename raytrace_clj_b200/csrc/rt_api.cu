@@ -650,13 +650,19 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     // blob layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_cull_a = take((size_t)n * 16);
+    const int n_cull = (int)align_up((size_t)n, GROUP);
+    size_t o_cull_a = take((size_t)n_cull * 16);
     size_t o_c0r = take((size_t)n * 16), o_c1 = take((size_t)n * 16), o_t0t1 = take((size_t)n * 8);
     size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n * 4), o_mat = take((size_t)n * 4);
     size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);
     size_t o_ttype = take((size_t)std::max(nt, 1) * 4), o_tparam = take((size_t)std::max(nt, 1) * 48), o_tchild = take((size_t)std::max(nt, 1) * 8);
     std::vector<unsigned char> blob(off, 0);
     build_cull_records(ctx, n, win_lo, win_hi, (float*)(blob.data() + o_cull_a));
+    for (int k = n; k < n_cull; ++k) {   // padding: r^2 = -inf, the key is -inf for every ray
+        float* rec = (float*)(blob.data() + o_cull_a) + 4 * (size_t)k;
+        rec[0] = rec[1] = rec[2] = 0.f;
+        rec[3] = -INFINITY;
+    }
     memcpy(blob.data() + o_c0r, ctx->h_c0r.data(), (size_t)n * 16);
     memcpy(blob.data() + o_c1, ctx->h_c1.data(), (size_t)n * 16);
     memcpy(blob.data() + o_t0t1, ctx->h_t0t1.data(), (size_t)n * 8);
@@ -684,6 +690,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         char* b = (char*)d.scene_blob;
         DevScene& sc = d.sc;
         sc.n = n;
+        sc.n_cull = n_cull;
         sc.cull_a = (const float4*)(b + o_cull_a);
         sc.ex_c0r = (const float4*)(b + o_c0r); sc.ex_c1 = (const float4*)(b + o_c1); sc.ex_t0t1 = (const float2*)(b + o_t0t1);
         sc.orig_id = (const int*)(b + o_orig); sc.cull_of_orig = (const int*)(b + o_cull_of);
@@ -693,8 +700,8 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     }
     cudaSetDevice(ctx->devs[0].dev);
     ctx->n_spheres = n;
-    ctx->preloaded = n <= kTileCap ? 1 : 0;
-    ctx->cull_cap = ctx->preloaded ? (int)align_up((size_t)n, 8) : kTileCap;
+    ctx->preloaded = n_cull <= kTileCap ? 1 : 0;
+    ctx->cull_cap = ctx->preloaded ? n_cull : kTileCap;
     ctx->win_lo = win_lo;
     ctx->win_hi = win_hi;
     ctx->has_scene = true;

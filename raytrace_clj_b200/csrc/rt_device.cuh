@@ -41,7 +41,8 @@ enum { DC_RAYS = 0, DC_SAMPLES, DC_TERM_LIGHT, DC_TERM_ABSORB, DC_TERM_DEPTH, DC
 // Scene in HBM.  "Cull order" is the caller's order (orig_id is the identity today; kept so a future
 // reordering, e.g. for locality, does not touch the kernels).
 struct DevScene {
-    int n;
+    int n;                    // spheres
+    int n_cull;               // cull records: n rounded up to a multiple of 16 (padding never survives)
     const float4* cull_a;     // [n] (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its
                               //     swept volume over the time window the context covers
     const float4* ex_c0r;     // [n] exact centre0 + radius   (float32 as marshalled)

@@ -71,12 +71,13 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) {
 __device__ __forceinline__ int slice_lo(int n, int part, int parts) { return (int)(((long long)n * part) / parts); }
 
 constexpr int LIST_K = 32;       // entries per thread
-constexpr int LIST_GUARD = 4;    // spheres between two list-full checks (= unroll group)
+constexpr int GROUP = 16;        // spheres per list entry; the cull records are padded to a multiple of GROUP
 
+// List entry (32 bits, one shared-memory bank per lane): (group << 2 | ray) << 16 | 16 sign bits, the sign of
+// sphere j of the group at bit 15 - j; a clear bit = that (ray, sphere) pair survived the cull.
 template <int R, int BLOCK>
 struct Culler {
-    static_assert(R == 1 || R == 2 || R == 4, "entry layout holds up to 4 sign bits");
-    static constexpr unsigned SIGN_MASK = (1u << R) - 1u;
+    static_assert(R == 1 || R == 2 || R == 4, "entry header holds 2 ray bits");
     float ox[R], oy[R], oz[R];     // origin
     float hx[R], hy[R], hz[R];     // cull direction: d * sqrt(1 + eps) / |d|
     float tm[R];                   // kept for the sinks (the cull itself is time-free)
@@ -96,19 +97,18 @@ struct Culler {
         RT_FOR_R asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]), "+f"(ox[r]), "+f"(oy[r]), "+f"(oz[r]), "+f"(tm[r]));
     }
 
-    // The list pointer is a byte address in the shared window (one LEA less per sphere than indexing).
-    static __device__ __forceinline__ void push_entry(unsigned& ptr, unsigned acc) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(acc) : "memory");
-        if ((~acc) & SIGN_MASK) ptr += BLOCK * 4;   // some ray's key has a clear sign bit: keep the entry
-    }
     static __device__ __forceinline__ unsigned list_begin(const uint32_t* list) {
         return (unsigned)__cvta_generic_to_shared(list + threadIdx.x);
     }
     static __device__ __forceinline__ int list_count(const uint32_t* list, unsigned ptr) {
         return (int)(ptr - list_begin(list)) / (BLOCK * 4);
     }
-    // survivors of a list entry: bit r set = ray r passed the cull (entry bit R-1-r is its key's sign)
-    static __device__ __forceinline__ unsigned survivors(unsigned e) { return (~__brev(e) >> (32 - R)) & SIGN_MASK; }
+    // decode an entry: ray, first sphere of its group, and the survivors as a bit set (bit j = sphere j of the group)
+    static __device__ __forceinline__ void decode(unsigned e, int& r, int& k0, unsigned& surv) {
+        r = (int)((e >> 16) & 3u);
+        k0 = (int)(e >> 18) * GROUP;
+        surv = (~__brev(e) >> 16) & 0xffffu;     // entry bit 15 - j -> bit j, inverted: 1 = survivor
+    }
 
     __device__ __forceinline__ unsigned key_bits(float fx, float fy, float fz, float r2i, int r) const {
         float b = fmaf(fz, hz[r], fmaf(fy, hy[r], fx * hx[r]));
@@ -116,43 +116,38 @@ struct Culler {
         return __float_as_uint(fmaf(b, fminf(b, 0.f), nc));
     }
 
-    // s[k] = (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its sweep.
-    // Spheres go two at a time: both entries are stored, ONE test decides whether the list pointer moves
-    // past both (an entry without survivors that rides along is skipped by the sink); the list-full
-    // check runs every LIST_GUARD spheres.
-    __device__ __forceinline__ unsigned test_sphere(unsigned sa, unsigned k) const {
-        const float4 S = lds128(sa);
-        unsigned acc = k;
-        RT_FOR_R acc = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc, 1);
-        return acc;
-    }
+    // s[k] = (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its sweep; `count` is a
+    // multiple of GROUP (padding records have r2 = -inf and never survive).  Per test: 11 FP32 instructions +
+    // ONE funnel shift that appends the key's sign to the ray's running mask; per GROUP spheres each ray's
+    // entry is stored and the list pointer bumped if any of its 16 tests survived.
     template <class Sink>
     __device__ __forceinline__ void cull_static(const DevScene& sc, const float4* __restrict__ s, int count, int kbase,
                                                 uint32_t* list, unsigned& ptr, Sink& sink) {
-        const unsigned limit = list_begin(list) + (LIST_K - LIST_GUARD) * BLOCK * 4;
+        const unsigned limit = list_begin(list) + (LIST_K - R) * BLOCK * 4;
         unsigned sa = smem_addr(s);
-        int k = 0;
-        for (; k + LIST_GUARD <= count; k += LIST_GUARD, sa += 16 * LIST_GUARD) {
-#pragma unroll
-            for (int u = 0; u < LIST_GUARD; u += 2) {
-                const unsigned a0 = test_sphere(sa + 16 * u, (unsigned)(k + u));
-                const unsigned a1 = test_sphere(sa + 16 * u + 16, (unsigned)(k + u + 1));
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(a0) : "memory");
-                asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(ptr), "r"(a1), "n"(BLOCK * 4) : "memory");
-                if (~(a0 & a1) & SIGN_MASK) ptr += BLOCK * 8;   // a survivor in either: keep both entries
+        for (int k = 0; k < count; k += GROUP) {
+            unsigned acc[R];
+            RT_FOR_R acc[r] = (unsigned)((k / GROUP) * 4 + r);
+#pragma unroll 4
+            for (int u = 0; u < GROUP; ++u, sa += 16) {
+                const float4 S = lds128(sa);
+                RT_FOR_R acc[r] = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc[r], 1);
+            }
+            RT_FOR_R {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(acc[r]) : "memory");
+                if ((~acc[r]) & 0xffffu) ptr += BLOCK * 4;   // some test of this ray survived: keep the entry
             }
             if (__any_sync(0xffffffffu, ptr > limit)) {   // warp-uniform: sinks may use warp collectives
                 sink.flush(*this, sc, list, list_count(list, ptr), kbase);
                 ptr = list_begin(list);
             }
         }
-        for (; k < count; ++k, sa += 16) push_entry(ptr, test_sphere(sa, (unsigned)k));
         sink.flush(*this, sc, list, list_count(list, ptr), kbase);
         ptr = list_begin(list);
     }
 
     // Whole scene.  In tiled mode every thread of the CTA must call it (tile loads use __syncthreads).
-    // A preloaded scene is a single resident tile s_cull[0, n); a tiled scene streams tiles of `cap` spheres.
+    // A preloaded scene is a single resident tile s_cull[0, n_cull); a tiled scene streams tiles of `cap` spheres.
     // Moving spheres are culled as the static bounding sphere of their swept volume (the FP64 refine
     // evaluates the exact moving sphere), so there is ONE hot loop.
     template <class Sink>
@@ -160,8 +155,8 @@ struct Culler {
                                         Sink& sink) {
         pin();
         unsigned ptr = list_begin(list);
-        for (int base = 0; base < sc.n; base += cap) {
-            int count = min(cap, sc.n - base);
+        for (int base = 0; base < sc.n_cull; base += cap) {
+            int count = min(cap, sc.n_cull - base);
             if (!preloaded) {
                 __syncthreads();
                 for (int i = threadIdx.x; i < count; i += BLOCK) s_cull[i] = __ldg(&sc.cull_a[base + i]);
@@ -171,20 +166,21 @@ struct Culler {
         }
     }
 
-    // Preloaded scene only: this warp tests slice `part` of `parts` of the sphere list (a short queue is
+    // Preloaded scene only: this warp tests slice `part` of `parts` of the sphere groups (a short queue is
     // spread over more warps by splitting the list; PairSink merges the results).
     template <class Sink>
     __device__ __forceinline__ void run_slice(const DevScene& sc, float4* s_cull, uint32_t* list, Sink& sink, int part,
                                               int parts) {
         pin();
         unsigned ptr = list_begin(list);
-        const int s0 = slice_lo(sc.n, part, parts), s1 = slice_lo(sc.n, part + 1, parts);
+        const int groups = sc.n_cull / GROUP;
+        const int s0 = slice_lo(groups, part, parts) * GROUP, s1 = slice_lo(groups, part + 1, parts) * GROUP;
         cull_static(sc, s_cull + s0, s1 - s0, s0, list, ptr, sink);
     }
 };
 
 __device__ __forceinline__ void preload_scene(const DevScene& sc, float4* s_cull, int block) {
-    for (int i = threadIdx.x; i < sc.n; i += block) s_cull[i] = __ldg(&sc.cull_a[i]);
+    for (int i = threadIdx.x; i < sc.n_cull; i += block) s_cull[i] = __ldg(&sc.cull_a[i]);
     __syncthreads();
 }
 
@@ -211,18 +207,17 @@ struct RefineSink {
 
     __device__ __forceinline__ void flush(const Culler<R, BLOCK>& C, const DevScene& sc, const uint32_t* list, int count,
                                           int kbase) {
-        int i = 0;
-        unsigned e = 0, pend = 0;   // pend: rays of the current entry still to refine (bit r = ray r)
+        int i = 0, r = 0, k0 = 0;
+        unsigned pend = 0;   // spheres of the current entry's group still to refine (bit j = sphere j)
         for (;;) {
             while (pend == 0 && i < count) {
-                e = list[i * BLOCK + threadIdx.x];
+                Culler<R, BLOCK>::decode(list[i * BLOCK + threadIdx.x], r, k0, pend);
                 ++i;
-                pend = Culler<R, BLOCK>::survivors(e);
             }
             if (pend == 0) break;
-            const int r = __ffs(pend) - 1;
+            const int j = __ffs(pend) - 1;
             pend &= pend - 1;
-            const int k = kbase + (int)(e >> R);
+            const int k = kbase + k0 + j;
             float sox = C.ox[0], soy = C.oy[0], soz = C.oz[0], sdx = dx[0], sdy = dy[0], sdz = dz[0], stm = C.tm[0];
 #pragma unroll
             for (int q = 1; q < R; ++q)
@@ -372,7 +367,7 @@ struct PairSink {
                                           int kbase) {
         const unsigned lane = threadIdx.x & 31u;
         unsigned np = 0;
-        for (int i = 0; i < count; ++i) np += __popc(Culler<R, BLOCK>::survivors(list[i * BLOCK + threadIdx.x]));
+        for (int i = 0; i < count; ++i) np += __popc((~list[i * BLOCK + threadIdx.x]) & 0xffffu);
         unsigned incl = np;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -387,15 +382,15 @@ struct PairSink {
         const bool fits = base + total <= W->pair_cap;
         unsigned w = base + incl - np;
         for (int i = 0; i < count; ++i) {
-            unsigned e = list[i * BLOCK + threadIdx.x];
-            unsigned pend = Culler<R, BLOCK>::survivors(e);
-            const unsigned k = (unsigned)kbase + (e >> R);
+            int r, k0;
+            unsigned pend;
+            Culler<R, BLOCK>::decode(list[i * BLOCK + threadIdx.x], r, k0, pend);
+            const unsigned idx = idx0 + 32u * (unsigned)r;
             while (pend) {
-                const int r = __ffs(pend) - 1;
+                const int j = __ffs(pend) - 1;
                 pend &= pend - 1;
-                const unsigned idx = idx0 + 32u * (unsigned)r;
                 if (fits) {
-                    W->pairs[w] = make_uint2(idx, k);
+                    W->pairs[w] = make_uint2(idx, (unsigned)(kbase + k0 + j));
                 } else {
                     if (w < W->pair_cap) W->pairs[w] = make_uint2(PAIR_NULL, 0u);
                     if (idx < n) W->best_key[idx] = BEST_KEY_OVERFLOW;
