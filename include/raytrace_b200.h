@@ -165,6 +165,13 @@ int rt_trace_primary(rt_ctx* ctx, int n, const float* origins /*3n*/, const floa
                      const float* times /*n or NULL*/, double tmin, double tmax,
                      double* out_t, int32_t* out_id);
 
+/* The contract of the FP32 cull (the brute-force loop over the sphere list), checked pair by pair on the
+ * device: out[0] = (ray, listed sphere) pairs whose exact FP64 test (hitable.clj:185-206) accepts a root in
+ * (tmin, tmax) but whose FP32 cull key says "cannot hit" — must be 0; out[1] = pairs the cull lets through;
+ * out[2] = pairs the exact test accepts.  tmin >= 0 (as for rt_trace_primary).                            */
+int rt_cull_check(rt_ctx* ctx, int n, const float* origins /*3n*/, const float* dirs /*3n*/,
+                  const float* times /*n or NULL*/, double tmin, double tmax, uint64_t out[3]);
+
 /* Camera rays exactly as the render kernels generate them for (pixel i, j, sample s):
  * out_origin/out_dir 3n floats, out_time n floats; ij is 2n int32 (i, j), s is n int32.
  * out_rand (5n floats or NULL) receives the uniforms the ray was built from:

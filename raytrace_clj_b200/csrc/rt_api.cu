@@ -80,11 +80,12 @@ struct rt_ctx {
     std::vector<DeviceBuffers> devs;
     bool has_scene = false, has_cam = false;
     int n_spheres = 0;
+    int n_list = 0, n_cull = 0;   // spheres in the cull list / cull records (padded)
     int cull_cap = 0, preloaded = 0;
     // time window [win_lo, win_hi] the movers' bounding spheres cover; grown (and the cull records rebuilt)
     // when a camera shutter interval or a traced ray's time falls outside
     double win_lo = 0.0, win_hi = 0.0;
-    std::vector<float> h_c0r, h_c1, h_t0t1;
+    std::vector<float> h_c0r, h_c1, h_t0t1;   // geometry in cull order
     std::vector<unsigned> h_flags;
     DevCamera cam{};
     std::atomic<uint64_t> n_launches{0};
@@ -201,7 +202,7 @@ float round_up_f32(double x) {
     return f;
 }
 
-size_t mega_smem_bytes(int cull_cap) { return (size_t)cull_cap * sizeof(float4) + (size_t)LIST_K * kBlock * sizeof(uint32_t); }
+size_t mega_smem_bytes(int cull_cap) { return (size_t)cull_cap * sizeof(float4) + Culler<kR, kBlock>::LIST_BYTES; }
 
 template <typename Kern>
 int configure_kernel(rt_ctx* ctx, Kern kern, size_t smem, int* blocks_per_sm) {
@@ -226,7 +227,7 @@ int env_int(const char* name, int dflt) {
 template <int BLOCK, int MINB>
 int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WaveParams)) {
     *kern = wf_cull<kR, BLOCK, MINB>;
-    *smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * BLOCK * sizeof(uint32_t);
+    *smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<kR, BLOCK>::LIST_BYTES;
     RT_CUDA(ctx, cudaFuncSetAttribute(*kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, *kern, BLOCK, *smem));
     if (*bps < 1) return fail(ctx, RT_ERR_CUDA, "cull kernel does not fit on an SM");
@@ -262,7 +263,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
 
     // cooperative tail kernel: every CTA must be resident, also next to the other lane's tail
     static const unsigned tail_entries = (unsigned)std::max(0, env_int("RT_TAIL_ENTRIES", (int)kTailEntries));
-    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + (size_t)LIST_K * 256 * sizeof(uint32_t);
+    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<1, 256>::LIST_BYTES;
     int tail_bps = 0, coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d.dev);
     RT_CUDA(ctx, cudaFuncSetAttribute(wf_tail<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
@@ -424,13 +425,15 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
     return launch_wave(ctx, d, P, want, stream);
 }
 
-// FP32 cull record per sphere: (-cx, -cy, -cz, r^2 inflated).  A moving sphere (hitable.clj:224-259) is
-// represented by the bounding sphere of its swept volume over [win_lo, win_hi]: centre = midpoint of
-// centre(win_lo), centre(win_hi), radius = r + half the travelled distance.  Inflation covers float rounding
-// of the record itself plus the cull's own rounding (CULL_EPS), so the cull only ever over-reports.
-void build_cull_records(const rt_ctx* ctx, int n, double win_lo, double win_hi, float* cull_a) {
-    const double eps = (double)CULL_EPS;
-    for (int i = 0; i < n; ++i) {
+// FP32 cull record per listed sphere: (-cx, -cy, -cz, W = r^2 inflated - c.c) (Culler, rt_kernels.cuh).  A moving
+// sphere (hitable.clj:224-259) is represented by the bounding sphere of its swept volume over [win_lo, win_hi]:
+// centre = midpoint of centre(win_lo), centre(win_hi), radius = r + half the travelled distance.  The inflation
+// covers the float rounding of the record itself and the sphere's share of the cull's rounding budget
+// (48 u c.c + 8 u r^2, u = 2^-24; the bound is 32.6 u c.c + 4.1 u r^2), so the cull only ever over-reports.
+// Records [n_list, n_cull) are padding: W = -inf, the key is -inf for every ray.
+void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* cull_a) {
+    const double eps = std::ldexp(1.0, -20), u = std::ldexp(1.0, -24);
+    for (int i = 0; i < ctx->n_list; ++i) {
         double r = std::fabs((double)ctx->h_c0r[4 * i + 3]);
         double mid[3], half2 = 0.0, cmax = 0.0;
         const bool moving = (ctx->h_flags[i] & RT_SPHERE_MOVING) != 0;
@@ -449,9 +452,19 @@ void build_cull_records(const rt_ctx* ctx, int n, double win_lo, double win_hi, 
         }
         double rb = r + std::sqrt(half2);
         double e = moving ? std::ldexp(1.0, -21) * (cmax + rb) : 0.0;   // float rounding of the midpoint (+ margin)
-        for (int c = 0; c < 3; ++c) cull_a[4 * i + c] = (float)(-mid[c]);   // negated: f = o + (-c)
+        double cc = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            const float neg = (float)(-mid[c]);       // negated: the chains are seeded FFMAs on -c
+            cull_a[4 * i + c] = neg;
+            cc += (double)neg * (double)neg;          // c.c of the record AS STORED
+        }
         double re = rb + e;
-        cull_a[4 * i + 3] = round_up_f32(re * re * (1.0 + eps));
+        double r2i = re * re * (1.0 + eps) + 48.0 * u * cc + 8.0 * u * re * re;
+        cull_a[4 * i + 3] = round_up_f32(r2i - cc);
+    }
+    for (int k = ctx->n_list; k < ctx->n_cull; ++k) {
+        cull_a[4 * k] = cull_a[4 * k + 1] = cull_a[4 * k + 2] = 0.f;
+        cull_a[4 * k + 3] = -INFINITY;
     }
 }
 
@@ -464,8 +477,9 @@ int ensure_window(rt_ctx* ctx, double lo, double hi) {
     bool any_moving = false;
     for (unsigned f : ctx->h_flags) any_moving |= (f & RT_SPHERE_MOVING) != 0;
     if (!any_moving) return RT_OK;
-    std::vector<float> cull((size_t)ctx->n_spheres * 4);
-    build_cull_records(ctx, ctx->n_spheres, ctx->win_lo, ctx->win_hi, cull.data());
+    std::vector<float> cull((size_t)ctx->n_cull * 4);
+    build_cull_records(ctx, ctx->win_lo, ctx->win_hi, cull.data());
+    if (cull.empty()) return RT_OK;
     for (auto& d : ctx->devs) {
         RT_CUDA(ctx, cudaSetDevice(d.dev));
         RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
@@ -633,44 +647,84 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         win_hi = std::max(win_hi, hi);
     }
 
-    // host copy of the geometry: the cull records are rebuilt when the time window has to grow
-    ctx->h_c0r.assign(s->center0_r, s->center0_r + 4 * (size_t)n);
+    // Cull order: listed spheres first (caller's order), then the "direct" spheres that bypass the cull.  A sphere
+    // is direct when it is large against the population (radius >= 8 x the median) and encloses or touches the
+    // centroid of the small spheres (a sky dome, a ground sphere): nearly every ray starts inside it or on it, so
+    // the cull would pass it anyway.  The choice changes the work split only — results are identical either way.
+    std::vector<int> perm((size_t)n);
+    int n_direct = 0;
+    {
+        std::vector<char> direct((size_t)n, 0);
+        static const int direct_env = env_int("RT_DIRECT_SPHERES", 1);
+        if (n > 16 && direct_env) {
+            std::vector<double> radii((size_t)n);
+            for (int i = 0; i < n; ++i) radii[(size_t)i] = std::fabs((double)s->center0_r[4 * i + 3]);
+            std::vector<double> sorted = radii;
+            std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());
+            const double big = 8.0 * sorted[(size_t)n / 2];
+            double cen[3] = {0, 0, 0};
+            int small = 0;
+            for (int i = 0; i < n; ++i)
+                if (radii[(size_t)i] < big) {
+                    for (int c = 0; c < 3; ++c) cen[c] += s->center0_r[4 * i + c];
+                    ++small;
+                }
+            for (int c = 0; c < 3; ++c) cen[c] /= std::max(1, small);
+            std::vector<std::pair<double, int>> cand;
+            for (int i = 0; i < n; ++i) {
+                if (radii[(size_t)i] < big) continue;
+                double d2 = 0.0;
+                for (int c = 0; c < 3; ++c) { double x = s->center0_r[4 * i + c] - cen[c]; d2 += x * x; }
+                if (std::sqrt(d2) <= 1.05 * radii[(size_t)i]) cand.emplace_back(-radii[(size_t)i], i);
+            }
+            std::sort(cand.begin(), cand.end());
+            for (size_t q = 0; q < cand.size() && q < 8; ++q) { direct[(size_t)cand[q].second] = 1; ++n_direct; }
+        }
+        int k = 0;
+        for (int i = 0; i < n; ++i) if (!direct[(size_t)i]) perm[(size_t)k++] = i;
+        for (int i = 0; i < n; ++i) if (direct[(size_t)i]) perm[(size_t)k++] = i;
+    }
+    const int n_list = n - n_direct;
+    const int n_cull = (int)align_up((size_t)n_list, CULL_PAD);
+
+    // host copy of the geometry (cull order): the cull records are rebuilt when the time window has to grow
+    ctx->h_c0r.assign(4 * (size_t)n, 0.f);
     ctx->h_c1.assign(4 * (size_t)n, 0.f);
     ctx->h_t0t1.assign(2 * (size_t)n, 0.f);
     ctx->h_flags.assign((size_t)n, 0u);
-    for (int i = 0; i < n; ++i) {
+    std::vector<int> h_mat((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        const int i = perm[(size_t)k];
         unsigned fl = s->sphere_flags ? s->sphere_flags[i] : 0u;
         bool moving = (fl & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
-        ctx->h_flags[i] = moving ? fl : (fl & ~RT_SPHERE_MOVING);
-        for (int c = 0; c < 3; ++c) ctx->h_c1[4 * i + c] = moving ? s->center1[4 * i + c] : s->center0_r[4 * i + c];
-        ctx->h_t0t1[2 * i] = moving ? s->t0t1[2 * i] : 0.f;
-        ctx->h_t0t1[2 * i + 1] = moving ? s->t0t1[2 * i + 1] : 1.f;
+        ctx->h_flags[k] = moving ? fl : (fl & ~RT_SPHERE_MOVING);
+        for (int c = 0; c < 4; ++c) ctx->h_c0r[4 * k + c] = s->center0_r[4 * i + c];
+        for (int c = 0; c < 3; ++c) ctx->h_c1[4 * k + c] = moving ? s->center1[4 * i + c] : s->center0_r[4 * i + c];
+        ctx->h_t0t1[2 * k] = moving ? s->t0t1[2 * i] : 0.f;
+        ctx->h_t0t1[2 * k + 1] = moving ? s->t0t1[2 * i + 1] : 1.f;
+        h_mat[(size_t)k] = s->material_id[i];
     }
+    ctx->n_list = n_list;
+    ctx->n_cull = n_cull;
 
     // blob layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const int n_cull = (int)align_up((size_t)n, GROUP);
-    size_t o_cull_a = take((size_t)n_cull * 16);
+    size_t o_cull_a = take((size_t)std::max(n_cull, 1) * 16);
     size_t o_c0r = take((size_t)n * 16), o_c1 = take((size_t)n * 16), o_t0t1 = take((size_t)n * 8);
     size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n * 4), o_mat = take((size_t)n * 4);
     size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);
     size_t o_ttype = take((size_t)std::max(nt, 1) * 4), o_tparam = take((size_t)std::max(nt, 1) * 48), o_tchild = take((size_t)std::max(nt, 1) * 8);
     std::vector<unsigned char> blob(off, 0);
-    build_cull_records(ctx, n, win_lo, win_hi, (float*)(blob.data() + o_cull_a));
-    for (int k = n; k < n_cull; ++k) {   // padding: r^2 = -inf, the key is -inf for every ray
-        float* rec = (float*)(blob.data() + o_cull_a) + 4 * (size_t)k;
-        rec[0] = rec[1] = rec[2] = 0.f;
-        rec[3] = -INFINITY;
-    }
+    build_cull_records(ctx, win_lo, win_hi, (float*)(blob.data() + o_cull_a));
     memcpy(blob.data() + o_c0r, ctx->h_c0r.data(), (size_t)n * 16);
     memcpy(blob.data() + o_c1, ctx->h_c1.data(), (size_t)n * 16);
     memcpy(blob.data() + o_t0t1, ctx->h_t0t1.data(), (size_t)n * 8);
     memcpy(blob.data() + o_flags, ctx->h_flags.data(), (size_t)n * 4);
     int* orig = (int*)(blob.data() + o_orig);
     int* cull_of = (int*)(blob.data() + o_cull_of);
-    for (int k = 0; k < n; ++k) orig[k] = cull_of[k] = k;   // cull order = caller order
-    memcpy(blob.data() + o_mat, s->material_id, (size_t)n * 4);
+    for (int k = 0; k < n; ++k) { orig[k] = perm[(size_t)k]; cull_of[perm[(size_t)k]] = k; }
+    memcpy(blob.data() + o_mat, h_mat.data(), (size_t)n * 4);
     memcpy(blob.data() + o_mtype, s->mat_type, (size_t)nm_ * 4);
     memcpy(blob.data() + o_mparam, s->mat_param, (size_t)nm_ * 4);
     memcpy(blob.data() + o_mtex, s->mat_tex, (size_t)nm_ * 4);
@@ -690,6 +744,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         char* b = (char*)d.scene_blob;
         DevScene& sc = d.sc;
         sc.n = n;
+        sc.n_list = n_list;
         sc.n_cull = n_cull;
         sc.cull_a = (const float4*)(b + o_cull_a);
         sc.ex_c0r = (const float4*)(b + o_c0r); sc.ex_c1 = (const float4*)(b + o_c1); sc.ex_t0t1 = (const float2*)(b + o_t0t1);
@@ -701,7 +756,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     cudaSetDevice(ctx->devs[0].dev);
     ctx->n_spheres = n;
     ctx->preloaded = n_cull <= kTileCap ? 1 : 0;
-    ctx->cull_cap = ctx->preloaded ? n_cull : kTileCap;
+    ctx->cull_cap = ctx->preloaded ? std::max(n_cull, CULL_PAD) : kTileCap;
     ctx->win_lo = win_lo;
     ctx->win_hi = win_hi;
     ctx->has_scene = true;
@@ -843,6 +898,7 @@ int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n < 0 || (n > 0 && (!origins || !dirs || !out_t || !out_id))) return fail(ctx, RT_ERR_ARG, "bad trace arguments");
+    if (!(tmin >= 0.0)) return fail(ctx, RT_ERR_ARG, "tmin must be >= 0: the cull discards spheres behind the origin");
     if (n == 0) return RT_OK;
     {
         double lo = 0.0, hi = 0.0;
@@ -879,6 +935,45 @@ int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs
     RT_CUDA(ctx, cudaMemcpyAsync(out_t, d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, d.stream));
     RT_CUDA(ctx, cudaMemcpyAsync(out_id, d_id, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
     RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return RT_OK;
+}
+
+int rt_cull_check(rt_ctx* ctx, int n, const float* origins, const float* dirs, const float* times, double tmin, double tmax,
+                  uint64_t out[3]) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || !out || (n > 0 && (!origins || !dirs))) return fail(ctx, RT_ERR_ARG, "bad cull_check arguments");
+    if (!(tmin >= 0.0)) return fail(ctx, RT_ERR_ARG, "tmin must be >= 0: the cull discards spheres behind the origin");
+    out[0] = out[1] = out[2] = 0;
+    if (n == 0) return RT_OK;
+    {
+        double lo = 0.0, hi = 0.0;
+        if (times) {
+            lo = INFINITY; hi = -INFINITY;
+            for (int i = 0; i < n; ++i) { lo = std::min(lo, (double)times[i]); hi = std::max(hi, (double)times[i]); }
+        }
+        if ((rc = ensure_window(ctx, lo, hi))) return rc;
+    }
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    size_t b_o = align_up((size_t)n * 12, 256), b_t = align_up((size_t)n * 4, 256);
+    if ((rc = ensure_scratch(ctx, d, 2 * b_o + b_t + 256))) return rc;
+    char* base = (char*)d.scratch;
+    float* d_o = (float*)base;
+    float* d_d = (float*)(base + b_o);
+    float* d_tm = (float*)(base + 2 * b_o);
+    unsigned long long* d_out = (unsigned long long*)(base + 2 * b_o + b_t);
+    RT_CUDA(ctx, cudaMemcpyAsync(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
+    if (times) RT_CUDA(ctx, cudaMemcpyAsync(d_tm, times, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
+    RT_CUDA(ctx, cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), d.stream));
+    cull_check_kernel<<<(n + 127) / 128, 128, 0, d.stream>>>(d.sc, n, d_o, d_d, times ? d_tm : nullptr, tmin, tmax, d_out);
+    RT_CUDA(ctx, cudaGetLastError());
+    unsigned long long h[3];
+    RT_CUDA(ctx, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    for (int i = 0; i < 3; ++i) out[i] = h[i];
     return RT_OK;
 }
 

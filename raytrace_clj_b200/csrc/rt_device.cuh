@@ -30,7 +30,7 @@ constexpr int MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE
 constexpr int TEX_CONSTANT = 0, TEX_UV_GRADIENT = 1, TEX_CHECKERBOARD = 2;
 constexpr int CAM_PINHOLE = 0, CAM_THIN_LENS = 1;
 
-// cull tolerances: radius^2 inflated by (1 + CULL_EPS), a = d.d deflated by (1 - CULL_EPS)
+// cull tolerances: the cull direction is scaled up by sqrt(1 + CULL_EPS); see Culler (rt_kernels.cuh)
 constexpr float CULL_EPS = 7.62939453125e-6f;  // 2^-17
 
 enum TermReason { TERM_NONE = 0, TERM_LIGHT = 1, TERM_ABSORB = 2, TERM_DEPTH = 3, TERM_MISS = 4 };
@@ -38,13 +38,16 @@ enum TermReason { TERM_NONE = 0, TERM_LIGHT = 1, TERM_ABSORB = 2, TERM_DEPTH = 3
 // device counter slots (subset of RT_CTR_* that the kernels write)
 enum { DC_RAYS = 0, DC_SAMPLES, DC_TERM_LIGHT, DC_TERM_ABSORB, DC_TERM_DEPTH, DC_TERM_MISS, DC_CANDIDATES, DC_COUNT = 8 };
 
-// Scene in HBM.  "Cull order" is the caller's order (orig_id is the identity today; kept so a future
-// reordering, e.g. for locality, does not touch the kernels).
+// Scene in HBM, every per-sphere array in "cull order": first the n_list spheres the FP32 cull runs over,
+// then the n - n_list "direct" spheres that bypass it (enclosing spheres such as a sky dome or a ground
+// sphere: the cull would pass them for nearly every ray, so they are tested exactly, once per ray, where the
+// closest hit is resolved).  orig_id maps cull order back to the caller's index (ties, reporting).
 struct DevScene {
     int n;                    // spheres
-    int n_cull;               // cull records: n rounded up to a multiple of 16 (padding never survives)
-    const float4* cull_a;     // [n] (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its
-                              //     swept volume over the time window the context covers
+    int n_list;               // spheres in the cull list = cull order [0, n_list)
+    int n_cull;               // cull records: n_list rounded up to a multiple of 8 (padding never survives)
+    const float4* cull_a;     // [n_cull] (-cx, -cy, -cz, W = r2_inflated - c.c); a moving sphere is the bounding
+                              //     sphere of its swept volume over the time window the context covers
     const float4* ex_c0r;     // [n] exact centre0 + radius   (float32 as marshalled)
     const float4* ex_c1;      // [n] exact centre1
     const float2* ex_t0t1;    // [n]

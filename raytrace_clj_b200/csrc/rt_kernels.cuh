@@ -41,18 +41,22 @@ struct RenderParams {
 };
 
 // ------------------------------------------------------------------------------------------
-// Culler: the FP32 test, per (ray, sphere), 11 FP32-pipe instructions = the 17-flop test of
-// SURVEY §8(d) (a = d.d is folded into a per-ray normalised direction h = d * sqrt(1+eps)/|d|):
-//     f   = o + (-c)                      3 FADD
-//     b   = f . h                         1 FMUL + 2 FFMA
-//     nc  = r2i - f . f                   3 FFMA
+// Culler: the FP32 test, per (ray, sphere), 9 FP32-pipe instructions + 1 funnel shift.  The 17-flop
+// test of SURVEY §8(d) is evaluated in expanded form so that everything that depends on the ray alone
+// or on the sphere alone is hoisted (f = o - c never materialises):
+//     b   = o.h - c.h                     3 FFMA   seeded with the ray's  P = o.h
+//     s   = (r2i - c.c) + 2 o.c           3 FFMA   seeded with the sphere's W = r2i - c.c, ray holds m = -2 o
+//     nc  = s - |o|^2                     1 FADD   ray holds Q = |o|^2 (deflated, see below)
 //     key = b * min(b, 0) + nc            1 FMNMX + 1 FFMA
-// key >= 0  <=>  (approaching and discriminant >= 0) or (origin inside the sphere): exactly the
-// spheres that can have a root in front of the origin; r2i is inflated and h is scaled up so
-// rounding can only add false positives.  No branch: the sign bits of the R keys are funnel-
-// shifted onto the sphere index, the 32-bit entry (k << R | signs; one bank per lane) is stored unconditionally to
-// the thread's shared-memory list and the list pointer advances only if some ray survived.
-// The Sink decides what happens to the survivors when the list fills / a sphere class ends.
+// with h = d * sqrt(1+eps) / |d| (a = d.d folded in).  key >= 0  <=>  (approaching and discriminant
+// >= 0) or (origin inside the sphere): exactly the spheres that can have a root in front of the
+// origin.  Rounding: with u = 2^-24 the computed key differs from the exact one by at most
+// u (32.6 |o|^2 + 32.6 |c|^2 + 4.1 r2i) (DESIGN.md "Precision"); the ray's share is taken off Q
+// (Q = |o|^2 (1 - 54 u)), the sphere's share is added to W on the host, so the cull only ever
+// over-reports.  tests/test_gpu_parity.py::test_cull_never_under_reports checks exactly that.
+// No branch and no compaction in the loop: the sign bits of a ray's keys are funnel-shifted into one
+// 32-bit mask per GROUP = 32 spheres, stored at a position that implies (group, ray).  The Sink
+// walks the masks of the groups flagged in a per-thread bitmap after every chunk of <= 512 spheres.
 // ------------------------------------------------------------------------------------------
 // 128-bit shared-memory load from a 32-bit shared-window address (keeps ptxas from re-deriving the
 // generic->shared base every iteration: S2UR/UMOV/UIADD3/ULEA/LEA per sphere pair in the profile)
@@ -70,99 +74,128 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) {
 // slice `part` of `parts` of [0, n)
 __device__ __forceinline__ int slice_lo(int n, int part, int parts) { return (int)(((long long)n * part) / parts); }
 
-constexpr int LIST_K = 32;       // entries per thread
-constexpr int GROUP = 16;        // spheres per list entry; the cull records are padded to a multiple of GROUP
+constexpr int GROUP = 32;                      // spheres per mask word
+constexpr int CHUNK_GROUPS = 16;               // mask words per ray between two sink flushes
+constexpr int CHUNK = GROUP * CHUNK_GROUPS;    // 512 spheres
+constexpr int CULL_PAD = 8;                    // the cull records are padded to a multiple of this (inner unroll)
+constexpr float RAY_DEFLATE = 1.0f - 3.2e-6f;  // 1 - 54 u: the ray's share of the rounding budget, taken off |o|^2
 
-// List entry (32 bits, one shared-memory bank per lane): (group << 2 | ray) << 16 | 16 sign bits, the sign of
-// sphere j of the group at bit 15 - j; a clear bit = that (ray, sphere) pair survived the cull.
+// mask words of a thread: word (group g, ray r) at list[(g * R + r) * BLOCK + threadIdx.x] (one bank per lane).
+// Bit layout: sphere j of a group of m spheres (m = 32, or the remainder in the last group of a chunk) is at
+// bit m - 1 - j; a CLEAR bit = that (ray, sphere) pair survived the cull; bits >= m are set.
 template <int R, int BLOCK>
 struct Culler {
-    static_assert(R == 1 || R == 2 || R == 4, "entry header holds 2 ray bits");
-    float ox[R], oy[R], oz[R];     // origin
     float hx[R], hy[R], hz[R];     // cull direction: d * sqrt(1 + eps) / |d|
-    float tm[R];                   // kept for the sinks (the cull itself is time-free)
+    float mx[R], my[R], mz[R];     // -2 o
+    float P[R];                    // o . h
+    float Q[R];                    // |o|^2 (1 - 54 u)
 
-    __device__ __forceinline__ void set_ray(int r, float o_x, float o_y, float o_z, float d_x, float d_y, float d_z,
-                                            float time) {
-        ox[r] = o_x; oy[r] = o_y; oz[r] = o_z; tm[r] = time;
+    static constexpr int LIST_WORDS = CHUNK_GROUPS * R;                         // per thread
+    static constexpr size_t LIST_BYTES = (size_t)LIST_WORDS * BLOCK * sizeof(uint32_t);   // per CTA
+
+    __device__ __forceinline__ void set_ray(int r, float o_x, float o_y, float o_z, float d_x, float d_y, float d_z) {
         float a = fmaf(d_z, d_z, fmaf(d_y, d_y, d_x * d_x));
         float s = rsqrtf(a) * (1.0f + 0.5f * CULL_EPS);
         hx[r] = d_x * s; hy[r] = d_y * s; hz[r] = d_z * s;
+        mx[r] = -2.0f * o_x; my[r] = -2.0f * o_y; mz[r] = -2.0f * o_z;
+        P[r] = fmaf(o_z, hz[r], fmaf(o_y, hy[r], o_x * hx[r]));
+        Q[r] = fmaf(o_z, o_z, fmaf(o_y, o_y, o_x * o_x)) * RAY_DEFLATE;
     }
-    // a dead slot: a ray that can never produce a candidate (b > 0 and far outside everything)
-    __device__ __forceinline__ void kill(int r) { set_ray(r, 1e18f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f); }
+    // a dead slot: nc = s - inf = -inf for every sphere, so the key's sign bit is always set
+    __device__ __forceinline__ void kill(int r) {
+        hx[r] = 1.f; hy[r] = 0.f; hz[r] = 0.f;
+        mx[r] = my[r] = mz[r] = 0.f;
+        P[r] = 0.f;
+        Q[r] = CUDART_INF_F;
+    }
 
     // opaque to the optimiser: otherwise ptxas rematerialises h (RSQ + 4 FMUL) per sphere to save registers
     __device__ __forceinline__ void pin() {
-        RT_FOR_R asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]), "+f"(ox[r]), "+f"(oy[r]), "+f"(oz[r]), "+f"(tm[r]));
+        RT_FOR_R asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]), "+f"(mx[r]), "+f"(my[r]), "+f"(mz[r]), "+f"(P[r]), "+f"(Q[r]));
     }
 
     static __device__ __forceinline__ unsigned list_begin(const uint32_t* list) {
         return (unsigned)__cvta_generic_to_shared(list + threadIdx.x);
     }
-    static __device__ __forceinline__ int list_count(const uint32_t* list, unsigned ptr) {
-        return (int)(ptr - list_begin(list)) / (BLOCK * 4);
-    }
-    // decode an entry: ray, first sphere of its group, and the survivors as a bit set (bit j = sphere j of the group)
-    static __device__ __forceinline__ void decode(unsigned e, int& r, int& k0, unsigned& surv) {
-        r = (int)((e >> 16) & 3u);
-        k0 = (int)(e >> 18) * GROUP;
-        surv = (~__brev(e) >> 16) & 0xffffu;     // entry bit 15 - j -> bit j, inverted: 1 = survivor
+    static __device__ __forceinline__ unsigned word(const uint32_t* list, int g, int r) {
+        return list[(g * R + r) * BLOCK + threadIdx.x];
     }
 
-    __device__ __forceinline__ unsigned key_bits(float fx, float fy, float fz, float r2i, int r) const {
-        float b = fmaf(fz, hz[r], fmaf(fy, hy[r], fx * hx[r]));
-        float nc = fmaf(-fz, fz, fmaf(-fy, fy, fmaf(-fx, fx, r2i)));
-        return __float_as_uint(fmaf(b, fminf(b, 0.f), nc));
+    // S = (-cx, -cy, -cz, W = r2i - c.c)
+    __device__ __forceinline__ unsigned key_bits(const float4 S, int r) const {
+        float b = fmaf(S.x, hx[r], fmaf(S.y, hy[r], fmaf(S.z, hz[r], P[r])));
+        float s = fmaf(S.x, mx[r], fmaf(S.y, my[r], fmaf(S.z, mz[r], S.w)));
+        return __float_as_uint(fmaf(b, fminf(b, 0.f), s - Q[r]));
     }
 
-    // s[k] = (-cx, -cy, -cz, r2_inflated); a moving sphere is the bounding sphere of its sweep; `count` is a
-    // multiple of GROUP (padding records have r2 = -inf and never survive).  Per test: 11 FP32 instructions +
-    // ONE funnel shift that appends the key's sign to the ray's running mask; per GROUP spheres each ray's
-    // entry is stored and the list pointer bumped if any of its 16 tests survived.
-    template <class Sink>
-    __device__ __forceinline__ void cull_static(const DevScene& sc, const float4* __restrict__ s, int count, int kbase,
-                                                uint32_t* list, unsigned& ptr, Sink& sink) {
-        const unsigned limit = list_begin(list) + (LIST_K - R) * BLOCK * 4;
-        unsigned sa = smem_addr(s);
-        for (int k = 0; k < count; k += GROUP) {
+    // One chunk: `count` records (a multiple of CULL_PAD, <= CHUNK) starting at shared address sa.  Writes the
+    // chunk's mask words and returns the bitmap of groups in which some ray of this thread has a survivor.
+    __device__ __forceinline__ unsigned cull_chunk(unsigned sa, int count, uint32_t* list) const {
+        unsigned la = list_begin(list), nz = 0;
+        const int full = count / GROUP;
+        for (int g = 0; g < full; ++g, la += R * BLOCK * 4) {
             unsigned acc[R];
-            RT_FOR_R acc[r] = (unsigned)((k / GROUP) * 4 + r);
-#pragma unroll 4
+            RT_FOR_R acc[r] = 0u;                  // all 32 bits are shifted out below
+#pragma unroll 8
             for (int u = 0; u < GROUP; ++u, sa += 16) {
                 const float4 S = lds128(sa);
-                RT_FOR_R acc[r] = __funnelshift_l(key_bits(ox[r] + S.x, oy[r] + S.y, oz[r] + S.z, S.w, r), acc[r], 1);
+                RT_FOR_R acc[r] = __funnelshift_l(key_bits(S, r), acc[r], 1);
             }
+            unsigned all = 0xffffffffu;
             RT_FOR_R {
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(ptr), "r"(acc[r]) : "memory");
-                if ((~acc[r]) & 0xffffu) ptr += BLOCK * 4;   // some test of this ray survived: keep the entry
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(la + (unsigned)(r * BLOCK * 4)), "r"(acc[r]) : "memory");
+                all &= acc[r];
             }
-            if (__any_sync(0xffffffffu, ptr > limit)) {   // warp-uniform: sinks may use warp collectives
-                sink.flush(*this, sc, list, list_count(list, ptr), kbase);
-                ptr = list_begin(list);
-            }
+            nz |= (all != 0xffffffffu ? 1u : 0u) << g;
         }
-        sink.flush(*this, sc, list, list_count(list, ptr), kbase);
-        ptr = list_begin(list);
+        const int rem = count - full * GROUP;
+        if (rem) {                                 // last, partial group of the chunk
+            unsigned acc[R];
+            RT_FOR_R acc[r] = 0xffffffffu;
+            for (int u = 0; u < rem; u += CULL_PAD) {
+#pragma unroll
+                for (int v = 0; v < CULL_PAD; ++v, sa += 16) {
+                    const float4 S = lds128(sa);
+                    RT_FOR_R acc[r] = __funnelshift_l(key_bits(S, r), acc[r], 1);
+                }
+            }
+            unsigned all = 0xffffffffu;
+            RT_FOR_R {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(la + (unsigned)(r * BLOCK * 4)), "r"(acc[r]) : "memory");
+                all &= acc[r];
+            }
+            nz |= (all != 0xffffffffu ? 1u : 0u) << full;
+        }
+        return nz;
     }
 
-    // Whole scene.  In tiled mode every thread of the CTA must call it (tile loads use __syncthreads).
-    // A preloaded scene is a single resident tile s_cull[0, n_cull); a tiled scene streams tiles of `cap` spheres.
+    // Records [s0, s1) of the resident tile (s1 - s0 a multiple of CULL_PAD), chunk by chunk; kbase = cull index
+    // of tile record 0.  Every lane of the warp must call it (sinks use warp collectives).
+    template <class Sink>
+    __device__ __forceinline__ void run_range(const float4* s_cull, int s0, int s1, int kbase, uint32_t* list, Sink& sink) {
+        for (int c0 = s0; c0 < s1; c0 += CHUNK) {
+            const int cc = min(CHUNK, s1 - c0);
+            const unsigned nz = cull_chunk(smem_addr(s_cull + c0), cc, list);
+            sink.flush(list, nz, cc, kbase + c0);
+        }
+    }
+
+    // Whole cull list.  In tiled mode every thread of the CTA must call it (tile loads use __syncthreads).
+    // A preloaded scene is a single resident tile s_cull[0, n_cull); a tiled scene streams tiles of `cap` records.
     // Moving spheres are culled as the static bounding sphere of their swept volume (the FP64 refine
     // evaluates the exact moving sphere), so there is ONE hot loop.
     template <class Sink>
     __device__ __forceinline__ void run(const DevScene& sc, float4* s_cull, int cap, bool preloaded, uint32_t* list,
                                         Sink& sink) {
         pin();
-        unsigned ptr = list_begin(list);
         for (int base = 0; base < sc.n_cull; base += cap) {
-            int count = min(cap, sc.n_cull - base);
+            const int count = min(cap, sc.n_cull - base);
             if (!preloaded) {
                 __syncthreads();
                 for (int i = threadIdx.x; i < count; i += BLOCK) s_cull[i] = __ldg(&sc.cull_a[base + i]);
                 __syncthreads();
             }
-            cull_static(sc, s_cull, count, base, list, ptr, sink);
+            run_range(s_cull, 0, count, base, list, sink);
         }
     }
 
@@ -172,10 +205,9 @@ struct Culler {
     __device__ __forceinline__ void run_slice(const DevScene& sc, float4* s_cull, uint32_t* list, Sink& sink, int part,
                                               int parts) {
         pin();
-        unsigned ptr = list_begin(list);
-        const int groups = sc.n_cull / GROUP;
-        const int s0 = slice_lo(groups, part, parts) * GROUP, s1 = slice_lo(groups, part + 1, parts) * GROUP;
-        cull_static(sc, s_cull + s0, s1 - s0, s0, list, ptr, sink);
+        const int groups = (sc.n_cull + GROUP - 1) / GROUP;
+        const int s0 = slice_lo(groups, part, parts) * GROUP, s1 = min(slice_lo(groups, part + 1, parts) * GROUP, sc.n_cull);
+        run_range(s_cull, s0, s1, 0, list, sink);
     }
 };
 
@@ -184,18 +216,50 @@ __device__ __forceinline__ void preload_scene(const DevScene& sc, float4* s_cull
     __syncthreads();
 }
 
+// Walks the survivors recorded in a thread's mask words: for (it.begin(nz, count); it.next(list, r, k);) ...
+// yields (ray r, chunk-relative sphere k) one pair at a time, so a warp runs max-over-lanes(#pairs) iterations.
+template <int R, int BLOCK>
+struct SurvivorIter {
+    unsigned z, sv;
+    int g, r, m, full, rem;
+    __device__ __forceinline__ void begin(unsigned nz, int count) {
+        z = nz; sv = 0u; g = 0; r = R - 1; m = 0;
+        full = count / GROUP; rem = count - full * GROUP;
+    }
+    __device__ __forceinline__ bool next(const uint32_t* list, int& ray, int& k) {
+        while (sv == 0u) {
+            if (++r == R) {
+                if (z == 0u) return false;
+                g = __ffs(z) - 1;
+                z &= z - 1u;
+                r = 0;
+                m = g < full ? GROUP : rem;
+            }
+            sv = ~Culler<R, BLOCK>::word(list, g, r);
+        }
+        const int bit = __ffs(sv) - 1;
+        sv &= sv - 1u;
+        ray = r;
+        k = g * GROUP + (m - 1 - bit);
+        return true;
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // RefineSink: the owning thread refines its survivors in FP64 and keeps the closest hit in
-// registers.  Each lane walks its own (ray, sphere) pairs through ONE refine call site: the warp
-// runs max-over-lanes(#pairs) iterations instead of (#entries x R) sparsely populated calls.
+// registers (trace kernel, megakernel).  It owns the rays as given (origin, un-normalised
+// direction, time); the Culler only holds what the FP32 test needs.
 // ------------------------------------------------------------------------------------------
 template <int R, int BLOCK>
 struct RefineSink {
+    float ox[R], oy[R], oz[R];     // origin
     float dx[R], dy[R], dz[R];     // direction as given (un-normalised, util.clj:13-16)
+    float tm[R];                   // ray time
     double best_t[R];
     int best_k[R], best_orig[R];
     unsigned ncand;
     double tmin, tmax;
+    const DevScene* sc;
 
     __device__ __forceinline__ void begin() {
         RT_FOR_R {
@@ -205,37 +269,39 @@ struct RefineSink {
         }
     }
 
-    __device__ __forceinline__ void flush(const Culler<R, BLOCK>& C, const DevScene& sc, const uint32_t* list, int count,
-                                          int kbase) {
-        int i = 0, r = 0, k0 = 0;
-        unsigned pend = 0;   // spheres of the current entry's group still to refine (bit j = sphere j)
-        for (;;) {
-            while (pend == 0 && i < count) {
-                Culler<R, BLOCK>::decode(list[i * BLOCK + threadIdx.x], r, k0, pend);
-                ++i;
-            }
-            if (pend == 0) break;
-            const int j = __ffs(pend) - 1;
-            pend &= pend - 1;
-            const int k = kbase + k0 + j;
-            float sox = C.ox[0], soy = C.oy[0], soz = C.oz[0], sdx = dx[0], sdy = dy[0], sdz = dz[0], stm = C.tm[0];
+    // exact test of (ray r, sphere k): closest t wins, exact ties go to the lower caller index (hitable.clj:17-26)
+    __device__ __forceinline__ void refine(int r, int k) {
+        float sox = ox[0], soy = oy[0], soz = oz[0], sdx = dx[0], sdy = dy[0], sdz = dz[0], stm = tm[0];
 #pragma unroll
-            for (int q = 1; q < R; ++q)
-                if (r == q) { sox = C.ox[q]; soy = C.oy[q]; soz = C.oz[q]; sdx = dx[q]; sdy = dy[q]; sdz = dz[q]; stm = C.tm[q]; }
-            const double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, sox, soy, soz, sdx, sdy, sdz,
-                                              stm, tmin, tmax);
-            ncand++;
-            if (t < CUDART_INF) {
-                const int orig = __ldg(&sc.orig_id[k]);
+        for (int q = 1; q < R; ++q)
+            if (r == q) { sox = ox[q]; soy = oy[q]; soz = oz[q]; sdx = dx[q]; sdy = dy[q]; sdz = dz[q]; stm = tm[q]; }
+        const double t = refine_candidate(sc->ex_c0r, sc->ex_c1, sc->ex_t0t1, sc->flags, k, sox, soy, soz, sdx, sdy, sdz, stm,
+                                          tmin, tmax);
+        ncand++;
+        if (t < CUDART_INF) {
+            const int orig = __ldg(&sc->orig_id[k]);
 #pragma unroll
-                for (int q = 0; q < R; ++q)   // exact ties go to the lower caller index (hitable.clj:17-26)
-                    if (r == q && (t < best_t[q] || (t == best_t[q] && orig < best_orig[q]))) {
-                        best_t[q] = t;
-                        best_k[q] = k;
-                        best_orig[q] = orig;
-                    }
-            }
+            for (int q = 0; q < R; ++q)
+                if (r == q && (t < best_t[q] || (t == best_t[q] && orig < best_orig[q]))) {
+                    best_t[q] = t;
+                    best_k[q] = k;
+                    best_orig[q] = orig;
+                }
         }
+    }
+
+    __device__ __forceinline__ void flush(const uint32_t* list, unsigned nz, int count, int kbase) {
+        SurvivorIter<R, BLOCK> it;
+        it.begin(nz, count);
+        int r, k;
+        while (it.next(list, r, k)) refine(r, kbase + k);
+    }
+
+    // the spheres that bypass the cull (DevScene::n_list .. n): tested directly for the rays in `live` (bit r)
+    __device__ __forceinline__ void direct(unsigned live) {
+        for (int k = sc->n_list; k < sc->n; ++k)
+            for (int r = 0; r < R; ++r)
+                if ((live >> r) & 1u) refine(r, k);
     }
 };
 
@@ -363,11 +429,14 @@ struct PairSink {
     unsigned n;                    // live entries in the queue
     const WaveParams* W;
 
-    __device__ __forceinline__ void flush(const Culler<R, BLOCK>&, const DevScene&, const uint32_t* list, int count,
-                                          int kbase) {
+    __device__ __forceinline__ void flush(const uint32_t* list, unsigned nz, int count, int kbase) {
+        if (!__any_sync(0xffffffffu, nz != 0u)) return;
         const unsigned lane = threadIdx.x & 31u;
         unsigned np = 0;
-        for (int i = 0; i < count; ++i) np += __popc((~list[i * BLOCK + threadIdx.x]) & 0xffffu);
+        for (unsigned z = nz; z; z &= z - 1u) {
+            const int g = __ffs(z) - 1;
+            RT_FOR_R np += __popc(~Culler<R, BLOCK>::word(list, g, r));
+        }
         unsigned incl = np;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -375,28 +444,23 @@ struct PairSink {
             if ((int)lane >= d) incl += v;
         }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) return;
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(&W->st->npairs, total);
         base = __shfl_sync(0xffffffffu, base, 0);
         const bool fits = base + total <= W->pair_cap;
         unsigned w = base + incl - np;
-        for (int i = 0; i < count; ++i) {
-            int r, k0;
-            unsigned pend;
-            Culler<R, BLOCK>::decode(list[i * BLOCK + threadIdx.x], r, k0, pend);
+        SurvivorIter<R, BLOCK> it;
+        it.begin(nz, count);
+        int r, k;
+        while (it.next(list, r, k)) {
             const unsigned idx = idx0 + 32u * (unsigned)r;
-            while (pend) {
-                const int j = __ffs(pend) - 1;
-                pend &= pend - 1;
-                if (fits) {
-                    W->pairs[w] = make_uint2(idx, (unsigned)(kbase + k0 + j));
-                } else {
-                    if (w < W->pair_cap) W->pairs[w] = make_uint2(PAIR_NULL, 0u);
-                    if (idx < n) W->best_key[idx] = BEST_KEY_OVERFLOW;
-                }
-                ++w;
+            if (fits) {
+                W->pairs[w] = make_uint2(idx, (unsigned)(kbase + k));
+            } else {
+                if (w < W->pair_cap) W->pairs[w] = make_uint2(PAIR_NULL, 0u);
+                if (idx < n) W->best_key[idx] = BEST_KEY_OVERFLOW;
             }
+            ++w;
         }
     }
 };
@@ -429,7 +493,7 @@ __device__ __forceinline__ void wf_cull_batches(const WaveParams& W, int cur, un
             unsigned idx = sink.idx0 + 32 * r;
             if (idx < n && batch < n_batches) {
                 float4 a = W.queue[cur][3 * (size_t)idx], b = W.queue[cur][3 * (size_t)idx + 1];
-                K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w);
+                K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z);
                 if (part == 0) {
                     W.best_t[idx] = BEST_T_INIT;
                     W.best_key[idx] = BEST_KEY_MISS;
@@ -493,7 +557,7 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, int cur) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         W.st->batch = 0;               // wf_cull is done with it
         W.st->qcount[cur ^ 1] = 0;     // wf_shade appends to it next
-        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);
+        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs + (unsigned long long)n * (unsigned)(P.sc.n - P.sc.n_list));
     }
     const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
     const unsigned warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -592,6 +656,19 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, int cur, 
             if (key == BEST_KEY_OVERFLOW) {                 // overflow mark: exact brute force for this entry
                 exact_closest_hit(P.sc, a.x, a.y, a.z, b.x, b.y, b.z, a.w, &td, &k);
                 key = k < 0 ? BEST_KEY_MISS : 1ull;
+            } else {
+                // the spheres that bypass the cull (enclosing spheres: the cull would pass them for nearly every
+                // ray) are tested here, exactly, from the registers that hold the ray anyway; same merge rule
+                for (int kd = P.sc.n_list; kd < P.sc.n; ++kd) {
+                    const double t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, kd, a.x, a.y, a.z, b.x,
+                                                      b.y, b.z, a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
+                    const unsigned long long kk = (((unsigned long long)(__ldg(&P.sc.orig_id[kd]) + 1)) << 32) | (unsigned)kd;
+                    if (t < td || (t < CUDART_INF && t == td && kk < key)) {
+                        td = t;
+                        key = kk;
+                        k = kd;
+                    }
+                }
             }
             if (key == BEST_KEY_MISS) {                     // core.clj:40-41 miss -> accum (black)
                 atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
@@ -702,13 +779,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
     I.tmin = 0.001;               // core.clj:25
     I.tmax = (double)FLT_MAX;     // Float/MAX_VALUE
     I.ncand = 0;
+    I.sc = &P.sc;
 
-    float ox[R], oy[R], oz[R], tmv[R];
-    float ar[R], ag[R], ab[R];    // attenuation (core.clj:23 `atten`)
+    float ar[R], ag[R], ab[R];    // attenuation (core.clj:23 `atten`); the rays themselves live in the sink
     uint32_t pix[R], smp[R];
     int depth[R];
     bool alive[R];
-    RT_FOR_R { alive[r] = false; ox[r] = oy[r] = oz[r] = tmv[r] = 0.f; I.dx[r] = 1.f; I.dy[r] = I.dz[r] = 0.f; }
+    RT_FOR_R { alive[r] = false; I.ox[r] = I.oy[r] = I.oz[r] = I.tm[r] = 0.f; I.dx[r] = 1.f; I.dy[r] = I.dz[r] = 0.f; }
     unsigned n_rays = 0, n_samples = 0;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
@@ -732,8 +809,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                     pix[r] = (uint32_t)j * (uint32_t)P.nx + (uint32_t)i;
                     smp[r] = (uint32_t)(P.sample_begin + (int)s_local);
                     float3 o, d;
-                    generate_ray(P.cam, P.nx, P.ny, i, j, pix[r], smp[r], P.key, o, d, tmv[r], nullptr);
-                    ox[r] = o.x; oy[r] = o.y; oz[r] = o.z;
+                    generate_ray(P.cam, P.nx, P.ny, i, j, pix[r], smp[r], P.key, o, d, I.tm[r], nullptr);
+                    I.ox[r] = o.x; I.oy[r] = o.y; I.oz[r] = o.z;
                     I.dx[r] = d.x; I.dy[r] = d.y; I.dz[r] = d.z;
                     ar[r] = ag[r] = ab[r] = 1.0f;
                     depth[r] = P.max_depth;
@@ -753,12 +830,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
         }
 
         // ---- intersect ----------------------------------------------------------------------------
+        unsigned live = 0;
         RT_FOR_R {
-            if (alive[r]) { K.set_ray(r, ox[r], oy[r], oz[r], I.dx[r], I.dy[r], I.dz[r], tmv[r]); n_rays++; }
+            if (alive[r]) { K.set_ray(r, I.ox[r], I.oy[r], I.oz[r], I.dx[r], I.dy[r], I.dz[r]); n_rays++; live |= 1u << r; }
             else K.kill(r);
         }
         I.begin();
         K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, I);
+        I.direct(live);
 
         // ---- shade ------------------------------------------------------------------------------
         RT_FOR_R {
@@ -767,11 +846,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                     alive[r] = false;
                     atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
                 } else {
-                    float3 o = f3(ox[r], oy[r], oz[r]), d = f3(I.dx[r], I.dy[r], I.dz[r]);
+                    float3 o = f3(I.ox[r], I.oy[r], I.oz[r]), d = f3(I.dx[r], I.dy[r], I.dz[r]);
                     float3 att, em;
                     int reason = TERM_NONE;
                     ScatterRng rng{P.key, pix[r], smp[r], (uint32_t)(P.max_depth - depth[r] + 1), nullptr, nullptr};
-                    bool cont = shade_hit(P.sc, I.best_k[r], (float)I.best_t[r], o, d, tmv[r], depth[r] > 0, rng, att, em,
+                    bool cont = shade_hit(P.sc, I.best_k[r], (float)I.best_t[r], o, d, I.tm[r], depth[r] > 0, rng, att, em,
                                           reason);
                     if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
                         float* dst = P.sum + (size_t)pix[r] * 3;
@@ -781,7 +860,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                     }
                     if (cont) {
                         ar[r] *= att.x; ag[r] *= att.y; ab[r] *= att.z;     // core.clj:31
-                        ox[r] = o.x; oy[r] = o.y; oz[r] = o.z;
+                        I.ox[r] = o.x; I.oy[r] = o.y; I.oz[r] = o.z;
                         I.dx[r] = d.x; I.dy[r] = d.y; I.dz[r] = d.z;
                         depth[r]--;
                     } else {
@@ -828,20 +907,26 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
     I.tmin = P.tmin;
     I.tmax = P.tmax;
     I.ncand = 0;
+    I.sc = &P.sc;
     for (long long base = (long long)blockIdx.x * BLOCK * R; base < P.n; base += (long long)gridDim.x * BLOCK * R) {
+        unsigned live = 0;
         RT_FOR_R {
             long long idx = base + (long long)r * BLOCK + threadIdx.x;
             if (idx < P.n) {
+                I.ox[r] = P.origins[3 * idx]; I.oy[r] = P.origins[3 * idx + 1]; I.oz[r] = P.origins[3 * idx + 2];
                 I.dx[r] = P.dirs[3 * idx]; I.dy[r] = P.dirs[3 * idx + 1]; I.dz[r] = P.dirs[3 * idx + 2];
-                K.set_ray(r, P.origins[3 * idx], P.origins[3 * idx + 1], P.origins[3 * idx + 2], I.dx[r], I.dy[r], I.dz[r],
-                          P.times ? P.times[idx] : 0.f);
+                I.tm[r] = P.times ? P.times[idx] : 0.f;
+                K.set_ray(r, I.ox[r], I.oy[r], I.oz[r], I.dx[r], I.dy[r], I.dz[r]);
+                live |= 1u << r;
             } else {
+                I.ox[r] = I.oy[r] = I.oz[r] = I.tm[r] = 0.f;
                 I.dx[r] = 1.f; I.dy[r] = 0.f; I.dz[r] = 0.f;
                 K.kill(r);
             }
         }
         I.begin();
         K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, I);
+        I.direct(live);
         RT_FOR_R {
             long long idx = base + (long long)r * BLOCK + threadIdx.x;
             if (idx < P.n) {
@@ -855,6 +940,36 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
 // ------------------------------------------------------------------------------------------
 // diagnostics
 // ------------------------------------------------------------------------------------------
+// The cull's contract, checked pair by pair: every (ray, listed sphere) whose exact FP64 test accepts a root in
+// (tmin, tmax) must have a clear sign bit in the FP32 key computed by the very code of the hot loop.
+// out[0] = pairs the cull would have lost (must be 0), out[1] = cull survivors, out[2] = exact candidates.
+__global__ void __launch_bounds__(128) cull_check_kernel(const DevScene sc, int n, const float* origins, const float* dirs,
+                                                         const float* times, double tmin, double tmax,
+                                                         unsigned long long* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long lost = 0, surv = 0, cand = 0;
+    if (idx < n) {
+        const float ox = origins[3 * idx], oy = origins[3 * idx + 1], oz = origins[3 * idx + 2];
+        const float dx = dirs[3 * idx], dy = dirs[3 * idx + 1], dz = dirs[3 * idx + 2];
+        const float tm = times ? times[idx] : 0.f;
+        Culler<1, 128> K;
+        K.set_ray(0, ox, oy, oz, dx, dy, dz);
+        K.pin();
+        for (int k = 0; k < sc.n_list; ++k) {
+            const bool culled = (K.key_bits(__ldg(&sc.cull_a[k]), 0) >> 31) != 0u;
+            const double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, ox, oy, oz, dx, dy, dz, tm, tmin, tmax);
+            surv += culled ? 0u : 1u;
+            if (t < CUDART_INF) {
+                cand++;
+                lost += culled ? 1u : 0u;
+            }
+        }
+    }
+    if (lost) atomicAdd(&out[0], lost);
+    if (surv) atomicAdd(&out[1], surv);
+    if (cand) atomicAdd(&out[2], cand);
+}
+
 __global__ void genrays_kernel(DevCamera cam, int n, int nx, int ny, const int* ij, const int* s, uint2 key, float* out_o,
                                float* out_d, float* out_t, float* out_rnd) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -204,7 +204,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_set_scene", "rt_set_camera", "rt_render",
     "rt_render_accumulate_device", "rt_resolve_device", "rt_trace_primary", "rt_generate_rays", "rt_shade_batch",
-    "rt_measure_fp32_peak", "rt_get_counters", "rt_reset_counters", "rt_set_profile", "rt_device_info",
+    "rt_measure_fp32_peak", "rt_get_counters", "rt_reset_counters", "rt_set_profile", "rt_device_info", "rt_cull_check",
 ]
 
 _lib = None
@@ -232,6 +232,7 @@ def load_library():
     L.rt_resolve_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int]
     L.rt_trace_primary.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, C.c_double, C.c_double, _f64p, _i32p]
+    L.rt_cull_check.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, C.c_double, C.c_double, _u64p]
     L.rt_generate_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_uint64, _f32p, _f32p,
                                    _f32p, _f32p]
     L.rt_reset_counters.argtypes = [C.c_void_p]
@@ -333,6 +334,16 @@ class Renderer:
         self._check(self.L.rt_trace_primary(self.h, n, _p(o, _f32p), _p(d, _f32p), _p(tm, _f32p), C.c_double(t_min),
                                             C.c_double(t_max), _p(t, _f64p), _p(ids, _i32p)), "rt_trace_primary")
         return t, ids
+
+    def cull_check(self, origins, dirs, times=None, t_min=0.001, t_max=float(np.finfo(np.float32).max)):
+        """(pairs the FP32 cull would lose — must be 0, cull survivors, exact candidates) over rays x listed spheres."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        tm = None if times is None else np.ascontiguousarray(times, np.float32)
+        out = np.zeros(3, np.uint64)
+        self._check(self.L.rt_cull_check(self.h, o.shape[0], _p(o, _f32p), _p(d, _f32p), _p(tm, _f32p), C.c_double(t_min),
+                                         C.c_double(t_max), _p(out, _u64p)), "rt_cull_check")
+        return int(out[0]), int(out[1]), int(out[2])
 
     def generate_rays(self, nx, ny, ij, s, seed=1):
         ij = np.ascontiguousarray(ij, np.int32).reshape(-1, 2)

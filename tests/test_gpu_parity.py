@@ -107,6 +107,57 @@ def test_trace_grazing_rays(renderer, scene_c2):
     _assert_hits_match(t_gpu, id_gpu, t_ref, id_ref)
 
 
+def _grazing_rays(flat, rng, n, origin_scale, jitter):
+    """n rays from origins |o| ~ origin_scale aimed at sphere silhouettes +- jitter (relative)."""
+    k = rng.integers(0, flat.n_spheres, n)
+    c = flat.center0_r[k, :3].astype(np.float64)
+    r = flat.center0_r[k, 3].astype(np.float64)
+    o = rng.normal(size=(n, 3)) * origin_scale
+    to_c = c - o
+    dist = np.linalg.norm(to_c, axis=1)
+    perp = np.cross(to_c, rng.normal(size=(n, 3)))
+    perp /= np.linalg.norm(perp, axis=1)[:, None]
+    target = c + perp * (r * (1.0 + rng.normal(scale=jitter, size=n)))[:, None]
+    d = (target - o) * rng.uniform(0.2, 3.0, size=(n, 1)) / dist[:, None]
+    return o.astype(np.float32), d.astype(np.float32)
+
+
+def test_cull_never_under_reports(renderer, scene_c2):
+    """The FP32 cull (expanded-form key, Culler in rt_kernels.cuh) may over-report but must never lose a
+    (ray, sphere) pair the exact FP64 test accepts — checked pair by pair on the device over ~3e8 pairs:
+    camera rays, rays from surfaces, silhouette-grazing rays, and origins far from the scene (where the
+    expanded form cancels worst: |o| up to ~3000)."""
+    flat, cam_type, cam, S = scene_c2
+    renderer.set_scene(flat)
+    rng = np.random.default_rng(21)
+    families = {}
+    o, d, tm = camera_rays(cam, 1200, 800, 100_000, rng)
+    families["camera"] = (o, d, tm)
+    t, _ = S.hit(o, d, tm, 0.001, FMAX)
+    p = (o.astype(np.float64) + t[:, None] * d.astype(np.float64)).astype(np.float32)
+    nd = rng.normal(size=p.shape).astype(np.float32) * rng.uniform(0.05, 2.0, size=(len(p), 1)).astype(np.float32)
+    families["surface"] = (p, nd, tm)
+    for scale in (1.0, 10.0, 100.0, 1000.0):
+        for jitter in (3e-7, 1e-4):
+            og, dg = _grazing_rays(flat, rng, 50_000, scale, jitter)
+            families[f"grazing |o|~{scale:g} +-{jitter:g}"] = (og, dg, rng.random(len(og)).astype(np.float32))
+    o2 = rng.uniform(-15, 15, size=(100_000, 3)).astype(np.float32)
+    o2[:, 1] = rng.uniform(-1, 3, size=len(o2))
+    families["volume"] = (o2, rng.normal(size=o2.shape).astype(np.float32), rng.random(len(o2)).astype(np.float32))
+    total_pairs = 0
+    for name, (o, d, tm) in families.items():
+        for tmin in (0.0, 0.001):
+            lost, survivors, candidates = renderer.cull_check(o, d, tm, tmin, FMAX)
+            assert lost == 0, f"{name}: the cull lost {lost} of {candidates} exact candidates (tmin {tmin})"
+            assert survivors >= candidates
+        total_pairs += len(o) * flat.n_spheres
+        if name == "camera":   # selectivity: the cull passes few pairs beyond the true candidates
+            assert survivors <= 1.5 * candidates + 0.002 * len(o) * flat.n_spheres
+    assert total_pairs > 2e8
+    with pytest.raises(rt.native.NativeError):
+        renderer.cull_check(o, d, tm, -1.0, FMAX)
+
+
 # hitable_test.clj:8-19
 GRIDPOINTS = [25.0 * np.array(p, float) for p in itertools.product((-1, 0, 1), repeat=3)]
 DIRECTIONS = [5.0 * np.array(p, float) for p in itertools.product((-1, 0, 1), repeat=3) if any(p)]
