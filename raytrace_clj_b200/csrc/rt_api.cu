@@ -430,10 +430,13 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
 // centre = midpoint of centre(win_lo), centre(win_hi), radius = r + half the travelled distance.  The inflation
 // covers the float rounding of the record itself and the sphere's share of the cull's rounding budget
 // (48 u c.c + 8 u r^2, u = 2^-24; the bound is 32.6 u c.c + 4.1 u r^2), so the cull only ever over-reports.
-// Records [n_list, n_cull) are padding: W = -inf, the key is -inf for every ray.
-void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* cull_a) {
+// Records [n_list, n_cull) are padding: W = -inf, the key is -inf for every ray.  The direct spheres' records
+// follow the padding (used as a pre-test where those spheres are resolved).
+void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* cull_all) {
     const double eps = std::ldexp(1.0, -20), u = std::ldexp(1.0, -24);
-    for (int i = 0; i < ctx->n_list; ++i) {
+    for (int i = 0; i < ctx->n_spheres; ++i) {
+        // listed spheres at [0, n_list); the direct spheres' records follow the padding, at n_cull + (i - n_list)
+        float* cull_a = i < ctx->n_list ? cull_all : cull_all + 4 * (size_t)(ctx->n_cull - ctx->n_list);
         double r = std::fabs((double)ctx->h_c0r[4 * i + 3]);
         double mid[3], half2 = 0.0, cmax = 0.0;
         const bool moving = (ctx->h_flags[i] & RT_SPHERE_MOVING) != 0;
@@ -463,8 +466,8 @@ void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* 
         cull_a[4 * i + 3] = round_up_f32(r2i - cc);
     }
     for (int k = ctx->n_list; k < ctx->n_cull; ++k) {
-        cull_a[4 * k] = cull_a[4 * k + 1] = cull_a[4 * k + 2] = 0.f;
-        cull_a[4 * k + 3] = -INFINITY;
+        cull_all[4 * k] = cull_all[4 * k + 1] = cull_all[4 * k + 2] = 0.f;
+        cull_all[4 * k + 3] = -INFINITY;
     }
 }
 
@@ -477,7 +480,7 @@ int ensure_window(rt_ctx* ctx, double lo, double hi) {
     bool any_moving = false;
     for (unsigned f : ctx->h_flags) any_moving |= (f & RT_SPHERE_MOVING) != 0;
     if (!any_moving) return RT_OK;
-    std::vector<float> cull((size_t)ctx->n_cull * 4);
+    std::vector<float> cull((size_t)(ctx->n_cull + ctx->n_spheres - ctx->n_list) * 4);
     build_cull_records(ctx, ctx->win_lo, ctx->win_hi, cull.data());
     if (cull.empty()) return RT_OK;
     for (auto& d : ctx->devs) {
@@ -655,6 +658,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     int n_direct = 0;
     {
         std::vector<char> direct((size_t)n, 0);
+        double direct_centroid[3] = {0, 0, 0};
         static const int direct_env = env_int("RT_DIRECT_SPHERES", 1);
         if (n > 16 && direct_env) {
             std::vector<double> radii((size_t)n);
@@ -669,7 +673,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
                     for (int c = 0; c < 3; ++c) cen[c] += s->center0_r[4 * i + c];
                     ++small;
                 }
-            for (int c = 0; c < 3; ++c) cen[c] /= std::max(1, small);
+            for (int c = 0; c < 3; ++c) { cen[c] /= std::max(1, small); direct_centroid[c] = cen[c]; }
             std::vector<std::pair<double, int>> cand;
             for (int i = 0; i < n; ++i) {
                 if (radii[(size_t)i] < big) continue;
@@ -682,7 +686,17 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         }
         int k = 0;
         for (int i = 0; i < n; ++i) if (!direct[(size_t)i]) perm[(size_t)k++] = i;
-        for (int i = 0; i < n; ++i) if (direct[(size_t)i]) perm[(size_t)k++] = i;
+        // direct spheres: the ones whose surface passes near the population's centroid first (a ground sphere: a hit
+        // there lets the distance pre-test skip the enclosing ones), the all-enclosing ones (a sky dome) last
+        std::vector<std::pair<double, int>> order;
+        for (int i = 0; i < n; ++i)
+            if (direct[(size_t)i]) {
+                double d2 = 0.0;
+                for (int c = 0; c < 3; ++c) { double x = s->center0_r[4 * i + c] - direct_centroid[c]; d2 += x * x; }
+                order.emplace_back(-std::sqrt(d2) / std::max(1e-30, std::fabs((double)s->center0_r[4 * i + 3])), i);
+            }
+        std::sort(order.begin(), order.end());
+        for (auto& o : order) perm[(size_t)k++] = o.second;
     }
     const int n_list = n - n_direct;
     const int n_cull = (int)align_up((size_t)n_list, CULL_PAD);
@@ -706,11 +720,12 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     }
     ctx->n_list = n_list;
     ctx->n_cull = n_cull;
+    ctx->n_spheres = n;
 
     // blob layout
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_cull_a = take((size_t)std::max(n_cull, 1) * 16);
+    size_t o_cull_a = take((size_t)(n_cull + n_direct) * 16);
     size_t o_c0r = take((size_t)n * 16), o_c1 = take((size_t)n * 16), o_t0t1 = take((size_t)n * 8);
     size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n * 4), o_mat = take((size_t)n * 4);
     size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);

@@ -129,9 +129,12 @@ struct Culler {
     }
 
     // One chunk: `count` records (a multiple of CULL_PAD, <= CHUNK) starting at shared address sa.  Writes the
-    // chunk's mask words and returns the bitmap of groups in which some ray of this thread has a survivor.
-    __device__ __forceinline__ unsigned cull_chunk(unsigned sa, int count, uint32_t* list) const {
-        unsigned la = list_begin(list), nz = 0;
+    // chunk's mask words and returns the bitmap of the words that hold a survivor: bit 16 r + g = (ray r, group g),
+    // so the sinks visit exactly those words (walking every word of a flagged group cost ~30 % of the warps' time).
+    __device__ __forceinline__ unsigned long long cull_chunk(unsigned sa, int count, uint32_t* list) const {
+        unsigned la = list_begin(list);
+        unsigned nzr[R];
+        RT_FOR_R nzr[r] = 0u;
         const int full = count / GROUP;
         for (int g = 0; g < full; ++g, la += R * BLOCK * 4) {
             unsigned acc[R];
@@ -141,12 +144,10 @@ struct Culler {
                 const float4 S = lds128(sa);
                 RT_FOR_R acc[r] = __funnelshift_l(key_bits(S, r), acc[r], 1);
             }
-            unsigned all = 0xffffffffu;
             RT_FOR_R {
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(la + (unsigned)(r * BLOCK * 4)), "r"(acc[r]) : "memory");
-                all &= acc[r];
+                nzr[r] |= (acc[r] != 0xffffffffu ? 1u : 0u) << g;
             }
-            nz |= (all != 0xffffffffu ? 1u : 0u) << g;
         }
         const int rem = count - full * GROUP;
         if (rem) {                                 // last, partial group of the chunk
@@ -159,13 +160,13 @@ struct Culler {
                     RT_FOR_R acc[r] = __funnelshift_l(key_bits(S, r), acc[r], 1);
                 }
             }
-            unsigned all = 0xffffffffu;
             RT_FOR_R {
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(la + (unsigned)(r * BLOCK * 4)), "r"(acc[r]) : "memory");
-                all &= acc[r];
+                nzr[r] |= (acc[r] != 0xffffffffu ? 1u : 0u) << full;
             }
-            nz |= (all != 0xffffffffu ? 1u : 0u) << full;
         }
+        unsigned long long nz = 0ull;
+        RT_FOR_R nz |= (unsigned long long)nzr[r] << (16 * r);
         return nz;
     }
 
@@ -175,7 +176,7 @@ struct Culler {
     __device__ __forceinline__ void run_range(const float4* s_cull, int s0, int s1, int kbase, uint32_t* list, Sink& sink) {
         for (int c0 = s0; c0 < s1; c0 += CHUNK) {
             const int cc = min(CHUNK, s1 - c0);
-            const unsigned nz = cull_chunk(smem_addr(s_cull + c0), cc, list);
+            const unsigned long long nz = cull_chunk(smem_addr(s_cull + c0), cc, list);
             sink.flush(list, nz, cc, kbase + c0);
         }
     }
@@ -220,21 +221,21 @@ __device__ __forceinline__ void preload_scene(const DevScene& sc, float4* s_cull
 // yields (ray r, chunk-relative sphere k) one pair at a time, so a warp runs max-over-lanes(#pairs) iterations.
 template <int R, int BLOCK>
 struct SurvivorIter {
-    unsigned z, sv;
+    unsigned long long z;
+    unsigned sv;
     int g, r, m, full, rem;
-    __device__ __forceinline__ void begin(unsigned nz, int count) {
-        z = nz; sv = 0u; g = 0; r = R - 1; m = 0;
+    __device__ __forceinline__ void begin(unsigned long long nz, int count) {
+        z = nz; sv = 0u; g = 0; r = 0; m = 0;
         full = count / GROUP; rem = count - full * GROUP;
     }
     __device__ __forceinline__ bool next(const uint32_t* list, int& ray, int& k) {
-        while (sv == 0u) {
-            if (++r == R) {
-                if (z == 0u) return false;
-                g = __ffs(z) - 1;
-                z &= z - 1u;
-                r = 0;
-                m = g < full ? GROUP : rem;
-            }
+        if (sv == 0u) {                      // every flagged word holds at least one survivor
+            if (z == 0ull) return false;
+            const int i = __ffsll((long long)z) - 1;
+            z &= z - 1ull;
+            r = i >> 4;
+            g = i & 15;
+            m = g < full ? GROUP : rem;
             sv = ~Culler<R, BLOCK>::word(list, g, r);
         }
         const int bit = __ffs(sv) - 1;
@@ -290,7 +291,7 @@ struct RefineSink {
         }
     }
 
-    __device__ __forceinline__ void flush(const uint32_t* list, unsigned nz, int count, int kbase) {
+    __device__ __forceinline__ void flush(const uint32_t* list, unsigned long long nz, int count, int kbase) {
         SurvivorIter<R, BLOCK> it;
         it.begin(nz, count);
         int r, k;
@@ -383,8 +384,14 @@ __device__ __forceinline__ bool take_work(const RenderParams& P, bool want, unsi
 // camera ray of work item w as a queue record
 __device__ __forceinline__ void make_path(const RenderParams& P, unsigned long long w, float4& a, float4& b, float4& c) {
     const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
-    unsigned s_local = (unsigned)(w / pshard);
-    unsigned q = (unsigned)(w - (unsigned long long)s_local * pshard);
+    unsigned s_local, q;
+    if (P.total_work <= 0xffffffffull) {     // warp-uniform: a 32-bit divide is ~4x fewer instructions than the 64-bit one
+        s_local = (unsigned)w / pshard;
+        q = (unsigned)w - s_local * pshard;
+    } else {
+        s_local = (unsigned)(w / pshard);
+        q = (unsigned)(w - (unsigned long long)s_local * pshard);
+    }
     int row_local = (int)(q / (unsigned)P.nx);
     int i = (int)(q - (unsigned)row_local * (unsigned)P.nx);
     int j = P.row_offset + row_local * P.row_stride;
@@ -429,13 +436,13 @@ struct PairSink {
     unsigned n;                    // live entries in the queue
     const WaveParams* W;
 
-    __device__ __forceinline__ void flush(const uint32_t* list, unsigned nz, int count, int kbase) {
-        if (!__any_sync(0xffffffffu, nz != 0u)) return;
+    __device__ __forceinline__ void flush(const uint32_t* list, unsigned long long nz, int count, int kbase) {
+        if (!__any_sync(0xffffffffu, nz != 0ull)) return;
         const unsigned lane = threadIdx.x & 31u;
         unsigned np = 0;
-        for (unsigned z = nz; z; z &= z - 1u) {
-            const int g = __ffs(z) - 1;
-            RT_FOR_R np += __popc(~Culler<R, BLOCK>::word(list, g, r));
+        for (unsigned long long z = nz; z; z &= z - 1ull) {
+            const int i = __ffsll((long long)z) - 1;
+            np += __popc(~Culler<R, BLOCK>::word(list, i & 15, i >> 4));
         }
         unsigned incl = np;
 #pragma unroll
@@ -465,33 +472,45 @@ struct PairSink {
     }
 };
 
+// Queue entries [e0, e1) in batches of 32*R, each batch optionally split into `parts` sphere slices.  The
+// (batch, slice) work items of this range are numbered item0, item0 + 1, ...; warps claim item numbers from the
+// shared counter (preloaded scenes) or take them in a CTA-uniform static order (tiled scenes).  `claimed` is an
+// item number this warp has already claimed (or ~0u); returns the first claimed number beyond the range, so a
+// following range can use it.
+constexpr unsigned ITEM_NONE = 0xffffffffu;
 template <int R, int BLOCK>
-__device__ __forceinline__ void wf_cull_batches(const WaveParams& W, int cur, unsigned n, int parts, float4* s_cull,
-                                                uint32_t* s_list) {
+__device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, int cur, unsigned e0, unsigned e1, int parts,
+                                                    unsigned item0, unsigned claimed, float4* s_cull, uint32_t* s_list) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
-    const unsigned n_batches = (n + 32 * R - 1) / (32 * R);
+    const unsigned n_batches = (e1 - e0 + 32 * R - 1) / (32 * R);
     const unsigned n_items = n_batches * (unsigned)parts;          // (batch, sphere slice) work items
     Culler<R, BLOCK> K;
     PairSink<R, BLOCK> sink;
-    sink.n = n;
+    sink.n = e1;
     sink.W = &W;
     unsigned item = blockIdx.x * warps + warp;                     // tiled scenes: CTA-uniform static order
     const unsigned uniform_end = (n_items + warps - 1) / warps * warps;
     for (;;) {
         if (P.preloaded) {
-            unsigned b = 0;
-            if (lane == 0) b = atomicAdd(&W.st->batch, 1u);
-            item = __shfl_sync(0xffffffffu, b, 0);
-            if (item >= n_items) break;
+            if (claimed != ITEM_NONE) {
+                item = claimed;
+                claimed = ITEM_NONE;
+            } else {
+                unsigned b = 0;
+                if (lane == 0) b = atomicAdd(&W.st->batch, 1u);
+                item = __shfl_sync(0xffffffffu, b, 0);
+            }
+            if (item >= item0 + n_items) return item;
+            item -= item0;
         } else {
             if (item - warp >= uniform_end) break;
         }
         const unsigned batch = item / (unsigned)parts, part = item - batch * (unsigned)parts;
-        sink.idx0 = batch * (32 * R) + lane;     // ray r of this lane = entry idx0 + 32 r
+        sink.idx0 = e0 + batch * (32 * R) + lane;     // ray r of this lane = entry idx0 + 32 r
         RT_FOR_R {
             unsigned idx = sink.idx0 + 32 * r;
-            if (idx < n && batch < n_batches) {
+            if (idx < e1 && batch < n_batches) {
                 float4 a = W.queue[cur][3 * (size_t)idx], b = W.queue[cur][3 * (size_t)idx + 1];
                 K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z);
                 if (part == 0) {
@@ -506,24 +525,32 @@ __device__ __forceinline__ void wf_cull_batches(const WaveParams& W, int cur, un
         else           K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, sink);
         item += gridDim.x * warps;
     }
+    return ITEM_NONE;
 }
 
-// queue length decides the shape of the cull work: full batches of R rays per thread while every warp of the
-// grid gets at least two one-ray batches' worth; below that 1 ray per thread, and below THAT the sphere
-// list is split across warps too (the pairs merge in wf_refine).  R = 1 instantiates only the short form.
+// Queue length decides the shape of the cull work.  A long queue: batches of R rays per thread for the bulk,
+// then — so that the warps do not finish up to a whole 32*R batch apart — one-ray batches for the last stretch
+// (two per warp of the grid), claimed from the same counter.  A short queue: 1 ray per thread, and below two
+// batches per warp the sphere list is split across warps too (the pairs merge in wf_refine).
+// R = 1 instantiates only the short form.
 template <int R, int BLOCK>
 __device__ __forceinline__ void wf_cull_body(const WaveParams& W, int cur, unsigned n, float4* s_cull, uint32_t* s_list) {
     const RenderParams& P = W.base;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
     const unsigned grid_warps = gridDim.x * (BLOCK / 32);
-    if (R > 1 && (n >= grid_warps * 64u || !P.preloaded)) {
-        wf_cull_batches<R, BLOCK>(W, cur, n, 1, s_cull, s_list);
+    if (R > 1 && !P.preloaded) {
+        wf_cull_batches<R, BLOCK>(W, cur, 0u, n, 1, 0u, ITEM_NONE, s_cull, s_list);
+    } else if (R > 1 && n >= grid_warps * 64u) {
+        const unsigned tail = grid_warps * 64u;                                       // two one-ray batches per warp
+        const unsigned n_bulk = (n - tail) / (32u * R) * (32u * R), bulk_items = n_bulk / (32u * R);
+        const unsigned next = wf_cull_batches<R, BLOCK>(W, cur, 0u, n_bulk, 1, 0u, ITEM_NONE, s_cull, s_list);
+        wf_cull_batches<1, BLOCK>(W, cur, n_bulk, n, 1, bulk_items, next, s_cull, s_list);
     } else {
         const unsigned b1 = (n + 31) / 32;
         int parts = 1;
         if (P.preloaded)
             while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
-        wf_cull_batches<1, BLOCK>(W, cur, n, parts, s_cull, s_list);
+        wf_cull_batches<1, BLOCK>(W, cur, 0u, n, parts, 0u, ITEM_NONE, s_cull, s_list);
     }
 }
 
@@ -557,7 +584,7 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, int cur) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         W.st->batch = 0;               // wf_cull is done with it
         W.st->qcount[cur ^ 1] = 0;     // wf_shade appends to it next
-        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs + (unsigned long long)n * (unsigned)(P.sc.n - P.sc.n_list));
+        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);   // + the direct spheres' exact tests, counted by wf_shade
     }
     const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
     const unsigned warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -638,7 +665,7 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, int cur, 
         W.st->npairs = 0;   // refine / tie-break are done with it
         W.st->exhausted = (*(volatile unsigned long long*)P.work_counter >= P.total_work) ? 1u : 0u;
     }
-    unsigned n_samples = 0;
+    unsigned n_samples = 0, n_direct = 0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned idx0 = blockIdx.x * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
         const unsigned idx = idx0 + lane;
@@ -660,6 +687,7 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, int cur, 
                 // the spheres that bypass the cull (enclosing spheres: the cull would pass them for nearly every
                 // ray) are tested here, exactly, from the registers that hold the ray anyway; same merge rule
                 for (int kd = P.sc.n_list; kd < P.sc.n; ++kd) {
+                    ++n_direct;
                     const double t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, kd, a.x, a.y, a.z, b.x,
                                                       b.y, b.z, a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
                     const unsigned long long kk = (((unsigned long long)(__ldg(&P.sc.orig_id[kd]) + 1)) << 32) | (unsigned)kd;
@@ -707,6 +735,7 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, int cur, 
             q[0] = a; q[1] = b; q[2] = c;
         }
     }
+    if (n_direct) atomicAdd(&s_ctr[DC_CANDIDATES], n_direct);
     return n_samples;
 }
 

@@ -377,6 +377,17 @@ def test_render_matches_oracle_material_stress(renderer, variant):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
+def test_render_matches_oracle_tiled_scene(renderer, variant):
+    """BASELINE config 5's shape at test scale: more spheres than one shared-memory tile holds (> 4096), so the
+    cull streams the sphere list through shared memory tile by tile and flushes the survivors chunk by chunk."""
+    sc = rt.scene.make_scale_sweep_scene(96, 64, 5000, random.Random(5))
+    flat = rt.native.marshal_world(sc["world"])
+    assert flat.n_spheres > 4096
+    cam_type, cam = rt.native.marshal_camera(sc["camera"])
+    _render_parity(renderer, flat, cam_type, cam, 96, 64, 48, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
 def test_render_matches_oracle_two_spheres_and_depth_cutoff(renderer, variant):
     """make-two-spheres (scene.clj:9-49: UVGradient on a Lambertian UVSphere) and a depth cutoff of 2."""
     sc = rt.scene.make_two_spheres(120, 80)
