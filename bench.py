@@ -38,8 +38,14 @@ WORKLOADS = {
     # name: (nx, ny, spp, depth, scene builder name, scene seed)
     "c2": (1200, 800, 10, 50, "random", 1),
     "c1": (200, 100, 100, 50, "random", 1),
+    "c3": (3840, 2160, 1024, 50, "random", 1),          # use with --scaling strong at N GPUs (sample slices)
     "c3-slice": (3840, 2160, 16, 50, "random", 1),
     "c4": (1200, 800, 64, 50, "stress", 4),
+    # config 5: brute-force scale sweep, 1920x1080, 64 spp
+    "c5-100": (1920, 1080, 64, 50, "sweep:100", 5),
+    "c5-1k": (1920, 1080, 64, 50, "sweep:1000", 5),
+    "c5-10k": (1920, 1080, 64, 50, "sweep:10000", 5),
+    "c5-100k": (1920, 1080, 64, 50, "sweep:100000", 5),
 }
 
 
@@ -51,6 +57,8 @@ def build_scene(name, nx, ny, seed):
         sc = rt.scene.make_random_scene(nx, ny, 11, True, rng)
     elif name == "stress":
         sc = rt.scene.make_material_stress_scene(nx, ny, 11, rng)
+    elif name.startswith("sweep:"):
+        sc = rt.scene.make_scale_sweep_scene(nx, ny, int(name.split(":")[1]), rng)
     else:
         raise ValueError(name)
     flat = rt.native.marshal_world(sc["world"])
@@ -169,6 +177,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", type=int, default=int(os.environ.get("RT_VARIANT", "1")), help="1 wavefront (default), 0 megakernel")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU renders the workload's spp (global spp = spp x N); strong: the spp are divided")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
     args = ap.parse_args()
@@ -197,6 +207,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     nx, ny, spp, depth, scene_name, scene_seed = WORKLOADS[args.workload]
+    if args.scaling == "strong":
+        if spp % world:
+            raise SystemExit(f"--scaling strong: {spp} spp do not divide over {world} GPUs")
+        spp //= world                                # per-GPU sample slice
     flat, cam_type, cam = build_scene(scene_name, nx, ny, scene_seed)
     r = rt.native.Renderer([local_rank])
     r.set_scene(flat)
@@ -310,16 +324,18 @@ def main():
         stage["tests"] = pc["sphere_tests"]
     barrier()
 
+    scene_desc = {"random": "make-random-scene n=11 moving=true", "stress": "make-random-scene n=11, 10/45/45 % Lambert/metal/glass"}.get(
+        scene_name, "5 hero objects + static r=0.2 spheres on a grid, scene.clj:369-375 placement rule")
     if rank == 0:
         achieved_tflops = FLOP_PER_TEST * (tests / world) / (kernel_ms * 1e-3) / 1e12   # per GPU, whole render step
         peak_measured = max(fp32_peak)
         line = {
             "metric": "samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: random-spheres scene {nx}x{ny}, {spp} spp per GPU, depth {depth}, "
-                            f"{flat.n_spheres} spheres (make-random-scene n=11 moving=true, scene seed {scene_seed})",
+                            f"{flat.n_spheres} spheres ({scene_desc}, scene seed {scene_seed})",
                 "variant": "megakernel" if args.variant == 0 else "wavefront",
                 "parallelism": f"sample-slice x{world}" if world > 1 else "single GPU",
                 "l2": "flushed between timed iterations (256 MiB fill); the scene itself is staged in shared memory",
@@ -358,7 +374,9 @@ def main():
 
             S = oracle.Scene(flat)
             cores = host_cores()
-            cpu_spp = spp if cores >= 8 else max(1, spp // 4)
+            # bounded sample: about 15 s of CPU work at ~0.25 G tests/s per core (2.6 rays per sample)
+            budget = 15.0 * 0.25e9 * cores / (nx * ny * 2.6 * flat.n_spheres)
+            cpu_spp = int(max(1, min(spp, budget)))
             S.render_accumulate(cam_type, cam, nx, ny, 0, 1, depth, seed=9, n_threads=cores)          # warm-up
             t0 = time.perf_counter()
             _, c = S.render_accumulate(cam_type, cam, nx, ny, 0, cpu_spp, depth, seed=1, n_threads=cores)
