@@ -41,17 +41,17 @@ struct RenderParams {
 };
 
 // ------------------------------------------------------------------------------------------
-// Culler: the FP32 test, per (ray, sphere), 9 FP32-pipe instructions + 1 funnel shift.  The 17-flop
+// Culler: the FP32 test, per (ray, sphere), 9 FP32-pipe instructions (8 FFMA + 1 FADD) + 1 funnel shift.  The 17-flop
 // test of SURVEY §8(d) is evaluated in expanded form so that everything that depends on the ray alone
 // or on the sphere alone is hoisted (f = o - c never materialises):
 //     b   = o.h - c.h                     3 FFMA   seeded with the ray's  P = o.h
 //     s   = (r2i - c.c) + 2 o.c           3 FFMA   seeded with the sphere's W = r2i - c.c, ray holds m = -2 o
 //     nc  = s - |o|^2                     1 FADD   ray holds Q = |o|^2 (deflated, see below)
-//     key = b * min(b, 0) + nc            1 FMNMX + 1 FFMA
+//     key = b * min(b, 0) + nc            2 FFMA   (c c - c |c| with c = b / sqrt 2; see key_bits)
 // with h = d * sqrt(1+eps) / |d| (a = d.d folded in).  key >= 0  <=>  (approaching and discriminant
 // >= 0) or (origin inside the sphere): exactly the spheres that can have a root in front of the
 // origin.  Rounding: with u = 2^-24 the computed key differs from the exact one by at most
-// u (32.6 |o|^2 + 32.6 |c|^2 + 4.1 r2i) (DESIGN.md "Precision"); the ray's share is taken off Q
+// u (33.6 |o|^2 + 33.6 |c|^2 + 4.1 r2i) (DESIGN.md "Precision"); the ray's share is taken off Q
 // (Q = |o|^2 (1 - 54 u)), the sphere's share is added to W on the host, so the cull only ever
 // over-reports.  tests/test_gpu_parity.py::test_cull_never_under_reports checks exactly that.
 // No branch and no compaction in the loop: the sign bits of a ray's keys are funnel-shifted into one
@@ -85,9 +85,9 @@ constexpr float RAY_DEFLATE = 1.0f - 3.2e-6f;  // 1 - 54 u: the ray's share of t
 // bit m - 1 - j; a CLEAR bit = that (ray, sphere) pair survived the cull; bits >= m are set.
 template <int R, int BLOCK>
 struct Culler {
-    float hx[R], hy[R], hz[R];     // cull direction: d * sqrt(1 + eps) / |d|
+    float hx[R], hy[R], hz[R];     // cull direction / sqrt 2: d * sqrt((1 + eps) / 2) / |d|
     float mx[R], my[R], mz[R];     // -2 o
-    float P[R];                    // o . h
+    float P[R];                    // o . h  (with that h)
     float Q[R];                    // |o|^2 (1 - 54 u)
 
     static constexpr int LIST_WORDS = CHUNK_GROUPS * R;                         // per thread
@@ -95,7 +95,7 @@ struct Culler {
 
     __device__ __forceinline__ void set_ray(int r, float o_x, float o_y, float o_z, float d_x, float d_y, float d_z) {
         float a = fmaf(d_z, d_z, fmaf(d_y, d_y, d_x * d_x));
-        float s = rsqrtf(a) * (1.0f + 0.5f * CULL_EPS);
+        float s = rsqrtf(a) * ((1.0f + 0.5f * CULL_EPS) * 0.70710678118654752f);   // h / sqrt 2, see key_bits
         hx[r] = d_x * s; hy[r] = d_y * s; hz[r] = d_z * s;
         mx[r] = -2.0f * o_x; my[r] = -2.0f * o_y; mz[r] = -2.0f * o_z;
         P[r] = fmaf(o_z, hz[r], fmaf(o_y, hy[r], o_x * hx[r]));
@@ -122,10 +122,13 @@ struct Culler {
     }
 
     // S = (-cx, -cy, -cz, W = r2i - c.c)
+    // b min(b, 0) is evaluated as c c - c |c| with c = b / sqrt 2 (the ray's h and P carry the 1 / sqrt 2): two FFMAs,
+    // the second with SASS operand modifiers (-c, |c|), instead of FMNMX + FFMA — the ALU pipe then only sees the
+    // funnel shift (loopbench: 11.5 vs 12.1 issue cycles per warp-test)
     __device__ __forceinline__ unsigned key_bits(const float4 S, int r) const {
-        float b = fmaf(S.x, hx[r], fmaf(S.y, hy[r], fmaf(S.z, hz[r], P[r])));
+        float c = fmaf(S.x, hx[r], fmaf(S.y, hy[r], fmaf(S.z, hz[r], P[r])));
         float s = fmaf(S.x, mx[r], fmaf(S.y, my[r], fmaf(S.z, mz[r], S.w)));
-        return __float_as_uint(fmaf(b, fminf(b, 0.f), s - Q[r]));
+        return __float_as_uint(fmaf(-c, fabsf(c), fmaf(c, c, s - Q[r])));
     }
 
     // One chunk: `count` records (a multiple of CULL_PAD, <= CHUNK) starting at shared address sa.  Writes the

@@ -10,3 +10,5 @@ python - <<'PY'
 import json
 d=json.load(open("gpurun_out/bench_c2.json")); print(d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["dominant_kernel"], d["e2e"]["value"], d.get("cpu_baseline",{}).get("value"))
 PY
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_c2_reference.json 2> gpurun_out/bench_c2_reference.err; echo "reference arm exit $?"
+python bench.py --variant 0 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_mega.json 2> gpurun_out/bench_c2_mega.err; echo "megakernel exit $?"
