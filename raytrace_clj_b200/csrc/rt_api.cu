@@ -140,7 +140,7 @@ int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
 }
 
 constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 2.6)
-constexpr size_t kWaveCapacity = 1u << 22;  // paths in flight per device (all lanes together)
+constexpr size_t kWaveCapacity = 1u << 24;  // paths in flight per device (all lanes together; ~5 GB of queues at full size)
 constexpr int kWaveChunk = 4;           // iterations enqueued between two polls of the queue count
 constexpr unsigned kTailEntries = 1u << 16;   // queue length at which the cooperative tail kernel takes over
 
