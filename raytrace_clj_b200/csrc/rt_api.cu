@@ -139,10 +139,9 @@ int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
     return RT_OK;
 }
 
-constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 2.6)
 constexpr size_t kWaveCapacity = 1u << 24;  // paths in flight per device (all lanes together; ~5 GB of queues at full size)
 constexpr int kWaveChunk = 4;           // iterations enqueued between two polls of the queue count
-constexpr unsigned kTailEntries = 1u << 16;   // queue length at which the cooperative tail kernel takes over
+constexpr unsigned kTailEntries = 1u << 19;   // queue length at which the per-CTA tail kernel takes over
 
 void free_lane(DeviceBuffers::WaveLane& L) {
     if (L.queue) cudaFree(L.queue);
@@ -264,12 +263,12 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     // cooperative tail kernel: every CTA must be resident, also next to the other lane's tail
     static const unsigned tail_entries = (unsigned)std::max(0, env_int("RT_TAIL_ENTRIES", (int)kTailEntries));
     const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<1, 256>::LIST_BYTES;
-    int tail_bps = 0, coop = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, d.dev);
+    int tail_bps = 0;
     RT_CUDA(ctx, cudaFuncSetAttribute(wf_tail<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
     RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_bps, wf_tail<256>, 256, tail_smem));
-    const int tail_grid = d.sm_count * (n_lanes > 1 ? 1 : std::min(tail_bps, 2));
-    const bool tail_ok = coop && tail_bps >= n_lanes && tail_entries > 0 && !ctx->profile;
+    static const int tail_ctas = std::max(1, env_int("RT_TAIL_CTAS_PER_SM", 0));
+    const int tail_grid = d.sm_count * (env_int("RT_TAIL_CTAS_PER_SM", 0) > 0 ? tail_ctas : (n_lanes > 1 ? 1 : std::max(1, std::min(tail_bps, 2))));
+    const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile;
 
     static const int light_block = std::max(64, std::min(256, env_int("RT_LIGHT_BLOCK", 256) / 32 * 32));
     const int light_grid = d.sm_count * 8 * 256 / light_block;
@@ -352,8 +351,8 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     done[l] = true;
                 } else if (tail_ok && snap.exhausted && snap.qcount[W[l].cur] <= tail_entries) {
                     // no new work can appear and the queue is short: one cooperative launch finishes this lane
-                    void* args[] = {(void*)&W[l]};
-                    RT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)wf_tail<256>, dim3(tail_grid), dim3(256), args, tail_smem, st[l]));
+                    wf_tail<256><<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
+                    RT_CUDA(ctx, cudaGetLastError());
                     ctx->n_launches += 1;
                     done[l] = true;
                 }

@@ -437,7 +437,10 @@ template <int R, int BLOCK>
 struct PairSink {
     unsigned idx0;                 // queue entry of ray r = idx0 + 32 r
     unsigned n;                    // live entries in the queue
-    const WaveParams* W;
+    uint2* pairs;                  // by value (not a WaveParams*): keeps a caller's modified copy of the params in registers
+    unsigned pair_cap;
+    unsigned long long* best_key;
+    WaveState* st;
 
     __device__ __forceinline__ void flush(const uint32_t* list, unsigned long long nz, int count, int kbase) {
         if (!__any_sync(0xffffffffu, nz != 0ull)) return;
@@ -455,9 +458,9 @@ struct PairSink {
         }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&W->st->npairs, total);
+        if (lane == 0) base = atomicAdd(&st->npairs, total);
         base = __shfl_sync(0xffffffffu, base, 0);
-        const bool fits = base + total <= W->pair_cap;
+        const bool fits = base + total <= pair_cap;
         unsigned w = base + incl - np;
         SurvivorIter<R, BLOCK> it;
         it.begin(nz, count);
@@ -465,10 +468,10 @@ struct PairSink {
         while (it.next(list, r, k)) {
             const unsigned idx = idx0 + 32u * (unsigned)r;
             if (fits) {
-                W->pairs[w] = make_uint2(idx, (unsigned)(kbase + k));
+                pairs[w] = make_uint2(idx, (unsigned)(kbase + k));
             } else {
-                if (w < W->pair_cap) W->pairs[w] = make_uint2(PAIR_NULL, 0u);
-                if (idx < n) W->best_key[idx] = BEST_KEY_OVERFLOW;
+                if (w < pair_cap) pairs[w] = make_uint2(PAIR_NULL, 0u);
+                if (idx < n) best_key[idx] = BEST_KEY_OVERFLOW;
             }
             ++w;
         }
@@ -481,8 +484,14 @@ struct PairSink {
 // item number this warp has already claimed (or ~0u); returns the first claimed number beyond the range, so a
 // following range can use it.
 constexpr unsigned ITEM_NONE = 0xffffffffu;
+// The CTAs that cooperate on one queue: the whole grid (bid = blockIdx.x of nblk = gridDim.x), or a single CTA
+// working alone on its own slice of the queue (bid 0 of 1; wf_tail).
+struct Scope {
+    unsigned bid, nblk;
+};
+__device__ __forceinline__ Scope grid_scope() { return Scope{blockIdx.x, gridDim.x}; }
 template <int R, int BLOCK>
-__device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, int cur, unsigned e0, unsigned e1, int parts,
+__device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope sc_, int cur, unsigned e0, unsigned e1, int parts,
                                                     unsigned item0, unsigned claimed, float4* s_cull, uint32_t* s_list) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
@@ -491,8 +500,11 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, int cur
     Culler<R, BLOCK> K;
     PairSink<R, BLOCK> sink;
     sink.n = e1;
-    sink.W = &W;
-    unsigned item = blockIdx.x * warps + warp;                     // tiled scenes: CTA-uniform static order
+    sink.pairs = W.pairs;
+    sink.pair_cap = W.pair_cap;
+    sink.best_key = W.best_key;
+    sink.st = W.st;
+    unsigned item = sc_.bid * warps + warp;                        // tiled scenes: CTA-uniform static order
     const unsigned uniform_end = (n_items + warps - 1) / warps * warps;
     for (;;) {
         if (P.preloaded) {
@@ -514,7 +526,8 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, int cur
         RT_FOR_R {
             unsigned idx = sink.idx0 + 32 * r;
             if (idx < e1 && batch < n_batches) {
-                float4 a = W.queue[cur][3 * (size_t)idx], b = W.queue[cur][3 * (size_t)idx + 1];
+                const float4* qc = cur ? W.queue[1] : W.queue[0];   // a select, not a dynamic index (keeps copies of W in registers)
+                float4 a = qc[3 * (size_t)idx], b = qc[3 * (size_t)idx + 1];
                 K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z);
                 if (part == 0) {
                     W.best_t[idx] = BEST_T_INIT;
@@ -526,7 +539,7 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, int cur
         }
         if (parts > 1) K.run_slice(P.sc, s_cull, s_list, sink, (int)part, parts);
         else           K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, sink);
-        item += gridDim.x * warps;
+        item += sc_.nblk * warps;
     }
     return ITEM_NONE;
 }
@@ -537,23 +550,23 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, int cur
 // batches per warp the sphere list is split across warps too (the pairs merge in wf_refine).
 // R = 1 instantiates only the short form.
 template <int R, int BLOCK>
-__device__ __forceinline__ void wf_cull_body(const WaveParams& W, int cur, unsigned n, float4* s_cull, uint32_t* s_list) {
+__device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int cur, unsigned n, float4* s_cull, uint32_t* s_list) {
     const RenderParams& P = W.base;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
-    const unsigned grid_warps = gridDim.x * (BLOCK / 32);
+    if (sc_.bid == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
+    const unsigned grid_warps = sc_.nblk * (BLOCK / 32);
     if (R > 1 && !P.preloaded) {
-        wf_cull_batches<R, BLOCK>(W, cur, 0u, n, 1, 0u, ITEM_NONE, s_cull, s_list);
+        wf_cull_batches<R, BLOCK>(W, sc_, cur, 0u, n, 1, 0u, ITEM_NONE, s_cull, s_list);
     } else if (R > 1 && n >= grid_warps * 64u) {
         const unsigned tail = grid_warps * 64u;                                       // two one-ray batches per warp
         const unsigned n_bulk = (n - tail) / (32u * R) * (32u * R), bulk_items = n_bulk / (32u * R);
-        const unsigned next = wf_cull_batches<R, BLOCK>(W, cur, 0u, n_bulk, 1, 0u, ITEM_NONE, s_cull, s_list);
-        wf_cull_batches<1, BLOCK>(W, cur, n_bulk, n, 1, bulk_items, next, s_cull, s_list);
+        const unsigned next = wf_cull_batches<R, BLOCK>(W, sc_, cur, 0u, n_bulk, 1, 0u, ITEM_NONE, s_cull, s_list);
+        wf_cull_batches<1, BLOCK>(W, sc_, cur, n_bulk, n, 1, bulk_items, next, s_cull, s_list);
     } else {
         const unsigned b1 = (n + 31) / 32;
         int parts = 1;
         if (P.preloaded)
             while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
-        wf_cull_batches<1, BLOCK>(W, cur, 0u, n, parts, 0u, ITEM_NONE, s_cull, s_list);
+        wf_cull_batches<1, BLOCK>(W, sc_, cur, 0u, n, parts, 0u, ITEM_NONE, s_cull, s_list);
     }
 }
 
@@ -567,7 +580,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
     if (n == 0) return;
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
-    wf_cull_body<R, BLOCK>(W, W.cur, n, s_cull, s_list);
+    wf_cull_body<R, BLOCK>(W, grid_scope(), W.cur, n, s_cull, s_list);
 }
 
 // one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved).
@@ -579,29 +592,30 @@ __device__ __forceinline__ unsigned wf_cand_region(const WaveParams& W, unsigned
     return ((W.pair_cap + total_warps * 32u - 1u) / (total_warps * 32u)) * 32u;   // pairs one warp can see
 }
 
-__device__ __forceinline__ void wf_refine_body(const WaveParams& W, int cur) {
+__device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, int cur) {
     const RenderParams& P = W.base;
     const unsigned n = W.st->qcount[cur];
     const unsigned npairs = min(W.st->npairs, W.pair_cap);
     const unsigned lane = threadIdx.x & 31u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (sc_.bid == 0 && threadIdx.x == 0) {
         W.st->batch = 0;               // wf_cull is done with it
         W.st->qcount[cur ^ 1] = 0;     // wf_shade appends to it next
         atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);   // + the direct spheres' exact tests, counted by wf_shade
     }
-    const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
-    const unsigned warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned total_warps = sc_.nblk * (blockDim.x >> 5);
+    const unsigned warp_id = sc_.bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const size_t region = (size_t)warp_id * wf_cand_region(W, total_warps);
     unsigned cnt = 0;
-    const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < npairs; i0 += stride) {   // warp-uniform
+    const unsigned stride = sc_.nblk * blockDim.x;
+    for (unsigned i0 = sc_.bid * blockDim.x + threadIdx.x - lane; i0 < npairs; i0 += stride) {   // warp-uniform
         const unsigned i = i0 + lane;
         bool cand = false;
         uint2 pr = make_uint2(PAIR_NULL, 0u);
         double t = CUDART_INF;
         if (i < npairs) pr = W.pairs[i];
         if (pr.x != PAIR_NULL && pr.x < n) {
-            const float4 a = W.queue[cur][3 * (size_t)pr.x], b = W.queue[cur][3 * (size_t)pr.x + 1];
+            const float4* qc = cur ? W.queue[1] : W.queue[0];
+            const float4 a = qc[3 * (size_t)pr.x], b = qc[3 * (size_t)pr.x + 1];
             const unsigned long long seen = __ldcg(&W.best_t[pr.x]);
             t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, (int)pr.y, a.x, a.y, a.z, b.x, b.y, b.z,
                                  a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
@@ -621,15 +635,15 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, int cur) {
     }
     if (lane == 0) W.cand_count[warp_id] = cnt;
 }
-__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) { wf_refine_body(W, W.cur); }
+__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) { wf_refine_body(W, grid_scope(), W.cur); }
 
 // exact ties go to the lower caller index, the Hitlist rule (hitable.clj:17-26): candidates that own the final
 // minimum t race with atomicMin on (caller index, k).  Same grid shape as wf_refine (warp-private regions).
-__device__ __forceinline__ void wf_tiebreak_body(const WaveParams& W) {
+__device__ __forceinline__ void wf_tiebreak_body(const WaveParams& W, Scope sc_) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
-    const unsigned warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned total_warps = sc_.nblk * (blockDim.x >> 5);
+    const unsigned warp_id = sc_.bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const size_t region = (size_t)warp_id * wf_cand_region(W, total_warps);
     const unsigned cnt = W.cand_count[warp_id];
     for (unsigned j = lane; j < cnt; j += 32) {
@@ -638,7 +652,7 @@ __device__ __forceinline__ void wf_tiebreak_body(const WaveParams& W) {
             atomicMin(&W.best_key[pr.x], (((unsigned long long)(__ldg(&P.sc.orig_id[pr.y]) + 1)) << 32) | pr.y);
     }
 }
-__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) { wf_tiebreak_body(W); }
+__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) { wf_tiebreak_body(W, grid_scope()); }
 
 // exact closest hit of one ray by brute force in FP64 (only for entries whose pairs overflowed the pair buffer)
 __device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, float oy, float oz, float dx, float dy, float dz,
@@ -658,19 +672,22 @@ __device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, floa
 }
 
 // s_ctr: shared counters of the calling kernel (DC_COUNT slots, zeroed by the caller); returns samples generated
-__device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, int cur, unsigned* s_ctr) {
+__device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_, int cur, unsigned* s_ctr) {
     const RenderParams& P = W.base;
     const unsigned n = W.st->qcount[cur];
     const unsigned lane = threadIdx.x & 31u;
-    const float4* qc = W.queue[cur];
-    float4* qn = W.queue[cur ^ 1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float4* qc = cur ? W.queue[1] : W.queue[0];
+    float4* qn = cur ? W.queue[0] : W.queue[1];
+    if (sc_.bid == 0 && threadIdx.x == 0) {
         W.st->npairs = 0;   // refine / tie-break are done with it
         W.st->exhausted = (*(volatile unsigned long long*)P.work_counter >= P.total_work) ? 1u : 0u;
     }
+    // once the (sample, pixel) counter is known to have run out, finished lanes stop asking it (a returning atomic
+    // per tile); the flag only ever goes 0 -> 1, so racing with the writer above is harmless
+    const bool no_work = *(volatile unsigned*)&W.st->exhausted != 0u;
     unsigned n_samples = 0, n_direct = 0;
-    const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned idx0 = blockIdx.x * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
+    const unsigned stride = sc_.nblk * blockDim.x;
+    for (unsigned idx0 = sc_.bid * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
         const unsigned idx = idx0 + lane;
         const bool have = idx < n;
         bool cont = false;
@@ -727,7 +744,7 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, int cur, 
         }
         // a finished path frees its lane for the next (sample, pixel)
         unsigned long long w;
-        if (take_work(P, have && !cont, lane, w)) {
+        if (!no_work && take_work(P, have && !cont, lane, w)) {
             make_path(P, w, a, b, c);
             cont = true;
             n_samples++;
@@ -747,41 +764,69 @@ __global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
     __shared__ unsigned s_ctr[DC_COUNT];
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned n_samples = wf_shade_body(W, W.cur, s_ctr);
+    const unsigned n_samples = wf_shade_body(W, grid_scope(), W.cur, s_ctr);
     atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
     __syncthreads();
     if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
 }
 
-// Tail of a render: the work counter is exhausted and the queue is short.  ONE cooperative launch runs all
-// the remaining bounces (up to the depth cutoff), stages of an iteration separated by grid.sync() instead of
-// kernel boundaries: the sphere list is staged in shared memory once, and a tiny iteration costs a few
-// barrier latencies instead of four kernel-launch floors (~30 us measured per iteration before).
+// Tail of a render: the work counter is exhausted and the queue is short (up to 50 more bounces of a shrinking
+// handful of paths).  ONE launch finishes the lane: the queue is cut into one slice per CTA, and every CTA runs
+// the wavefront stages on its own slice by itself — its queue counters live in shared memory, the stages are
+// separated by __syncthreads() (tens of cycles) instead of kernel boundaries (~8 us of launch floors per
+// iteration) or grid.sync() (the cooperative form of this kernel: ~20 us per iteration, 0.75 ms per render).
+// The slices are the CTA's ranges of the lane's own buffers, so a slice's population can only shrink in place.
+constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 1.5)
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     __shared__ unsigned s_ctr[DC_COUNT];
-    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
-    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
-    __syncthreads();
-    unsigned n_samples = 0;
+    __shared__ WaveState s_st;
     int cur = W.cur;
+    const unsigned n_all = W.st->qcount[cur];
+    const unsigned K = ((n_all + gridDim.x - 1) / gridDim.x + 31u) / 32u * 32u;      // slice capacity
+    const unsigned first = blockIdx.x * K;
+    if (first >= n_all) return;                                                       // CTA-uniform
+    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        s_st.qcount[cur] = min(K, n_all - first);
+        s_st.qcount[cur ^ 1] = 0;
+        s_st.batch = 0;
+        s_st.npairs = 0;
+        s_st.exhausted = 1;
+    }
+    // this CTA's view of the lane's buffers
+    const unsigned warps = BLOCK / 32;
+    WaveParams L = W;
+    L.queue[0] = W.queue[0] + 3 * (size_t)first;
+    L.queue[1] = W.queue[1] + 3 * (size_t)first;
+    L.best_t = W.best_t + first;
+    L.best_key = W.best_key + first;
+    L.pairs = W.pairs + (size_t)first * kPairsPerEntry;
+    L.pair_cap = K * kPairsPerEntry;
+    const size_t cand_slice = (size_t)wf_cand_region(L, warps) * warps;
+    L.cands = W.cands + (size_t)blockIdx.x * cand_slice;
+    L.cand_t = W.cand_t + (size_t)blockIdx.x * cand_slice;
+    L.cand_count = W.cand_count + blockIdx.x * warps;
+    L.st = &s_st;
+    L.capacity = (int)K;
+    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
+    const Scope solo{0u, 1u};
+    unsigned n_samples = 0;
     for (;;) {
-        const unsigned n = *(volatile unsigned*)&W.st->qcount[cur];
+        __syncthreads();
+        const unsigned n = *(volatile unsigned*)&s_st.qcount[cur];
         if (n == 0) break;
-        wf_cull_body<1, BLOCK>(W, cur, n, s_cull, s_list);
-        grid.sync();
-        wf_refine_body(W, cur);
-        grid.sync();
-        wf_tiebreak_body(W);
-        grid.sync();
-        n_samples += wf_shade_body(W, cur, s_ctr);
-        grid.sync();
+        wf_cull_body<1, BLOCK>(L, solo, cur, n, s_cull, s_list);
+        __syncthreads();
+        wf_refine_body(L, solo, cur);
+        __syncthreads();
+        wf_tiebreak_body(L, solo);
+        __syncthreads();
+        n_samples += wf_shade_body(L, solo, cur, s_ctr);
         cur ^= 1;
     }
     atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
