@@ -3,6 +3,7 @@
 //   FORM 0: translated form  f = o - c; b = f.h; nc = r2 - f.f            (11 FP32 instr / test, round-1 first version)
 //   FORM 1: expanded form    b = P - c.h; s = W + 2 o.c; nc = s - Q       ( 9 FP32 instr / test, shipped)
 //   FORM 2: FORM 1 with b min(b,0) written c c - c |c| (no FMNMX: the ALU pipe only sees the funnel shift)
+//   FORM 3: all rays share the origin: the sphere's record carries (W + 2 o.c) - |o|^2, 5 FFMA per test (shipped for camera rays)
 //   MODE 0: math only (keys summed)   1: + sign funnel, one mask word per 32 spheres per ray (shipped)
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -53,6 +54,9 @@ __global__ void __launch_bounds__(BLOCK) k(const float4* __restrict__ spheres, f
                         float b = fmaf(S.x, hx[r], fmaf(S.y, hy[r], fmaf(S.z, hz[r], P[r])));
                         float t = fmaf(S.x, ax[r], fmaf(S.y, ay[r], fmaf(S.z, az[r], S.w)));
                         key = fmaf(b, fminf(b, 0.f), t - Q[r]);
+                    } else if (FORM == 3) {   // common-origin form: (W + 2 o.c) - |o|^2 precomputed per sphere in S.w
+                        float b = fmaf(S.x, hx[r], fmaf(S.y, hy[r], fmaf(S.z, hz[r], P[r])));
+                        key = fmaf(-b, fabsf(b), fmaf(b, b, S.w));
                     } else {   // FORM 2: b min(b,0) = c c - c |c| with c = b / sqrt 2 (h, P prescaled): FMNMX -> FFMA with |.| modifier
                         float b = fmaf(S.x, hx[r], fmaf(S.y, hy[r], fmaf(S.z, hz[r], P[r])));
                         float t = fmaf(S.x, ax[r], fmaf(S.y, ay[r], fmaf(S.z, az[r], S.w)));
@@ -107,8 +111,10 @@ int main() {
     run<1, 0, 128, 8>("expanded form, math only (9+1 instr)", sph, out, 5);
     run<0, 1, 128, 8>("translated form + funnel + mask words", sph, out, 5);
     run<1, 1, 128, 8>("expanded form + funnel + mask words (shipped)", sph, out, 5);
-    run<2, 1, 128, 8>("expanded, FMNMX replaced by FFMA |.| (all-FMA key)", sph, out, 5);
+    run<2, 1, 128, 8>("expanded, all-FMA key c c - c |c| (shipped)", sph, out, 5);
     run<2, 1, 128, 8>("expanded, FMNMX replaced by FFMA |.| (all-FMA key)", sph, out, 4);
+    run<3, 1, 128, 8>("common-origin form (5 FFMA + funnel), shipped for camera rays", sph, out, 4);
+    run<3, 1, 128, 8>("common-origin form (5 FFMA + funnel)", sph, out, 5);
     run<1, 1, 128, 4>("expanded form + funnel + mask words", sph, out, 5);
     run<1, 1, 128, 16>("expanded form + funnel + mask words", sph, out, 5);
     run<1, 1, 128, 8>("expanded form + funnel + mask words", sph, out, 3);

@@ -226,7 +226,7 @@ int env_int(const char* name, int dflt) {
 template <int BLOCK, int MINB>
 int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WaveParams)) {
     *kern = wf_cull<kR, BLOCK, MINB>;
-    *smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<kR, BLOCK>::LIST_BYTES;
+    *smem = 2 * (size_t)ctx->cull_cap * sizeof(float4) + Culler<kR, BLOCK>::LIST_BYTES;   // general + common-origin tiles
     RT_CUDA(ctx, cudaFuncSetAttribute(*kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, *kern, BLOCK, *smem));
     if (*bps < 1) return fail(ctx, RT_ERR_CUDA, "cull kernel does not fit on an SM");
@@ -347,9 +347,9 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 DeviceBuffers::WaveLane& L = d.lanes[l];
                 RT_CUDA(ctx, cudaEventSynchronize(L.ev_poll[(chunk - 1) & 1]));
                 const WaveState& snap = L.h_state[(chunk - 1) & 1];
-                if (snap.qcount[W[l].cur] == 0) {   // kWaveChunk is even: same parity
+                if (snap.cnt[W[l].cur][0] == 0 && snap.cnt[W[l].cur][1] == 0) {   // kWaveChunk is even: same parity
                     done[l] = true;
-                } else if (tail_ok && snap.exhausted && snap.qcount[W[l].cur] <= tail_entries) {
+                } else if (tail_ok && snap.exhausted && snap.cnt[W[l].cur][1] == 0 && snap.cnt[W[l].cur][0] <= tail_entries) {
                     // no new work can appear and the queue is short: one cooperative launch finishes this lane
                     wf_tail<256><<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
                     RT_CUDA(ctx, cudaGetLastError());
@@ -403,6 +403,8 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
     P.total_work = (unsigned long long)sample_count * (unsigned long long)nx * (unsigned long long)P.rows_in_shard;
     P.cull_cap = ctx->cull_cap;
     P.preloaded = ctx->preloaded;
+    static const int common_env = env_int("RT_COMMON_ORIGIN", 1);
+    P.common_origin = (common_env && (ctx->cam.type == CAM_PINHOLE || ctx->cam.lens_radius == 0.f)) ? 1 : 0;
     RT_CUDA(ctx, cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long), stream));
     if (P.total_work == 0) return RT_OK;
     if ((sample_begin + sample_count) >= (1 << 24)) return fail(ctx, RT_ERR_ARG, "sample index must stay below 2^24");

@@ -38,6 +38,7 @@ struct RenderParams {
     unsigned long long total_work;        // sample_count * nx * rows_in_shard
     int cull_cap;                         // float4 slots of the shared-memory sphere tile
     int preloaded;                        // 1: whole scene fits one tile (loaded once per CTA)
+    int common_origin;                    // 1: every camera ray starts at cam.origin (pinhole, or aperture 0)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -83,12 +84,18 @@ constexpr float RAY_DEFLATE = 1.0f - 3.2e-6f;  // 1 - 54 u: the ray's share of t
 // mask words of a thread: word (group g, ray r) at list[(g * R + r) * BLOCK + threadIdx.x] (one bank per lane).
 // Bit layout: sphere j of a group of m spheres (m = 32, or the remainder in the last group of a chunk) is at
 // bit m - 1 - j; a CLEAR bit = that (ray, sphere) pair survived the cull; bits >= m are set.
-template <int R, int BLOCK>
+// COMMON = true: every ray of the batch starts at the SAME origin (camera rays of a pinhole or zero-aperture
+// camera, 39 % of all rays on the random scene).  Then s - Q = (W + 2 o.c) - |o|^2 depends on the sphere only: it
+// is computed once per sphere per kernel (common_record) and stored in the record's 4th component, and the test
+// shrinks to the 3-FFMA chain of c plus the 2 key FFMAs: 5 FP32 instructions + 1 funnel shift instead of 9 + 1,
+// with bit-identical keys.
+template <int R, int BLOCK, bool COMMON = false>
 struct Culler {
     float hx[R], hy[R], hz[R];     // cull direction / sqrt 2: d * sqrt((1 + eps) / 2) / |d|
     float mx[R], my[R], mz[R];     // -2 o
     float P[R];                    // o . h  (with that h)
     float Q[R];                    // |o|^2 (1 - 54 u)
+    float cox, coy, coz;           // COMMON: the origin every ray of the kernel's common-origin region starts at
 
     static constexpr int LIST_WORDS = CHUNK_GROUPS * R;                         // per thread
     static constexpr size_t LIST_BYTES = (size_t)LIST_WORDS * BLOCK * sizeof(uint32_t);   // per CTA
@@ -101,7 +108,8 @@ struct Culler {
         P[r] = fmaf(o_z, hz[r], fmaf(o_y, hy[r], o_x * hx[r]));
         Q[r] = fmaf(o_z, o_z, fmaf(o_y, o_y, o_x * o_x)) * RAY_DEFLATE;
     }
-    // a dead slot: nc = s - inf = -inf for every sphere, so the key's sign bit is always set
+    // a dead slot.  General form: nc = s - inf = -inf for every sphere, so the key's sign bit is always set.
+    // (Common-origin form: nothing about the ray can kill it — the sinks drop a dead ray's words instead.)
     __device__ __forceinline__ void kill(int r) {
         hx[r] = 1.f; hy[r] = 0.f; hz[r] = 0.f;
         mx[r] = my[r] = mz[r] = 0.f;
@@ -111,7 +119,11 @@ struct Culler {
 
     // opaque to the optimiser: otherwise ptxas rematerialises h (RSQ + 4 FMUL) per sphere to save registers
     __device__ __forceinline__ void pin() {
-        RT_FOR_R asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]), "+f"(mx[r]), "+f"(my[r]), "+f"(mz[r]), "+f"(P[r]), "+f"(Q[r]));
+        if (COMMON) {
+            RT_FOR_R asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]), "+f"(P[r]));
+        } else {
+            RT_FOR_R asm volatile("" : "+f"(hx[r]), "+f"(hy[r]), "+f"(hz[r]), "+f"(mx[r]), "+f"(my[r]), "+f"(mz[r]), "+f"(P[r]), "+f"(Q[r]));
+        }
     }
 
     static __device__ __forceinline__ unsigned list_begin(const uint32_t* list) {
@@ -121,12 +133,22 @@ struct Culler {
         return list[(g * R + r) * BLOCK + threadIdx.x];
     }
 
-    // S = (-cx, -cy, -cz, W = r2i - c.c)
+    // the record of a sphere for rays that all start at o: (-cx, -cy, -cz, (W + 2 o.c) - |o|^2 (1 - 54 u)) — the
+    // very operations key_bits applies per ray in the general form, applied once
+    static __device__ __forceinline__ float4 common_record(float4 S, float o_x, float o_y, float o_z) {
+        const float m_x = -2.0f * o_x, m_y = -2.0f * o_y, m_z = -2.0f * o_z;
+        const float q = fmaf(o_z, o_z, fmaf(o_y, o_y, o_x * o_x)) * RAY_DEFLATE;
+        S.w = fmaf(S.x, m_x, fmaf(S.y, m_y, fmaf(S.z, m_z, S.w))) - q;
+        return S;
+    }
+
+    // S = (-cx, -cy, -cz, W = r2i - c.c)   [COMMON: the 4th component is common_record's]
     // b min(b, 0) is evaluated as c c - c |c| with c = b / sqrt 2 (the ray's h and P carry the 1 / sqrt 2): two FFMAs,
     // the second with SASS operand modifiers (-c, |c|), instead of FMNMX + FFMA — the ALU pipe then only sees the
     // funnel shift (loopbench: 11.5 vs 12.1 issue cycles per warp-test)
     __device__ __forceinline__ unsigned key_bits(const float4 S, int r) const {
         float c = fmaf(S.x, hx[r], fmaf(S.y, hy[r], fmaf(S.z, hz[r], P[r])));
+        if (COMMON) return __float_as_uint(fmaf(-c, fabsf(c), fmaf(c, c, S.w)));
         float s = fmaf(S.x, mx[r], fmaf(S.y, my[r], fmaf(S.z, mz[r], S.w)));
         return __float_as_uint(fmaf(-c, fabsf(c), fmaf(c, c, s - Q[r])));
     }
@@ -196,7 +218,11 @@ struct Culler {
             const int count = min(cap, sc.n_cull - base);
             if (!preloaded) {
                 __syncthreads();
-                for (int i = threadIdx.x; i < count; i += BLOCK) s_cull[i] = __ldg(&sc.cull_a[base + i]);
+                for (int i = threadIdx.x; i < count; i += BLOCK) {
+                    float4 S = __ldg(&sc.cull_a[base + i]);
+                    if (COMMON) S = common_record(S, cox, coy, coz);
+                    s_cull[i] = S;
+                }
                 __syncthreads();
             }
             run_range(s_cull, 0, count, base, list, sink);
@@ -332,13 +358,21 @@ struct RefineSink {
 //                  + prefix popc + one atomic per warp, same for the (sample, pixel) work counter)
 //   The host enqueues iterations ahead and polls the queue count every few iterations.
 // ------------------------------------------------------------------------------------------
-struct WaveState {
-    unsigned qcount[2];            // entries in queue[i]
+// A queue holds two populations: paths in flight at [0, qcount) and, when every camera ray starts at the same
+// origin (WaveParams::base.common_origin), the fresh camera rays at [capacity - pcount, capacity) — the cull runs
+// its common-origin form over those (Culler<.., COMMON>).
+struct alignas(8) WaveState {
+    unsigned cnt[2][2];            // cnt[i][0]: general entries of queue[i]; cnt[i][1]: its common-origin entries, at the
+                                   // top of the queue.  One 64-bit word per queue: wf_shade claims both with ONE atomic.
     unsigned batch;                // next batch (wf_cull)
     unsigned npairs;               // pairs emitted this iteration
     unsigned exhausted;            // the (sample, pixel) work counter has run past the end
-    unsigned pad[3];
+    unsigned pad;
 };
+// entry index of the i-th entry of a queue holding n_g general and n_p common-origin entries
+__device__ __forceinline__ unsigned wf_entry(unsigned i, unsigned n_g, unsigned n_p, unsigned capacity) {
+    return i < n_g ? i : capacity - n_p + (i - n_g);
+}
 
 struct WaveParams {
     RenderParams base;
@@ -414,15 +448,18 @@ __global__ void wf_init(unsigned long long* work_counter, unsigned long long val
 
 __global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned long long first, unsigned count) {
     const RenderParams& P = W.base;
+    const unsigned e0 = P.common_origin ? (unsigned)W.capacity - count : 0u;   // camera rays: the common-origin region
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         float4 a, b, c;
         make_path(P, first + i, a, b, c);
-        float4* q = W.queue[0] + 3 * (size_t)i;
+        float4* q = W.queue[0] + 3 * (size_t)(e0 + i);
         q[0] = a; q[1] = b; q[2] = c;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        W.st->qcount[0] = count;
-        W.st->qcount[1] = 0;
+        W.st->cnt[0][0] = P.common_origin ? 0u : count;
+        W.st->cnt[0][1] = P.common_origin ? count : 0u;
+        W.st->cnt[1][0] = 0;
+        W.st->cnt[1][1] = 0;
         W.st->batch = 0;
         W.st->npairs = 0;
         W.st->exhausted = 0;
@@ -436,13 +473,15 @@ __global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned 
 template <int R, int BLOCK>
 struct PairSink {
     unsigned idx0;                 // queue entry of ray r = idx0 + 32 r
-    unsigned n;                    // live entries in the queue
+    unsigned n;                    // end of the entry range being culled
+    unsigned long long live;       // bits 16 r .. 16 r + 15 set if ray r of this lane is a live entry
     uint2* pairs;                  // by value (not a WaveParams*): keeps a caller's modified copy of the params in registers
     unsigned pair_cap;
     unsigned long long* best_key;
     WaveState* st;
 
     __device__ __forceinline__ void flush(const uint32_t* list, unsigned long long nz, int count, int kbase) {
+        nz &= live;                                    // a dead ray's words (common-origin form) are not survivors
         if (!__any_sync(0xffffffffu, nz != 0ull)) return;
         const unsigned lane = threadIdx.x & 31u;
         unsigned np = 0;
@@ -490,14 +529,15 @@ struct Scope {
     unsigned bid, nblk;
 };
 __device__ __forceinline__ Scope grid_scope() { return Scope{blockIdx.x, gridDim.x}; }
-template <int R, int BLOCK>
+template <int R, int BLOCK, bool COMMON>
 __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope sc_, int cur, unsigned e0, unsigned e1, int parts,
                                                     unsigned item0, unsigned claimed, float4* s_cull, uint32_t* s_list) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
     const unsigned n_batches = (e1 - e0 + 32 * R - 1) / (32 * R);
     const unsigned n_items = n_batches * (unsigned)parts;          // (batch, sphere slice) work items
-    Culler<R, BLOCK> K;
+    Culler<R, BLOCK, COMMON> K;
+    K.cox = P.cam.origin.x; K.coy = P.cam.origin.y; K.coz = P.cam.origin.z;
     PairSink<R, BLOCK> sink;
     sink.n = e1;
     sink.pairs = W.pairs;
@@ -523,12 +563,14 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope s
         }
         const unsigned batch = item / (unsigned)parts, part = item - batch * (unsigned)parts;
         sink.idx0 = e0 + batch * (32 * R) + lane;     // ray r of this lane = entry idx0 + 32 r
+        sink.live = 0ull;
         RT_FOR_R {
             unsigned idx = sink.idx0 + 32 * r;
             if (idx < e1 && batch < n_batches) {
                 const float4* qc = cur ? W.queue[1] : W.queue[0];   // a select, not a dynamic index (keeps copies of W in registers)
                 float4 a = qc[3 * (size_t)idx], b = qc[3 * (size_t)idx + 1];
                 K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z);
+                sink.live |= 0xffffull << (16 * r);
                 if (part == 0) {
                     W.best_t[idx] = BEST_T_INIT;
                     W.best_key[idx] = BEST_KEY_MISS;
@@ -544,29 +586,46 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope s
     return ITEM_NONE;
 }
 
-// Queue length decides the shape of the cull work.  A long queue: batches of R rays per thread for the bulk,
-// then — so that the warps do not finish up to a whole 32*R batch apart — one-ray batches for the last stretch
-// (two per warp of the grid), claimed from the same counter.  A short queue: 1 ray per thread, and below two
-// batches per warp the sphere list is split across warps too (the pairs merge in wf_refine).
-// R = 1 instantiates only the short form.
+// The shape of the cull work.  The queue holds n_p common-origin entries (camera rays, culled in the cheaper
+// common-origin form against the tile s_cullc) and n_g general ones.  A long queue: batches of R rays per thread
+// for the bulk of both, then — so that the warps do not finish up to a whole 32*R batch apart — one-ray batches
+// for the last stretch (two per warp of the grid), all claimed from the same counter.  A short queue: 1 ray per
+// thread, and below two batches per warp the sphere list is split across warps too (the pairs merge in
+// wf_refine).  R = 1 instantiates only the short form.  s_cullc may be null when n_p is 0 (the tail).
 template <int R, int BLOCK>
-__device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int cur, unsigned n, float4* s_cull, uint32_t* s_list) {
+__device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int cur, unsigned n_g, unsigned n_p, float4* s_cull,
+                                             float4* s_cullc, uint32_t* s_list) {
     const RenderParams& P = W.base;
+    const unsigned n = n_g + n_p, p0 = (unsigned)W.capacity - n_p;
     if (sc_.bid == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
     const unsigned grid_warps = sc_.nblk * (BLOCK / 32);
     if (R > 1 && !P.preloaded) {
-        wf_cull_batches<R, BLOCK>(W, sc_, cur, 0u, n, 1, 0u, ITEM_NONE, s_cull, s_list);
+        // tiled scene: CTA-uniform static order; the tile loader builds the common-origin records itself
+        if (n_p) wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, 1, 0u, ITEM_NONE, s_cull, s_list);
+        if (n_g) wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, n_g, 1, 0u, ITEM_NONE, s_cull, s_list);
     } else if (R > 1 && n >= grid_warps * 64u) {
-        const unsigned tail = grid_warps * 64u;                                       // two one-ray batches per warp
-        const unsigned n_bulk = (n - tail) / (32u * R) * (32u * R), bulk_items = n_bulk / (32u * R);
-        const unsigned next = wf_cull_batches<R, BLOCK>(W, sc_, cur, 0u, n_bulk, 1, 0u, ITEM_NONE, s_cull, s_list);
-        wf_cull_batches<1, BLOCK>(W, sc_, cur, n_bulk, n, 1, bulk_items, next, s_cull, s_list);
+        const unsigned tail = grid_warps * 64u, per = 32u * R;                       // two one-ray batches per warp
+        const unsigned g_rest0 = min(n_g, tail), p_rest0 = min(n_p, tail - g_rest0);
+        const unsigned g_bulk = (n_g - g_rest0) / per * per, p_bulk = (n_p - p_rest0) / per * per;
+        unsigned items = 0;
+        unsigned next = wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + p_bulk, 1, items, ITEM_NONE, s_cullc, s_list);
+        items += p_bulk / per;
+        next = wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, g_bulk, 1, items, next, s_cull, s_list);
+        items += g_bulk / per;
+        next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0 + p_bulk, p0 + n_p, 1, items, next, s_cullc, s_list);
+        items += (n_p - p_bulk + 31u) / 32u;
+        wf_cull_batches<1, BLOCK, false>(W, sc_, cur, g_bulk, n_g, 1, items, next, s_cull, s_list);
     } else {
         const unsigned b1 = (n + 31) / 32;
         int parts = 1;
         if (P.preloaded)
             while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
-        wf_cull_batches<1, BLOCK>(W, sc_, cur, 0u, n, parts, 0u, ITEM_NONE, s_cull, s_list);
+        unsigned next = ITEM_NONE, items = 0;
+        if (n_p) {
+            next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, parts, 0u, ITEM_NONE, P.preloaded ? s_cullc : s_cull, s_list);
+            items = (n_p + 31u) / 32u * (unsigned)parts;
+        }
+        if (n_g) wf_cull_batches<1, BLOCK, false>(W, sc_, cur, 0u, n_g, parts, items, next, s_cull, s_list);
     }
 }
 
@@ -576,11 +635,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
-    const unsigned n = W.st->qcount[W.cur];
-    if (n == 0) return;
-    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
+    float4* s_cullc = reinterpret_cast<float4*>(s_list + Culler<R, BLOCK>::LIST_WORDS * BLOCK);   // common-origin records
+    const unsigned n_g = W.st->cnt[W.cur][0], n_p = W.st->cnt[W.cur][1];
+    if (n_g + n_p == 0) return;
+    if (P.preloaded) {
+        preload_scene(P.sc, s_cull, BLOCK);
+        if (n_p)
+            for (int i = threadIdx.x; i < P.sc.n_cull; i += BLOCK)
+                s_cullc[i] = Culler<R, BLOCK, true>::common_record(s_cull[i], P.cam.origin.x, P.cam.origin.y, P.cam.origin.z);
+    }
     __syncthreads();
-    wf_cull_body<R, BLOCK>(W, grid_scope(), W.cur, n, s_cull, s_list);
+    wf_cull_body<R, BLOCK>(W, grid_scope(), W.cur, n_g, n_p, s_cull, s_cullc, s_list);
 }
 
 // one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved).
@@ -594,12 +659,12 @@ __device__ __forceinline__ unsigned wf_cand_region(const WaveParams& W, unsigned
 
 __device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, int cur) {
     const RenderParams& P = W.base;
-    const unsigned n = W.st->qcount[cur];
     const unsigned npairs = min(W.st->npairs, W.pair_cap);
     const unsigned lane = threadIdx.x & 31u;
     if (sc_.bid == 0 && threadIdx.x == 0) {
         W.st->batch = 0;               // wf_cull is done with it
-        W.st->qcount[cur ^ 1] = 0;     // wf_shade appends to it next
+        W.st->cnt[cur ^ 1][0] = 0;     // wf_shade appends to both regions of the other queue next
+        W.st->cnt[cur ^ 1][1] = 0;
         atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);   // + the direct spheres' exact tests, counted by wf_shade
     }
     const unsigned total_warps = sc_.nblk * (blockDim.x >> 5);
@@ -613,7 +678,7 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, i
         uint2 pr = make_uint2(PAIR_NULL, 0u);
         double t = CUDART_INF;
         if (i < npairs) pr = W.pairs[i];
-        if (pr.x != PAIR_NULL && pr.x < n) {
+        if (pr.x != PAIR_NULL) {
             const float4* qc = cur ? W.queue[1] : W.queue[0];
             const float4 a = qc[3 * (size_t)pr.x], b = qc[3 * (size_t)pr.x + 1];
             const unsigned long long seen = __ldcg(&W.best_t[pr.x]);
@@ -674,7 +739,7 @@ __device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, floa
 // s_ctr: shared counters of the calling kernel (DC_COUNT slots, zeroed by the caller); returns samples generated
 __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_, int cur, unsigned* s_ctr) {
     const RenderParams& P = W.base;
-    const unsigned n = W.st->qcount[cur];
+    const unsigned n_g = W.st->cnt[cur][0], n_p = W.st->cnt[cur][1], n = n_g + n_p;
     const unsigned lane = threadIdx.x & 31u;
     const float4* qc = cur ? W.queue[1] : W.queue[0];
     float4* qn = cur ? W.queue[0] : W.queue[1];
@@ -688,9 +753,9 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_
     unsigned n_samples = 0, n_direct = 0;
     const unsigned stride = sc_.nblk * blockDim.x;
     for (unsigned idx0 = sc_.bid * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
-        const unsigned idx = idx0 + lane;
-        const bool have = idx < n;
-        bool cont = false;
+        const bool have = idx0 + lane < n;
+        const unsigned idx = wf_entry(idx0 + lane, n_g, n_p, (unsigned)W.capacity);
+        bool cont = false, fresh = false;
         float4 a, b, c;
         if (have) {
             a = qc[3 * (size_t)idx]; b = qc[3 * (size_t)idx + 1]; c = qc[3 * (size_t)idx + 2];
@@ -746,13 +811,26 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_
         unsigned long long w;
         if (!no_work && take_work(P, have && !cont, lane, w)) {
             make_path(P, w, a, b, c);
-            cont = true;
+            fresh = P.common_origin != 0;       // a camera ray from the common origin: the other region of the queue
+            cont = !fresh;
             n_samples++;
         }
-        unsigned slot = warp_claim(&W.st->qcount[cur ^ 1], cont, lane);
-        if (cont) {
-            float4* q = qn + 3 * (size_t)slot;
-            q[0] = a; q[1] = b; q[2] = c;
+        // one 64-bit atomic per warp claims the general slots (low word) and the common-origin slots (high word)
+        const unsigned mc = __ballot_sync(0xffffffffu, cont), mf = __ballot_sync(0xffffffffu, fresh);
+        if (mc | mf) {
+            unsigned long long base = 0ull;
+            if (lane == 0)
+                base = atomicAdd(reinterpret_cast<unsigned long long*>(&W.st->cnt[cur ^ 1][0]),
+                                 ((unsigned long long)__popc(mf) << 32) | (unsigned long long)__popc(mc));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (cont) {
+                float4* q = qn + 3 * (size_t)((unsigned)base + __popc(mc & lt));
+                q[0] = a; q[1] = b; q[2] = c;
+            } else if (fresh) {
+                float4* q = qn + 3 * (size_t)((unsigned)W.capacity - 1u - ((unsigned)(base >> 32) + __popc(mf & lt)));
+                q[0] = a; q[1] = b; q[2] = c;
+            }
         }
     }
     if (n_direct) atomicAdd(&s_ctr[DC_CANDIDATES], n_direct);
@@ -786,14 +864,15 @@ __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
     __shared__ unsigned s_ctr[DC_COUNT];
     __shared__ WaveState s_st;
     int cur = W.cur;
-    const unsigned n_all = W.st->qcount[cur];
+    const unsigned n_all = W.st->cnt[cur][0];        // the host launches the tail only when the common-origin region is empty
     const unsigned K = ((n_all + gridDim.x - 1) / gridDim.x + 31u) / 32u * 32u;      // slice capacity
     const unsigned first = blockIdx.x * K;
     if (first >= n_all) return;                                                       // CTA-uniform
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
-        s_st.qcount[cur] = min(K, n_all - first);
-        s_st.qcount[cur ^ 1] = 0;
+        s_st.cnt[cur][0] = min(K, n_all - first);
+        s_st.cnt[cur ^ 1][0] = 0;
+        s_st.cnt[0][1] = s_st.cnt[1][1] = 0;
         s_st.batch = 0;
         s_st.npairs = 0;
         s_st.exhausted = 1;
@@ -818,9 +897,9 @@ __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
     unsigned n_samples = 0;
     for (;;) {
         __syncthreads();
-        const unsigned n = *(volatile unsigned*)&s_st.qcount[cur];
+        const unsigned n = *(volatile unsigned*)&s_st.cnt[cur][0];
         if (n == 0) break;
-        wf_cull_body<1, BLOCK>(L, solo, cur, n, s_cull, s_list);
+        wf_cull_body<1, BLOCK>(L, solo, cur, n, 0u, s_cull, nullptr, s_list);
         __syncthreads();
         wf_refine_body(L, solo, cur);
         __syncthreads();
