@@ -115,6 +115,10 @@ int main() {
     run<2, 1, 128, 8>("expanded, FMNMX replaced by FFMA |.| (all-FMA key)", sph, out, 4);
     run<3, 1, 128, 8>("common-origin form (5 FFMA + funnel), shipped for camera rays", sph, out, 4);
     run<3, 1, 128, 8>("common-origin form (5 FFMA + funnel)", sph, out, 5);
+    run<2, 1, 128, 8>("expanded, all-FMA key", sph, out, 1);
+    run<2, 1, 128, 8>("expanded, all-FMA key", sph, out, 2);
+    run<2, 1, 128, 8>("expanded, all-FMA key", sph, out, 3);
+    run<3, 1, 128, 8>("common-origin form", sph, out, 2);
     run<1, 1, 128, 4>("expanded form + funnel + mask words", sph, out, 5);
     run<1, 1, 128, 16>("expanded form + funnel + mask words", sph, out, 5);
     run<1, 1, 128, 8>("expanded form + funnel + mask words", sph, out, 3);

@@ -368,6 +368,18 @@ def test_render_matches_oracle_random_scene(renderer, scene_c2, variant):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
+def test_render_matches_oracle_defocus_camera(renderer, scene_c2, variant):
+    """A lens with a real aperture (camera.clj:35-48 disk sample): camera rays no longer share an origin, so the
+    wavefront's common-origin cull form must stay off and fresh camera rays join the general queue region."""
+    flat, _, _, _ = scene_c2
+    sc = rt.scene.make_random_scene(160, 100, 11, True, random.Random(1))
+    cam_type, cam = rt.native.marshal_camera(sc["camera"])
+    cam = np.array(cam, np.float32)
+    cam[21] = 0.3          # aperture (lens radius 0.15), focus distance 10 already baked into lleft / horiz / vert
+    _render_parity(renderer, flat, cam_type, cam, 160, 100, 96, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
 def test_render_matches_oracle_material_stress(renderer, variant):
     """BASELINE config 4: metal/glass-heavy mix, depth 50 (long paths, absorbed rays, TIR)."""
     sc = rt.scene.make_material_stress_scene(160, 96, 11, random.Random(4))
