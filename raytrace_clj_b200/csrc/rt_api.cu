@@ -226,7 +226,9 @@ int env_int(const char* name, int dflt) {
 template <int BLOCK, int MINB>
 int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WaveParams)) {
     *kern = wf_cull<kR, BLOCK, MINB>;
-    *smem = 2 * (size_t)ctx->cull_cap * sizeof(float4) + Culler<kR, BLOCK>::LIST_BYTES;   // general + common-origin tiles
+    // a resident scene keeps two tiles (general + common-origin records); a tiled scene streams ONE tile and the loader
+    // writes whichever form the batch needs
+    *smem = (ctx->preloaded ? 2 : 1) * (size_t)ctx->cull_cap * sizeof(float4) + Culler<kR, BLOCK>::LIST_BYTES;
     RT_CUDA(ctx, cudaFuncSetAttribute(*kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, *kern, BLOCK, *smem));
     if (*bps < 1) return fail(ctx, RT_ERR_CUDA, "cull kernel does not fit on an SM");
@@ -771,8 +773,11 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     }
     cudaSetDevice(ctx->devs[0].dev);
     ctx->n_spheres = n;
+    // resident up to kTileCap records; beyond that the list is streamed through a smaller tile (RT_TILE_RECORDS,
+    // a multiple of 512) so that several CTAs still fit on an SM
+    static const int tile_records = std::max(CHUNK, std::min(kTileCap, env_int("RT_TILE_RECORDS", 1024) / CHUNK * CHUNK));
     ctx->preloaded = n_cull <= kTileCap ? 1 : 0;
-    ctx->cull_cap = ctx->preloaded ? std::max(n_cull, CULL_PAD) : kTileCap;
+    ctx->cull_cap = ctx->preloaded ? std::max(n_cull, CULL_PAD) : tile_records;
     ctx->win_lo = win_lo;
     ctx->win_hi = win_hi;
     ctx->has_scene = true;

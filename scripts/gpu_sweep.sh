@@ -1,12 +1,12 @@
 mkdir -p gpurun_out
-while read -r common wl steps; do
-  RT_COMMON_ORIGIN=$common timeout 600 python bench.py --workload $wl --steps $steps --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_s.json 2> gpurun_out/bench_s.err
-  python - $common $wl <<'PY'
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log
+run() { name=$1; shift
+  timeout 1200 python bench.py "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "$name exit $?"
+  python - gpurun_out/$name.json <<'PY'
 import json,sys
-d=json.load(open("gpurun_out/bench_s.json")); k=d["roofline"]["dominant_kernel"]
-print("common/workload",*sys.argv[1:], "ms %.3f frac %.4f"%(d["ms_per_step"], d["roofline"]["frac"]), "cull %.2f (%.3f)"%(k["ms_per_step"],k["frac"]), {a:round(b,2) for a,b in k["other_stages_ms"].items()}, flush=True)
+d=json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1]); k=d["roofline"]["dominant_kernel"]
+print(sys.argv[1], "ms %.2f"%d["ms_per_step"], "value %.1fM samples/s"%(d["value"]/1e6), "tests %.3fT/s"%(d["tests_per_sec"]/1e12), "frac %.4f"%d["roofline"]["frac"], "cull frac %.3f"%k["frac"], flush=True)
 PY
-done <<'CFG'
-1 c5-10k 1
-0 c5-10k 1
-CFG
+}
+run bench_c5_10k --workload c5-10k --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1
+run bench_c5_100k --workload c5-100k --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1
