@@ -60,6 +60,8 @@ struct DeviceBuffers {
         cudaEvent_t ev_poll[2] = {nullptr, nullptr};
         cudaEvent_t ev_done = nullptr;
         cudaStream_t stream = nullptr;      // lane 0 runs on the caller's stream, the others on their own
+        cudaStream_t stage_stream = nullptr;   // high priority: refine / tie-break / shade of this lane (RT_CULL_CLAIMS > 0)
+        cudaEvent_t ev_culled = nullptr, ev_shaded = nullptr;
         size_t entries = 0;
     } lanes[kMaxLanes];
     cudaEvent_t ev_lane_start = nullptr;
@@ -163,6 +165,9 @@ void free_wave(DeviceBuffers& d) {
             if (e) cudaEventDestroy(e);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
         if (L.stream) cudaStreamDestroy(L.stream);
+        if (L.stage_stream) cudaStreamDestroy(L.stage_stream);
+        if (L.ev_culled) cudaEventDestroy(L.ev_culled);
+        if (L.ev_shaded) cudaEventDestroy(L.ev_shaded);
         L = DeviceBuffers::WaveLane();
     }
     if (d.ev_lane_start) cudaEventDestroy(d.ev_lane_start);
@@ -177,6 +182,11 @@ int ensure_lane(rt_ctx* ctx, DeviceBuffers& d, int lane, size_t entries) {
         for (auto& e : L.ev_poll) RT_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         RT_CUDA(ctx, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
         if (lane > 0) RT_CUDA(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        int prio_least = 0, prio_greatest = 0;
+        RT_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        RT_CUDA(ctx, cudaStreamCreateWithPriority(&L.stage_stream, cudaStreamNonBlocking, prio_greatest));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&L.ev_culled, cudaEventDisableTiming));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&L.ev_shaded, cudaEventDisableTiming));
         if (!d.ev_lane_start) RT_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_lane_start, cudaEventDisableTiming));
     }
     if (L.entries >= entries) return RT_OK;
@@ -272,9 +282,17 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     const int tail_grid = d.sm_count * (env_int("RT_TAIL_CTAS_PER_SM", 0) > 0 ? tail_ctas : (n_lanes > 1 ? 1 : std::max(1, std::min(tail_bps, 2))));
     const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile;
 
-    static const int light_block = std::max(64, std::min(256, env_int("RT_LIGHT_BLOCK", 256) / 32 * 32));
+    static const int light_block = std::max(64, std::min(256, env_int("RT_LIGHT_BLOCK", 128) / 32 * 32));   // <= a cull CTA in every resource
     const int light_grid = d.sm_count * 8 * 256 / light_block;
     const int cull_grid = d.sm_count * bps;
+    // RT_CULL_CLAIMS = k > 0 (resident scenes): cull warps retire after k batches — the cull becomes many short CTAs, SM
+    // slots turn over every few tens of microseconds, and the OTHER lane's refine / tie-break / shade kernels, launched
+    // on a high-priority stream, take the freed slots at once instead of waiting for the whole persistent cull to end.
+    // 0 = persistent cull warps, one stream per lane.
+    static const int claims_env = std::max(0, env_int("RT_CULL_CLAIMS", 2));
+    const int claims = (ctx->profile || !ctx->preloaded || n_lanes < 2) ? 0 : claims_env;
+    const int cull_warps = cull_block / 32, resident_warps = cull_grid * cull_warps;
+    unsigned n_bound[kMaxLanes];   // upper bound of each lane's queue length (sizes the short-CTA grids)
     WaveParams W[kMaxLanes];
     cudaStream_t st[kMaxLanes];
     bool done[kMaxLanes];
@@ -296,6 +314,8 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
         W[l].capacity = (int)capacity;
         W[l].pair_cap = (unsigned)std::min<size_t>(capacity * kPairsPerEntry, 0xfffffff0u);
         W[l].cur = 0;
+        W[l].claims_per_warp = claims;
+        W[l].resident_warps = claims ? resident_warps : 0;
         st[l] = l == 0 ? stream : L.stream;
         done[l] = false;
     }
@@ -305,6 +325,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     for (int l = 0; l < n_lanes; ++l) {
         count0[l] = (unsigned)std::min<unsigned long long>(capacity, P.total_work - total0);
         total0 += count0[l];
+        n_bound[l] = count0[l];
     }
     wf_init<<<1, 1, 0, stream>>>(P.work_counter, total0);
     RT_CUDA(ctx, cudaEventRecord(d.ev_lane_start, stream));
@@ -328,14 +349,28 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 if (ctx->profile)
                     for (auto& x : e) { RT_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
                 if (ctx->profile) cudaEventRecord(e[0], st[l]);
-                cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
-                if (ctx->profile) cudaEventRecord(e[1], st[l]);
-                wf_refine<<<light_grid, light_block, 0, st[l]>>>(W[l]);
-                if (ctx->profile) cudaEventRecord(e[2], st[l]);
-                wf_tiebreak<<<light_grid, light_block, 0, st[l]>>>(W[l]);
-                if (ctx->profile) cudaEventRecord(e[3], st[l]);
-                wf_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
-                if (ctx->profile) cudaEventRecord(e[4], st[l]);
+                if (claims) {
+                    // every work item of the launch must find a warp: items <= n / (32 R) + 2 resident_warps + 8 (wf_cull_body)
+                    const unsigned items = n_bound[l] / (32u * kR) + 2u * (unsigned)resident_warps + 8u;
+                    const unsigned ctas = (items + (unsigned)(cull_warps * claims) - 1u) / (unsigned)(cull_warps * claims);
+                    cull<<<ctas, cull_block, smem, st[l]>>>(W[l]);
+                    RT_CUDA(ctx, cudaEventRecord(L.ev_culled, st[l]));
+                    RT_CUDA(ctx, cudaStreamWaitEvent(L.stage_stream, L.ev_culled, 0));
+                    wf_refine<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    wf_tiebreak<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    wf_shade<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    RT_CUDA(ctx, cudaEventRecord(L.ev_shaded, L.stage_stream));
+                    RT_CUDA(ctx, cudaStreamWaitEvent(st[l], L.ev_shaded, 0));
+                } else {
+                    cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
+                    if (ctx->profile) cudaEventRecord(e[1], st[l]);
+                    wf_refine<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                    if (ctx->profile) cudaEventRecord(e[2], st[l]);
+                    wf_tiebreak<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                    if (ctx->profile) cudaEventRecord(e[3], st[l]);
+                    wf_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                    if (ctx->profile) cudaEventRecord(e[4], st[l]);
+                }
                 W[l].cur ^= 1;
                 ctx->n_launches += 4;
             }
@@ -349,6 +384,8 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 DeviceBuffers::WaveLane& L = d.lanes[l];
                 RT_CUDA(ctx, cudaEventSynchronize(L.ev_poll[(chunk - 1) & 1]));
                 const WaveState& snap = L.h_state[(chunk - 1) & 1];
+                if (snap.exhausted)   // from here on a lane's population only shrinks
+                    n_bound[l] = std::min(n_bound[l], snap.cnt[W[l].cur][0] + snap.cnt[W[l].cur][1]);
                 if (snap.cnt[W[l].cur][0] == 0 && snap.cnt[W[l].cur][1] == 0) {   // kWaveChunk is even: same parity
                     done[l] = true;
                 } else if (tail_ok && snap.exhausted && snap.cnt[W[l].cur][1] == 0 && snap.cnt[W[l].cur][0] <= tail_entries) {

@@ -387,6 +387,10 @@ struct WaveParams {
     int capacity;                  // multiple of 32
     unsigned pair_cap;
     int cur;                       // queue read by this iteration
+    int claims_per_warp;           // wf_cull: 0 = persistent warps (claim batches until none is left); k > 0 = a warp retires
+                                   // after k batches (many short CTAs: the SM's slots turn over, so the other lane's
+                                   // high-priority stage kernels get on the SM while this cull is still running)
+    int resident_warps;            // wf_cull warps resident on the device at once (sizes the balancing tail); 0 = the grid's
 };
 
 constexpr unsigned long long BEST_T_INIT = 0x7ff0000000000000ull;   // +inf
@@ -523,6 +527,7 @@ struct PairSink {
 // item number this warp has already claimed (or ~0u); returns the first claimed number beyond the range, so a
 // following range can use it.
 constexpr unsigned ITEM_NONE = 0xffffffffu;
+constexpr unsigned ITEM_STOP = 0xfffffffeu;   // this warp has used up its claims (WaveParams::claims_per_warp)
 // The CTAs that cooperate on one queue: the whole grid (bid = blockIdx.x of nblk = gridDim.x), or a single CTA
 // working alone on its own slice of the queue (bid 0 of 1; wf_tail).
 struct Scope {
@@ -531,7 +536,8 @@ struct Scope {
 __device__ __forceinline__ Scope grid_scope() { return Scope{blockIdx.x, gridDim.x}; }
 template <int R, int BLOCK, bool COMMON>
 __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope sc_, int cur, unsigned e0, unsigned e1, int parts,
-                                                    unsigned item0, unsigned claimed, float4* s_cull, uint32_t* s_list) {
+                                                    unsigned item0, unsigned claimed, int& budget, float4* s_cull, uint32_t* s_list) {
+    if (claimed == ITEM_STOP) return ITEM_STOP;
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
     const unsigned n_batches = (e1 - e0 + 32 * R - 1) / (32 * R);
@@ -582,6 +588,7 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope s
         if (parts > 1) K.run_slice(P.sc, s_cull, s_list, sink, (int)part, parts);
         else           K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, sink);
         item += sc_.nblk * warps;
+        if (P.preloaded && budget > 0 && --budget == 0) return ITEM_STOP;
     }
     return ITEM_NONE;
 }
@@ -598,23 +605,24 @@ __device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int
     const RenderParams& P = W.base;
     const unsigned n = n_g + n_p, p0 = (unsigned)W.capacity - n_p;
     if (sc_.bid == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
-    const unsigned grid_warps = sc_.nblk * (BLOCK / 32);
+    const unsigned grid_warps = W.resident_warps > 0 ? (unsigned)W.resident_warps : sc_.nblk * (BLOCK / 32);
+    int budget = W.claims_per_warp;
     if (R > 1 && !P.preloaded) {
         // tiled scene: CTA-uniform static order; the tile loader builds the common-origin records itself
-        if (n_p) wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, 1, 0u, ITEM_NONE, s_cull, s_list);
-        if (n_g) wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, n_g, 1, 0u, ITEM_NONE, s_cull, s_list);
+        if (n_p) wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, 1, 0u, ITEM_NONE, budget, s_cull, s_list);
+        if (n_g) wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, n_g, 1, 0u, ITEM_NONE, budget, s_cull, s_list);
     } else if (R > 1 && n >= grid_warps * 64u) {
         const unsigned tail = grid_warps * 64u, per = 32u * R;                       // two one-ray batches per warp
         const unsigned g_rest0 = min(n_g, tail), p_rest0 = min(n_p, tail - g_rest0);
         const unsigned g_bulk = (n_g - g_rest0) / per * per, p_bulk = (n_p - p_rest0) / per * per;
         unsigned items = 0;
-        unsigned next = wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + p_bulk, 1, items, ITEM_NONE, s_cullc, s_list);
+        unsigned next = wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + p_bulk, 1, items, ITEM_NONE, budget, s_cullc, s_list);
         items += p_bulk / per;
-        next = wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, g_bulk, 1, items, next, s_cull, s_list);
+        next = wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, g_bulk, 1, items, next, budget, s_cull, s_list);
         items += g_bulk / per;
-        next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0 + p_bulk, p0 + n_p, 1, items, next, s_cullc, s_list);
+        next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0 + p_bulk, p0 + n_p, 1, items, next, budget, s_cullc, s_list);
         items += (n_p - p_bulk + 31u) / 32u;
-        wf_cull_batches<1, BLOCK, false>(W, sc_, cur, g_bulk, n_g, 1, items, next, s_cull, s_list);
+        wf_cull_batches<1, BLOCK, false>(W, sc_, cur, g_bulk, n_g, 1, items, next, budget, s_cull, s_list);
     } else {
         const unsigned b1 = (n + 31) / 32;
         int parts = 1;
@@ -622,10 +630,10 @@ __device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int
             while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
         unsigned next = ITEM_NONE, items = 0;
         if (n_p) {
-            next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, parts, 0u, ITEM_NONE, P.preloaded ? s_cullc : s_cull, s_list);
+            next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, parts, 0u, ITEM_NONE, budget, P.preloaded ? s_cullc : s_cull, s_list);
             items = (n_p + 31u) / 32u * (unsigned)parts;
         }
-        if (n_g) wf_cull_batches<1, BLOCK, false>(W, sc_, cur, 0u, n_g, parts, items, next, s_cull, s_list);
+        if (n_g) wf_cull_batches<1, BLOCK, false>(W, sc_, cur, 0u, n_g, parts, items, next, budget, s_cull, s_list);
     }
 }
 
@@ -892,6 +900,8 @@ __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
     L.cand_count = W.cand_count + blockIdx.x * warps;
     L.st = &s_st;
     L.capacity = (int)K;
+    L.claims_per_warp = 0;
+    L.resident_warps = 0;
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     const Scope solo{0u, 1u};
     unsigned n_samples = 0;
