@@ -769,6 +769,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     size_t o_c0r = take((size_t)n * 16), o_c1 = take((size_t)n * 16), o_t0t1 = take((size_t)n * 8);
     size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n * 4), o_mat = take((size_t)n * 4);
     size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);
+    size_t o_srec = take((size_t)n * 16), o_scol = take((size_t)n * 16);
     size_t o_ttype = take((size_t)std::max(nt, 1) * 4), o_tparam = take((size_t)std::max(nt, 1) * 48), o_tchild = take((size_t)std::max(nt, 1) * 8);
     std::vector<unsigned char> blob(off, 0);
     build_cull_records(ctx, win_lo, win_hi, (float*)(blob.data() + o_cull_a));
@@ -780,6 +781,21 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     int* cull_of = (int*)(blob.data() + o_cull_of);
     for (int k = 0; k < n; ++k) { orig[k] = perm[(size_t)k]; cull_of[perm[(size_t)k]] = k; }
     memcpy(blob.data() + o_mat, h_mat.data(), (size_t)n * 4);
+    {   // per-sphere shading records: material and (constant) texture resolved once, here
+        int* srec = (int*)(blob.data() + o_srec);
+        float* scol = (float*)(blob.data() + o_scol);
+        for (int k = 0; k < n; ++k) {
+            const int m = h_mat[(size_t)k], tex = s->mat_tex[m];
+            const bool has_tex = s->mat_type[m] != RT_MAT_DIELECTRIC && tex >= 0 && tex < nt;
+            const int tex_type = has_tex ? s->tex_type[tex] : -1;
+            srec[4 * k + 0] = s->mat_type[m];
+            srec[4 * k + 1] = tex;
+            srec[4 * k + 2] = tex_type;
+            srec[4 * k + 3] = (int)ctx->h_flags[(size_t)k];
+            scol[4 * k + 0] = s->mat_param[m];
+            for (int c = 0; c < 3; ++c) scol[4 * k + 1 + c] = tex_type == RT_TEX_CONSTANT ? s->tex_params[12 * tex + c] : 0.f;
+        }
+    }
     memcpy(blob.data() + o_mtype, s->mat_type, (size_t)nm_ * 4);
     memcpy(blob.data() + o_mparam, s->mat_param, (size_t)nm_ * 4);
     memcpy(blob.data() + o_mtex, s->mat_tex, (size_t)nm_ * 4);
@@ -805,6 +821,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         sc.ex_c0r = (const float4*)(b + o_c0r); sc.ex_c1 = (const float4*)(b + o_c1); sc.ex_t0t1 = (const float2*)(b + o_t0t1);
         sc.orig_id = (const int*)(b + o_orig); sc.cull_of_orig = (const int*)(b + o_cull_of);
         sc.flags = (const unsigned*)(b + o_flags); sc.mat_id = (const int*)(b + o_mat);
+        sc.shade_rec = (const int4*)(b + o_srec); sc.shade_col = (const float4*)(b + o_scol);
         sc.mat_type = (const int*)(b + o_mtype); sc.mat_param = (const float*)(b + o_mparam); sc.mat_tex = (const int*)(b + o_mtex);
         sc.tex_type = (const int*)(b + o_ttype); sc.tex_params = (const float*)(b + o_tparam); sc.tex_child = (const int*)(b + o_tchild);
     }

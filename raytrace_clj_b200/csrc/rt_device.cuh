@@ -55,6 +55,9 @@ struct DevScene {
     const int* cull_of_orig;  // [n] caller's sphere index -> cull order
     const unsigned* flags;    // [n]
     const int* mat_id;        // [n]
+    const int4* shade_rec;    // [n] (material type, texture id, texture type, sphere flags): the material / texture tables
+                              //     resolved per sphere at upload, so a hit costs ONE dependent load level instead of four
+    const float4* shade_col;  // [n] (material parameter fuzz | ri, then the colour of a CONSTANT texture)
     const int* mat_type;      // [m]
     const float* mat_param;   // [m]
     const int* mat_tex;       // [m]
@@ -202,10 +205,18 @@ __device__ __noinline__ double refine_candidate(const float4* __restrict__ ex_c0
     if (disc >= 0.0) {
         double sq = __dsqrt_rn(disc);
         double two_a = dmul(2.0, a);
-        double t = __ddiv_rn(dsub(-b, sq), two_a);
-        if (t > tmin && t < tmax) return t;
-        t = __ddiv_rn(dadd(-b, sq), two_a);
-        if (t > tmin && t < tmax) return t;
+        // tmin >= 0 and 2a >= 0: a root whose numerator is <= 0 cannot pass t > tmin, so its division (the costliest
+        // part of the test) is skipped — the accepted t is still computed exactly as the reference does
+        double num = dsub(-b, sq);
+        if (num > 0.0) {
+            double t = __ddiv_rn(num, two_a);
+            if (t > tmin && t < tmax) return t;
+        }
+        num = dadd(-b, sq);
+        if (num > 0.0) {
+            double t = __ddiv_rn(num, two_a);
+            if (t > tmin && t < tmax) return t;
+        }
     }
     return CUDART_INF;
 }
@@ -263,7 +274,9 @@ struct ScatterRng {
 __device__ __forceinline__ bool shade_hit(const DevScene& sc, int k, float t, float3& o, float3& d, float time,
                                           bool allow_scatter, const ScatterRng& rng, float3& atten, float3& emitted,
                                           int& reason) {
-    unsigned flags = __ldg(&sc.flags[k]);
+    const int4 rec = __ldg(&sc.shade_rec[k]);
+    const float4 col = __ldg(&sc.shade_col[k]);
+    const unsigned flags = (unsigned)rec.w;
     float4 c0r = __ldg(&sc.ex_c0r[k]);
     float3 center = f3(c0r.x, c0r.y, c0r.z);
     if (flags & SPH_MOVING) {
@@ -282,11 +295,11 @@ __device__ __forceinline__ bool shade_hit(const DevScene& sc, int k, float t, fl
         u = 1.0f - (phi + PI) / (2.0f * PI);
         v = (theta + PI / 2.0f) / PI;
     }
-    int m = __ldg(&sc.mat_id[k]);
-    int type = __ldg(&sc.mat_type[m]);
-    float param = __ldg(&sc.mat_param[m]);
-    int tex = __ldg(&sc.mat_tex[m]);
-    emitted = (type == MAT_DIFFUSE_LIGHT) ? tex_sample(sc, tex, u, v, p) : f3(0.f, 0.f, 0.f);
+    const int type = rec.x, tex = rec.y;
+    const bool const_tex = rec.z == TEX_CONSTANT;
+    const float param = col.x;
+    const float3 const_col = f3(col.y, col.z, col.w);
+    emitted = (type == MAT_DIFFUSE_LIGHT) ? (const_tex ? const_col : tex_sample(sc, tex, u, v, p)) : f3(0.f, 0.f, 0.f);
     atten = f3(1.f, 1.f, 1.f);
     if (!allow_scatter) {                      // core.clj:26 (pos? depth) fails: scatter is not evaluated
         reason = TERM_DEPTH;
@@ -296,7 +309,7 @@ __device__ __forceinline__ bool shade_hit(const DevScene& sc, int k, float t, fl
         float3 s = rng.unit_sphere();
         d = n + s;
         o = p;
-        atten = tex_sample(sc, tex, u, v, p);
+        atten = const_tex ? const_col : tex_sample(sc, tex, u, v, p);
         return true;
     }
     if (type == MAT_METAL) {                   // shader.clj:46-59
@@ -306,7 +319,7 @@ __device__ __forceinline__ bool shade_hit(const DevScene& sc, int k, float t, fl
         if (dot3(nd, n) > 0.f) {
             d = nd;
             o = p;
-            atten = tex_sample(sc, tex, u, v, p);
+            atten = const_tex ? const_col : tex_sample(sc, tex, u, v, p);
             return true;
         }
         reason = TERM_ABSORB;

@@ -680,12 +680,16 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, i
     const size_t region = (size_t)warp_id * wf_cand_region(W, total_warps);
     unsigned cnt = 0;
     const unsigned stride = sc_.nblk * blockDim.x;
-    for (unsigned i0 = sc_.bid * blockDim.x + threadIdx.x - lane; i0 < npairs; i0 += stride) {   // warp-uniform
-        const unsigned i = i0 + lane;
+    // the pair of the NEXT trip is loaded before this trip's pair is refined: its latency hides behind the gathers
+    // and the FP64 test of the current one (the loop is a chain of dependent loads: pair -> ray -> sphere)
+    const unsigned i_first = sc_.bid * blockDim.x + threadIdx.x;
+    uint2 pr_next = i_first < npairs ? W.pairs[i_first] : make_uint2(PAIR_NULL, 0u);
+    for (unsigned i0 = i_first - lane; i0 < npairs; i0 += stride) {   // warp-uniform
+        const uint2 pr = pr_next;
+        const unsigned i_next = i0 + lane + stride;
+        pr_next = i_next < npairs ? W.pairs[i_next] : make_uint2(PAIR_NULL, 0u);
         bool cand = false;
-        uint2 pr = make_uint2(PAIR_NULL, 0u);
         double t = CUDART_INF;
-        if (i < npairs) pr = W.pairs[i];
         if (pr.x != PAIR_NULL) {
             const float4* qc = cur ? W.queue[1] : W.queue[0];
             const float4 a = qc[3 * (size_t)pr.x], b = qc[3 * (size_t)pr.x + 1];
