@@ -355,10 +355,11 @@ def main():
                 "peak_ffma_tflops": fp32_peak[0], "peak_ffma2_tflops": fp32_peak[1],
                 "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
                 "flop_per_test": FLOP_PER_TEST,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one full-queue wf_cull launch (2.1 M rays), from the
-                # committed `ncu --set full` capture (profiles/r01_ncu_wf_cull_summary.txt); C2 only
-                "traffic": 127.4e6 if args.workload == "c2" and args.variant == 1 else None,
-                "traffic_note": "bytes per wf_cull launch (ncu); the kernel is FP32-issue bound, not HBM bound: 0.3 TB/s",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the largest wf_cull launch of a C2 frame (a lane's 4.8 M
+                # camera rays), from the committed `ncu --set full` capture (profiles/r01_ncu_wf_cull_common_summary.txt)
+                "traffic": 343.5e6 if args.workload == "c2" and args.variant == 1 else None,
+                "traffic_note": "bytes per wf_cull launch (ncu): 72 B per ray (ray record in, pairs and closest-hit words out); "
+                                "the kernel is FP32-issue bound, not HBM bound (0.6 TB/s)",
                 "note": "non-tensor FP32 pipe; HBM is not the bound (scene in shared memory). `achieved` divides the "
                         "17-flop tests by the time of the WHOLE render step (cull + refine + tie-break + shade kernels)",
                 "dominant_kernel": None if not stage else {
