@@ -250,19 +250,15 @@ int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WavePar
 // (they share only the work counter and the frame, both atomics): one lane's FP32-issue-bound cull kernel
 // co-runs with the other lane's latency-bound refine / shade kernels.  The host enqueues kWaveChunk
 // iterations per lane ahead of the GPU and polls each lane's queue count; when the work counter is
-// exhausted and a lane's queue is short, one cooperative wf_tail launch finishes that lane.
+// exhausted and a lane's queue is short, one wf_tail launch finishes that lane (every CTA on its own slice).
 int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned long long, cudaStream_t stream) {
-    // CTA shape of the cull kernel; RT_CULL_SHAPE = "256x2" | "256x3" | "128x4" | "128x5" | "128x6"
+    // CTA shape of the cull kernel (threads x register-cap CTAs/SM); RT_CULL_SHAPE = "128x5" (default) | "128x6" | "256x2"
     static const std::string shape = getenv("RT_CULL_SHAPE") ? getenv("RT_CULL_SHAPE") : "128x5";
     void (*cull)(const WaveParams) = nullptr;
     size_t smem = 0;
     int bps = 0, cull_block = 256, rc;
     if (shape == "256x2") rc = cull_config<256, 2>(ctx, &smem, &bps, &cull);
-    else if (shape == "256x3") rc = cull_config<256, 3>(ctx, &smem, &bps, &cull);
-    else if (shape == "128x4") { rc = cull_config<128, 4>(ctx, &smem, &bps, &cull); cull_block = 128; }
     else if (shape == "128x6") { rc = cull_config<128, 6>(ctx, &smem, &bps, &cull); cull_block = 128; }
-    else if (shape == "128x7") { rc = cull_config<128, 7>(ctx, &smem, &bps, &cull); cull_block = 128; }
-    else if (shape == "128x8") { rc = cull_config<128, 8>(ctx, &smem, &bps, &cull); cull_block = 128; }
     else { rc = cull_config<128, 5>(ctx, &smem, &bps, &cull); cull_block = 128; }
     if (rc) return rc;
     static const int cull_ctas_env = env_int("RT_CULL_CTAS_PER_SM", 4);   // one fewer than the occupancy limit leaves
@@ -272,7 +268,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     const int n_lanes = (ctx->profile || P.total_work < 65536) ? 1 : lanes_env;   // stage timing wants one lane
     const size_t capacity = align_up((size_t)std::min<unsigned long long>(cap_env / n_lanes, (P.total_work + n_lanes - 1) / n_lanes), 32);
 
-    // cooperative tail kernel: every CTA must be resident, also next to the other lane's tail
+    // tail kernel: one CTA per SM per lane (two lanes' tails run side by side)
     static const unsigned tail_entries = (unsigned)std::max(0, env_int("RT_TAIL_ENTRIES", (int)kTailEntries));
     const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<1, 256>::LIST_BYTES;
     int tail_bps = 0;
@@ -389,7 +385,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 if (snap.cnt[W[l].cur][0] == 0 && snap.cnt[W[l].cur][1] == 0) {   // kWaveChunk is even: same parity
                     done[l] = true;
                 } else if (tail_ok && snap.exhausted && snap.cnt[W[l].cur][1] == 0 && snap.cnt[W[l].cur][0] <= tail_entries) {
-                    // no new work can appear and the queue is short: one cooperative launch finishes this lane
+                    // no new work can appear and the queue is short: one launch finishes this lane
                     wf_tail<256><<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
                     RT_CUDA(ctx, cudaGetLastError());
                     ctx->n_launches += 1;

@@ -1,22 +1,20 @@
 // rt_kernels.cuh — sm_100a kernels of libraytrace_b200.so.
 //
-//   Culler<R,BLOCK>    the hot loop: brute-force FP32 cull of R rays per thread against the sphere
-//                      list staged in shared memory (Hitlist.hit?, hitable.clj:15-26), survivors
-//                      recorded branch-free in per-thread shared-memory lists
+//   Culler<R,BLOCK,COMMON>  the hot loop: brute-force FP32 cull of R rays per thread against the sphere list staged in
+//                      shared memory (Hitlist.hit?, hitable.clj:15-26); the survivors' sign bits go, branch-free, to
+//                      per-thread mask words in shared memory.  COMMON: the cheaper form for rays that share an origin.
+//   SurvivorIter       walks the mask words that hold a survivor
 //   RefineSink         survivors refined in FP64 by the owning thread (trace kernel, megakernel)
-//   PairSink           survivors emitted as (ray, sphere) pairs for a pooled, CTA-wide FP64 refine
-//                      (wavefront kernel)
-//   wf_generate / wf_cull / wf_refine / wf_tiebreak / wf_shade
-//                      wavefront path tracer: one global path queue, one kernel per stage
-//                      (pixel + color, core.clj:17-57); wf_cull is the persistent hot-loop kernel
+//   PairSink           survivors emitted as (ray, sphere) pairs for the pooled FP64 refine (wavefront kernels)
+//   wf_generate / wf_cull / wf_refine / wf_tiebreak / wf_shade / wf_tail
+//                      wavefront path tracer (pixel + color, core.clj:17-57): one kernel per stage over a queue of
+//                      paths; wf_cull is the hot-loop kernel, wf_tail finishes the last short iterations CTA by CTA
 //   mega_kernel        persistent megakernel with per-lane path regeneration, kept for comparison
 //   trace_kernel       closest hit of caller-given rays (rt_trace_primary)
-//   shade_kernel / genrays_kernel   diagnostics for the parity tests
+//   cull_check_kernel / shade_kernel / genrays_kernel   diagnostics for the parity tests
 //   resolve_kernel     core.clj:52-57 + the y flip of core.clj:105 (+ NVLink peer reduce)
 //   ffma_peak_kernel   FP32 roofline denominator measured on the box
 #pragma once
-
-#include <cooperative_groups.h>
 
 #include "rt_device.cuh"
 
