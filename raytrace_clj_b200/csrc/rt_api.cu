@@ -65,6 +65,10 @@ struct DeviceBuffers {
         size_t entries = 0;
     } lanes[kMaxLanes];
     cudaEvent_t ev_lane_start = nullptr;
+    // timeline trace (RT_TRACE): one record per wavefront kernel launch of the last render
+    TraceRec* d_trace = nullptr;
+    struct TraceMeta { const char* kernel; int lane, iter; };
+    std::vector<TraceMeta> trace_meta;
     // scratch for diagnostics
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -172,6 +176,8 @@ void free_wave(DeviceBuffers& d) {
     }
     if (d.ev_lane_start) cudaEventDestroy(d.ev_lane_start);
     d.ev_lane_start = nullptr;
+    if (d.d_trace) cudaFree(d.d_trace);
+    d.d_trace = nullptr;
 }
 
 int ensure_lane(rt_ctx* ctx, DeviceBuffers& d, int lane, size_t entries) {
@@ -315,6 +321,22 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
         st[l] = l == 0 ? stream : L.stream;
         done[l] = false;
     }
+    // RT_TRACE=<file>: device-side timeline of this render's kernels (dumped by the next rt_get_counters)
+    static const char* trace_path = getenv("RT_TRACE");
+    constexpr int kTraceMax = 8192;
+    const bool tracing = trace_path && *trace_path;
+    if (tracing) {
+        if (!d.d_trace) RT_CUDA(ctx, cudaMalloc(&d.d_trace, kTraceMax * sizeof(TraceRec)));
+        static const std::vector<TraceRec> init((size_t)kTraceMax, TraceRec{~0ull, 0ull});
+        RT_CUDA(ctx, cudaMemcpyAsync(d.d_trace, init.data(), init.size() * sizeof(TraceRec), cudaMemcpyHostToDevice, stream));
+        d.trace_meta.clear();
+    }
+    auto trace_slot = [&](const char* kernel, int lane, int iter) -> TraceRec* {
+        if (!tracing || (int)d.trace_meta.size() >= kTraceMax) return nullptr;
+        d.trace_meta.push_back({kernel, lane, iter});
+        return d.d_trace + (d.trace_meta.size() - 1);
+    };
+    int iter_no[kMaxLanes] = {};
     // the shared work counter starts past every lane's first fill
     unsigned count0[kMaxLanes];
     unsigned long long total0 = 0;
@@ -327,6 +349,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     RT_CUDA(ctx, cudaEventRecord(d.ev_lane_start, stream));
     for (int l = 0; l < n_lanes; ++l) {
         if (l > 0) RT_CUDA(ctx, cudaStreamWaitEvent(st[l], d.ev_lane_start, 0));
+        W[l].trace = trace_slot("generate", l, 0);
         wf_generate<<<std::max(1, std::min(light_grid, (int)((count0[l] + 255) / 256))), 256, 0, st[l]>>>(W[l], first, count0[l]);
         first += count0[l];
         ctx->n_launches += 1;
@@ -349,25 +372,34 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     // every work item of the launch must find a warp: items <= n / (32 R) + 2 resident_warps + 8 (wf_cull_body)
                     const unsigned items = n_bound[l] / (32u * kR) + 2u * (unsigned)resident_warps + 8u;
                     const unsigned ctas = (items + (unsigned)(cull_warps * claims) - 1u) / (unsigned)(cull_warps * claims);
+                    W[l].trace = trace_slot("cull", l, iter_no[l]);
                     cull<<<ctas, cull_block, smem, st[l]>>>(W[l]);
                     RT_CUDA(ctx, cudaEventRecord(L.ev_culled, st[l]));
                     RT_CUDA(ctx, cudaStreamWaitEvent(L.stage_stream, L.ev_culled, 0));
+                    W[l].trace = trace_slot("refine", l, iter_no[l]);
                     wf_refine<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    W[l].trace = trace_slot("tiebreak", l, iter_no[l]);
                     wf_tiebreak<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    W[l].trace = trace_slot("shade", l, iter_no[l]);
                     wf_shade<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
                     RT_CUDA(ctx, cudaEventRecord(L.ev_shaded, L.stage_stream));
                     RT_CUDA(ctx, cudaStreamWaitEvent(st[l], L.ev_shaded, 0));
                 } else {
+                    W[l].trace = trace_slot("cull", l, iter_no[l]);
                     cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[1], st[l]);
+                    W[l].trace = trace_slot("refine", l, iter_no[l]);
                     wf_refine<<<light_grid, light_block, 0, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[2], st[l]);
+                    W[l].trace = trace_slot("tiebreak", l, iter_no[l]);
                     wf_tiebreak<<<light_grid, light_block, 0, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[3], st[l]);
+                    W[l].trace = trace_slot("shade", l, iter_no[l]);
                     wf_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[4], st[l]);
                 }
                 W[l].cur ^= 1;
+                ++iter_no[l];
                 ctx->n_launches += 4;
             }
             RT_CUDA(ctx, cudaGetLastError());
@@ -386,6 +418,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     done[l] = true;
                 } else if (tail_ok && snap.exhausted && snap.cnt[W[l].cur][1] == 0 && snap.cnt[W[l].cur][0] <= tail_entries) {
                     // no new work can appear and the queue is short: one launch finishes this lane
+                    W[l].trace = trace_slot("tail", l, iter_no[l]);
                     wf_tail<256><<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
                     RT_CUDA(ctx, cudaGetLastError());
                     ctx->n_launches += 1;
@@ -1170,6 +1203,22 @@ int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]) {
         RT_CUDA(ctx, cudaDeviceSynchronize());
         RT_CUDA(ctx, cudaMemcpy(dc, d.d_counters, sizeof(dc), cudaMemcpyDeviceToHost));
         for (int i = 0; i < DC_COUNT; ++i) total[i] += dc[i];
+        if (!d.trace_meta.empty() && d.d_trace && getenv("RT_TRACE")) {   // timeline of the last traced render
+            std::vector<TraceRec> rec(d.trace_meta.size());
+            RT_CUDA(ctx, cudaMemcpy(rec.data(), d.d_trace, rec.size() * sizeof(TraceRec), cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull;
+            for (auto& r : rec) if (r.t_end) t0 = std::min(t0, r.t_start);
+            if (FILE* f = fopen(getenv("RT_TRACE"), "a")) {   // appended: one block per traced render that was followed by rt_get_counters
+                fprintf(f, "# device %d, %zu launches: kernel lane iteration start_us end_us duration_us (%%globaltimer, relative to the first kernel)\n", d.dev, rec.size());
+                for (size_t i = 0; i < rec.size(); ++i) {
+                    if (!rec[i].t_end) continue;   // the launch found an empty queue
+                    fprintf(f, "%-9s %d %3d %10.1f %10.1f %9.1f\n", d.trace_meta[i].kernel, d.trace_meta[i].lane, d.trace_meta[i].iter,
+                            (rec[i].t_start - t0) * 1e-3, (rec[i].t_end - t0) * 1e-3, (rec[i].t_end - rec[i].t_start) * 1e-3);
+                }
+                fclose(f);
+            }
+            d.trace_meta.clear();
+        }
         if (d.timed) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, d.ev0, d.ev1) == cudaSuccess) d.last_ms = ms;

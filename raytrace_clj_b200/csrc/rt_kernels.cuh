@@ -372,6 +372,27 @@ __device__ __forceinline__ unsigned wf_entry(unsigned i, unsigned n_g, unsigned 
     return i < n_g ? i : capacity - n_p + (i - n_g);
 }
 
+// Timeline tracing (RT_TRACE=<file>): every wavefront kernel launch owns one record; thread 0 of every CTA folds its
+// entry / exit %globaltimer into it.  Shows how the two lanes' kernels really interleave on the device (ncu serialises
+// them; there is no nsys in this environment).
+struct TraceRec {
+    unsigned long long t_start, t_end;   // ns, %globaltimer; min over CTAs / max over CTAs
+};
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+struct TraceScope {
+    TraceRec* rec;
+    __device__ __forceinline__ explicit TraceScope(TraceRec* r) : rec(r) {
+        if (rec && threadIdx.x == 0) atomicMin(&rec->t_start, global_timer_ns());
+    }
+    __device__ __forceinline__ ~TraceScope() {
+        if (rec && threadIdx.x == 0) atomicMax(&rec->t_end, global_timer_ns());
+    }
+};
+
 struct WaveParams {
     RenderParams base;
     float4* queue[2];              // 3 * capacity float4 each
@@ -389,6 +410,7 @@ struct WaveParams {
                                    // after k batches (many short CTAs: the SM's slots turn over, so the other lane's
                                    // high-priority stage kernels get on the SM while this cull is still running)
     int resident_warps;            // wf_cull warps resident on the device at once (sizes the balancing tail); 0 = the grid's
+    TraceRec* trace;               // this launch's timeline record, or null
 };
 
 constexpr unsigned long long BEST_T_INIT = 0x7ff0000000000000ull;   // +inf
@@ -449,6 +471,7 @@ __device__ __forceinline__ void make_path(const RenderParams& P, unsigned long l
 __global__ void wf_init(unsigned long long* work_counter, unsigned long long value) { *work_counter = value; }
 
 __global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned long long first, unsigned count) {
+    TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     const unsigned e0 = P.common_origin ? (unsigned)W.capacity - count : 0u;   // camera rays: the common-origin region
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
@@ -637,6 +660,7 @@ __device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int
 
 template <int R, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
+    TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
@@ -710,7 +734,10 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, i
     }
     if (lane == 0) W.cand_count[warp_id] = cnt;
 }
-__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) { wf_refine_body(W, grid_scope(), W.cur); }
+__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) {
+    TraceScope trace(W.trace);
+    wf_refine_body(W, grid_scope(), W.cur);
+}
 
 // exact ties go to the lower caller index, the Hitlist rule (hitable.clj:17-26): candidates that own the final
 // minimum t race with atomicMin on (caller index, k).  Same grid shape as wf_refine (warp-private regions).
@@ -727,7 +754,10 @@ __device__ __forceinline__ void wf_tiebreak_body(const WaveParams& W, Scope sc_)
             atomicMin(&W.best_key[pr.x], (((unsigned long long)(__ldg(&P.sc.orig_id[pr.y]) + 1)) << 32) | pr.y);
     }
 }
-__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) { wf_tiebreak_body(W, grid_scope()); }
+__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) {
+    TraceScope trace(W.trace);
+    wf_tiebreak_body(W, grid_scope());
+}
 
 // exact closest hit of one ray by brute force in FP64 (only for entries whose pairs overflowed the pair buffer)
 __device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, float oy, float oz, float dx, float dy, float dz,
@@ -848,6 +878,7 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_
 }
 
 __global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
+    TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     __shared__ unsigned s_ctr[DC_COUNT];
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
@@ -867,6 +898,7 @@ __global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
 constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 1.5)
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
+    TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;

@@ -1,13 +1,19 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log
-while read -r wl steps; do
-  timeout 300 python bench.py --workload $wl --steps $steps --warmup 3 --no-cpu-baseline > gpurun_out/bench_s.json 2> gpurun_out/bench_s.err || tail -3 gpurun_out/bench_s.err
-  python - $wl <<'PY'
+while read -r kb ctas wl steps; do
+  RT_LIGHT_SMEM_KB=$kb RT_CULL_CTAS_PER_SM=$ctas timeout 300 python bench.py --workload $wl --steps $steps --warmup 3 --no-cpu-baseline > gpurun_out/bench_s.json 2> gpurun_out/bench_s.err || tail -3 gpurun_out/bench_s.err
+  python - $kb $ctas $wl <<'PY'
 import json,sys
-d=json.load(open("gpurun_out/bench_s.json")); k=d["roofline"]["dominant_kernel"]
-print("workload",*sys.argv[1:], "ms %.3f frac %.4f"%(d["ms_per_step"], d["roofline"]["frac"]), "cull %.2f (%.3f)"%(k["ms_per_step"],k["frac"]), {a:round(b,2) for a,b in k["other_stages_ms"].items()}, "e2e %.1fM"%(d["e2e"]["value"]/1e6), flush=True)
+d=json.load(open("gpurun_out/bench_s.json"))
+print("light smem KB / cull ctas / workload",*sys.argv[1:], "ms %.3f frac %.4f"%(d["ms_per_step"], d["roofline"]["frac"]), "e2e %.1fM"%(d["e2e"]["value"]/1e6), flush=True)
 PY
 done <<'CFG'
-c2 30
-c4 5
+0 4 c2 20
+20 4 c2 20
+30 4 c2 20
+40 4 c2 20
+48 4 c2 20
+0 4 c3-slice 4
+30 4 c3-slice 4
+40 4 c3-slice 4
+48 4 c3-slice 4
 CFG
