@@ -1,19 +1,9 @@
 mkdir -p gpurun_out
-while read -r kb ctas wl steps; do
-  RT_LIGHT_SMEM_KB=$kb RT_CULL_CTAS_PER_SM=$ctas timeout 300 python bench.py --workload $wl --steps $steps --warmup 3 --no-cpu-baseline > gpurun_out/bench_s.json 2> gpurun_out/bench_s.err || tail -3 gpurun_out/bench_s.err
-  python - $kb $ctas $wl <<'PY'
-import json,sys
-d=json.load(open("gpurun_out/bench_s.json"))
-print("light smem KB / cull ctas / workload",*sys.argv[1:], "ms %.3f frac %.4f"%(d["ms_per_step"], d["roofline"]["frac"]), "e2e %.1fM"%(d["e2e"]["value"]/1e6), flush=True)
+timeout 600 python -m pytest tests -m gpu -x -q -k "render or counters or sharding" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -2 gpurun_out/pytest_gpu.log
+for i in 1 2; do
+timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s.json 2> gpurun_out/bench_s.err || tail -3 gpurun_out/bench_s.err
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/bench_s.json")); print("c2 ms %.3f frac %.4f"%(d["ms_per_step"], d["roofline"]["frac"]), flush=True)
 PY
-done <<'CFG'
-0 4 c2 20
-20 4 c2 20
-30 4 c2 20
-40 4 c2 20
-48 4 c2 20
-0 4 c3-slice 4
-30 4 c3-slice 4
-40 4 c3-slice 4
-48 4 c3-slice 4
-CFG
+done
