@@ -27,7 +27,8 @@ namespace {
 
 constexpr int kR = 4;          // rays (path slots) per thread
 constexpr int kBlock = 256;
-constexpr int kMinBlocks = 2;
+constexpr int kMinBlocks = 1;     // megakernel: NO register cap — capped at 128 registers it spilled 288 bytes and one path in ~600 k
+                                  // differed from run to run (the uncapped build is bit-reproducible and agrees with the wavefront)
 constexpr int kTileCap = 4096; // float4 slots of the shared-memory sphere tile when the scene is tiled
 
 thread_local std::string g_create_error;

@@ -434,6 +434,30 @@ def test_counters_define_the_metric(renderer, scene_c2, variant):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
+def test_render_is_reproducible(renderer, scene_c2, variant):
+    """The same seed renders the same paths whatever the scheduling: every counter (rays, samples, how each path ended)
+    is identical across runs and the float sums differ only by the order of the atomic adds.  (A race in the queue
+    logic — a lost or duplicated path, a stale closest hit — would show here; compute-sanitizer is closed on this pool.)"""
+    flat, cam_type, cam, _ = scene_c2
+    renderer.set_scene(flat)
+    sc = rt.scene.make_random_scene(480, 320, 11, True, random.Random(1))
+    cam_type, cam = rt.native.marshal_camera(sc["camera"])
+    renderer.set_camera(cam_type, cam)
+    runs = []
+    for _ in range(3):
+        renderer.reset_counters()
+        lin, img = renderer.render(480, 320, 4, 50, seed=99, variant=variant)     # 614 400 samples: two lanes + tail
+        c = renderer.counters()
+        runs.append((lin, img, {k: c[k] for k in ("rays", "samples", "term_light", "term_absorb", "term_depth", "term_miss", "candidates")}))
+    for lin, img, c in runs[1:]:
+        assert c == runs[0][2]
+        assert np.allclose(lin, runs[0][0], rtol=1e-5, atol=1e-6)
+        assert (img != runs[0][1]).mean() < 1e-4          # an 8-bit value may sit on a rounding edge
+    c = runs[0][2]
+    assert c["samples"] == 480 * 320 * 4 == c["term_light"] + c["term_absorb"] + c["term_depth"] + c["term_miss"]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
 def test_resolve_bit_exact_and_sharding(renderer, scene_c2, variant):
     """rt_render_accumulate_device + rt_resolve_device on caller-owned device buffers (the per-GPU leg of the
     sharded render): sample slices and interleaved rows add up to the unsharded sums; the 8-bit resolve is
