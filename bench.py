@@ -74,7 +74,7 @@ def host_cores():
 
 
 def scene_bytes(flat):
-    return int(sum(getattr(flat, k).nbytes for k in flat.__dataclass_fields__)) + 24 * 4
+    return flat.nbytes() + 24 * 4
 
 
 class ClockSampler:

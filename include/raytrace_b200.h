@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2   /* 2: + rt_set_scene_ex / rt_scene_ext, rt_trace_paths, rt_set_accel, rt_set_option, rt_sample_device (additive) */
 
 typedef struct rt_ctx rt_ctx;
 
@@ -44,7 +44,8 @@ typedef enum rt_status {
     RT_ERR_UNSUPPORTED = -2,  /* object / material / texture type outside the hot path  */
     RT_ERR_CUDA = -3,         /* CUDA runtime error; rt_last_error has the CUDA string  */
     RT_ERR_STATE = -4,        /* call order: render before set_scene / set_camera       */
-    RT_ERR_NODEVICE = -5      /* no usable CUDA device (there is no CPU fallback)       */
+    RT_ERR_NODEVICE = -5,     /* no usable CUDA device (there is no CPU fallback)       */
+    RT_ERR_NCCL = -6          /* NCCL not loadable / a collective failed (multi-device reduce) */
 } rt_status;
 
 /* sphere_flags bits */
@@ -57,10 +58,50 @@ typedef enum rt_status {
 #define RT_MAT_DIELECTRIC    2  /* shader.clj:76-104  param = ri                      */
 #define RT_MAT_DIFFUSE_LIGHT 3  /* shader.clj:114-119 tex = emission                  */
 
+#define RT_MAT_ISOTROPIC     4  /* shader.clj:129-138 tex = albedo; scattered ray time = hit t (as in the reference); rt_set_scene_ex only */
+
 /* texture types (texture.clj) */
 #define RT_TEX_CONSTANT      0  /* texture.clj:14-16  params[0..2] = colour                                  */
 #define RT_TEX_UV_GRADIENT   1  /* texture.clj:26-34  params = co[3] cu[3] cv[3] cuv[3]                       */
 #define RT_TEX_CHECKERBOARD  2  /* texture.clj:44-50  params[0] = scale, children = {tex0, tex1}              */
+/* the following need rt_set_scene_ex (Perlin tables / images travel in rt_scene_ext) */
+#define RT_TEX_PERLIN_NOISE  3  /* texture.clj:60-64  params[0] = scale                                       */
+#define RT_TEX_PERLIN_TURB   4  /* texture.clj:74-78  params[0] = scale, params[1] = depth                    */
+#define RT_TEX_MARBLE        5  /* texture.clj:88-93  params[0] = scale, params[1] = depth                    */
+#define RT_TEX_FLIP_U        6  /* texture.clj:103-106 children[0] = tex                                      */
+#define RT_TEX_FLIP_V        7  /* texture.clj:113-116 children[0] = tex                                      */
+#define RT_TEX_IMAGE_MAP     8  /* texture.clj:126-133 params[0] = image index (indices clamped to the image) */
+
+/* primitive types (hitable.clj), rt_scene_ext.prim_type */
+#define RT_PRIM_SPHERE    0  /* Sphere / UVSphere / MovingSphere: center0_r, center1, t0t1, sphere_flags as in rt_scene_desc */
+#define RT_PRIM_RECT_XY   1  /* hitable.clj:272-297  prim_params = x0 y0 x1 y1 k   (inclusive t range, unlike spheres)      */
+#define RT_PRIM_RECT_XZ   2  /* hitable.clj:303-328  prim_params = x0 z0 x1 z1 k                                            */
+#define RT_PRIM_RECT_YZ   3  /* hitable.clj:334-359  prim_params = y0 z0 y1 z1 k                                            */
+#define RT_PRIM_TRIANGLE  4  /* hitable.clj:548-581  prim_params = v0 v1 v2 (9 floats); single-sided, un-normalised normal  */
+#define RT_PRIM_MEDIUM    5  /* hitable.clj:516-543  ConstantMedium: prim_params[0] = density, prim_aux = {first boundary
+                                primitive, count} (a sphere: 1; a Box: its 6 rectangles); material = RT_MAT_ISOTROPIC          */
+
+/* wrapper ops folded into a leaf's transform chain, outermost first (rt_scene_ext.xform_ops) */
+#define RT_XOP_NONE       0
+#define RT_XOP_TRANSLATE  1  /* hitable.clj:391-405  params = offset x y z   */
+#define RT_XOP_ROTATE_Y   2  /* hitable.clj:410-486  params = sin(theta), cos(theta) */
+#define RT_XOP_FLIP       3  /* hitable.clj:375-386  FlipNormals             */
+#define RT_XFORM_MAX_OPS  4
+
+/* which leaf wins an EXACT tie in t (coincident geometry only) */
+#define RT_TIE_HITLIST    0  /* the world is a Hitlist (hitable.clj:15-26): the first sphere in caller order, but a later
+                                rectangle / triangle (inclusive range test) replaces an equal earlier hit                    */
+#define RT_TIE_BVH        1  /* the world is a bvh-node tree (hitable.clj:97-106, right child wins): the LAST leaf in flatten order */
+
+/* closest-hit search (rt_set_accel) */
+#define RT_ACCEL_BRUTE_FORCE 0  /* FP32 cull over ALL listed primitives per ray: the roofline path (default)                 */
+#define RT_ACCEL_BVH         1  /* flattened GPU BVH feeding the same FP64 refine: the role of hitable.clj:97-123             */
+
+/* how a path ended (rt_trace_paths out_term) */
+#define RT_TERM_LIGHT   1
+#define RT_TERM_ABSORB  2
+#define RT_TERM_DEPTH   3
+#define RT_TERM_MISS    4
 
 /* camera types (camera.clj) */
 #define RT_CAM_PINHOLE    0     /* camera.clj:8-16   uses origin, lleft, horiz, vert; ray time 0, no RNG draws */
@@ -94,6 +135,42 @@ typedef struct rt_scene_desc {
 } rt_scene_desc;
 
 /*
+ * Everything beyond spheres and the three basic textures (ABI 2, additive: rt_scene_desc is unchanged).
+ * Every per-primitive array of rt_scene_desc AND of this struct then holds n_spheres WORLD primitives (flatten
+ * order) followed by n_boundary BOUNDARY primitives (the boundaries of media; never hit directly).
+ * Replaces: RectXY/XZ/YZ, FlipNormals, Translate, RotateY, Box, ConstantMedium, Triangle (hitable.clj:269-581),
+ * Isotropic (shader.clj:129-143), PerlinNoise/Turbulence/Marble/FlipTexture/ImageMap (texture.clj:60-138) and
+ * the Perlin tables perlin.clj:6-17 (marshalled: the reference draws them from the unseeded RNG at load time).
+ */
+typedef struct rt_scene_ext {
+    int32_t struct_bytes;          /* sizeof(rt_scene_ext) as the caller knows it                                   */
+    int32_t n_boundary;            /* boundary primitives after the n_spheres world primitives                       */
+    const int32_t* prim_type;      /* n_spheres + n_boundary: RT_PRIM_*; NULL => all spheres                         */
+    const float* prim_params;      /* 12 * (n_spheres + n_boundary)                                                  */
+    const int32_t* prim_aux;       /* 2 * (n_spheres + n_boundary): medium = {first boundary primitive, count}       */
+    const int32_t* prim_xform;     /* n_spheres + n_boundary: index into the transform table or -1                   */
+    int32_t n_xforms;
+    const int32_t* xform_ops;      /* RT_XFORM_MAX_OPS * n_xforms: RT_XOP_*, outermost wrapper first, 0-terminated   */
+    const float* xform_params;     /* 4 floats per op                                                                */
+    int32_t tie_rule;              /* RT_TIE_*                                                                       */
+    const float* perlin_vectors;   /* 256 * 3 (perlin.clj:6-8) or NULL                                               */
+    const int32_t* perlin_perm;    /* 3 * 256: perm-x, perm-y, perm-z (perlin.clj:10-17) or NULL                      */
+    int32_t n_images;
+    const int32_t* image_wh;       /* 2 * n_images: width, height                                                    */
+    const int64_t* image_offset;   /* n_images: byte offset of image i in image_rgb                                  */
+    const uint8_t* image_rgb;      /* RGB bytes, rows top to bottom (imagez get-pixel x y)                           */
+} rt_scene_ext;
+
+/* one logged ray of rt_trace_paths */
+typedef struct rt_path_bounce {
+    float o[3];
+    float time;
+    float d[3];
+    int32_t hit_id;                /* caller's primitive index, -1 = miss, -2 = the path had ended before this bounce */
+    double t;
+} rt_path_bounce;
+
+/*
  * Camera record (camera.clj:35 ThinLensCamera / camera.clj:8 PinholeCamera):
  * cam[0..20] = origin lleft horiz vert u v w (3 floats each), cam[21] = aperture,
  * cam[22] = t0, cam[23] = t1.
@@ -115,7 +192,11 @@ enum {
     RT_CTR_REFINE_NS,
     RT_CTR_TIEBREAK_NS,
     RT_CTR_SHADE_NS,
-    RT_CTR_COUNT = 16
+    RT_CTR_DIRECT_TESTS,     /* exact (FP64) tests of the few enclosing spheres that bypass the FP32 cull (counted apart
+                                from the culled tests; RT_CTR_SPHERE_TESTS = rays * n still counts every pair once)   */
+    RT_CTR_BVH_NODE_TESTS,   /* RT_ACCEL_BVH: box tests (the reference's `aabb.intersection.total`, metrics.clj:9)     */
+    RT_CTR_REDUCE_NS,        /* multi-device rt_render: device time of the cross-device reduce, ns                     */
+    RT_CTR_COUNT = 24
 };
 
 /* ---- lifecycle ------------------------------------------------------------------------ */
@@ -130,11 +211,23 @@ int rt_abi_version(void);
 
 /* ---- scene / camera (replace the record graph built at core.clj:82-90) ---------------- */
 int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* scene);
+/* the same with the extension record (ext may be NULL = rt_set_scene) */
+int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* scene, const rt_scene_ext* ext);
+/* closest-hit search used by the renders that follow: RT_ACCEL_BRUTE_FORCE (default) or RT_ACCEL_BVH */
+int rt_set_accel(rt_ctx* ctx, int accel);
+/* Per-context tuning knob; the RT_* environment variables only give the defaults at rt_create.  Names:
+ * "wave_lanes", "wave_capacity", "cull_claims", "cull_ctas_per_sm", "light_block", "tail_entries", "tile_records",
+ * "direct_spheres", "common_origin", "reduce" (0 peer loads in the resolve kernel, 1 ncclReduce), "rows" (multi-device
+ * partition: 0 sample slices, 1 interleaved rows).  Unknown name -> RT_ERR_ARG.                                   */
+int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_set_camera(rt_ctx* ctx, int cam_type, const float cam[24]);
 
 /* ---- the hot path (replaces core.clj:99-108) ------------------------------------------ */
 
-/* Render nsamples per pixel, depth cutoff max_depth (reference: 50, core.clj:20,45).
+/* Limits (checked, RT_ERR_ARG): nx * ny <= (2^31 - 1) / 3 pixels; nsamples (and sample_begin + sample_count) < 2^24;
+ * the wavefront variant packs the remaining depth in 8 bits: max_depth <= 255 (the megakernel takes any depth >= 0).
+ *
+ * Render nsamples per pixel, depth cutoff max_depth (reference: 50, core.clj:20,45).
  * out_linear_rgb: nx*ny*3 float, per-pixel SUM over samples / nsamples (before gamma),
  *                 pixel (i, j) at ((j*nx)+i)*3, j = 0 is the BOTTOM row (reference's j); may be NULL.
  * out_rgb8:       nx*ny*3 bytes after sqrt, *255.99, min, truncate (core.clj:52-57), row 0 = TOP
@@ -164,6 +257,19 @@ int rt_resolve_device(rt_ctx* ctx, int nx, int ny, int nsamples_total, const flo
 int rt_trace_primary(rt_ctx* ctx, int n, const float* origins /*3n*/, const float* dirs /*3n*/,
                      const float* times /*n or NULL*/, double tmin, double tmax,
                      double* out_t, int32_t* out_id);
+
+/* The production render code (either variant: same queues / cull / refine / shade kernels) run for n caller-chosen
+ * (pixel, sample) pairs of an nx x ny frame instead of the whole frame: pixel[q] = j * nx + i (j = 0 bottom row),
+ * sample[q] = the sample index keyed into the Philox counters.  Per path: out_radiance (3n, what `color` returns,
+ * core.clj:17-41), out_nrays (hit?(world) calls), out_term (RT_TERM_*); out_log (n * log_bounces records or NULL)
+ * receives the first log_bounces rays of every path with the hit the renderer resolved for them.               */
+int rt_trace_paths(rt_ctx* ctx, int nx, int ny, int n, const int32_t* pixel, const int32_t* sample, int max_depth,
+                   uint64_t seed, int variant, float* out_radiance, int32_t* out_nrays, int32_t* out_term,
+                   int log_bounces, rt_path_bounce* out_log);
+
+/* n points of the device's rand-in-unit-sphere (kind 0: 3n floats) or rand-in-unit-disk (kind 1: 2n floats) —
+ * util.clj:32-52 in closed form — drawn from the Philox counters (pixel = index, sample 0, bounce 1 | 0).       */
+int rt_sample_device(rt_ctx* ctx, int kind, int n, uint64_t seed, float* out);
 
 /* The contract of the FP32 cull (the brute-force loop over the sphere list), checked pair by pair on the
  * device: out[0] = (ray, listed sphere) pairs whose exact FP64 test (hitable.clj:185-206) accepts a root in

@@ -39,8 +39,10 @@ struct DeviceBuffers {
     int dev = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
-    // scene
+    // scene (the device blob and its pinned staging copy are reused across rt_set_scene calls)
     void* scene_blob = nullptr;
+    void* scene_stage = nullptr;
+    size_t scene_bytes = 0;
     DevScene sc{};
     // frame
     float* d_sum = nullptr;
@@ -81,19 +83,43 @@ struct DeviceBuffers {
 
 }  // namespace
 
+// Tuning knobs of one context.  The RT_* environment variables give the defaults at rt_create; rt_set_option changes
+// them per context afterwards (two contexts of one process can differ).
+struct Options {
+    int wave_lanes = 2;               // RT_WAVE_LANES: independent halves of the path population (1..kMaxLanes)
+    long long wave_capacity = 1ll << 24;   // RT_WAVE_CAPACITY: paths in flight per device, all lanes together
+    int cull_claims = 2;              // RT_CULL_CLAIMS: batches a cull warp takes before it retires (0 = persistent warps)
+    int cull_ctas_per_sm = 4;         // RT_CULL_CTAS_PER_SM
+    int cull_shape = 0;               // RT_CULL_SHAPE: 0 = 128x5 (default), 1 = 128x6, 2 = 256x2
+    int light_block = 128;            // RT_LIGHT_BLOCK: CTA size of the stage kernels
+    long long tail_entries = 1 << 19; // RT_TAIL_ENTRIES: queue length at which wf_tail takes over
+    int tail_ctas_per_sm = 0;         // RT_TAIL_CTAS_PER_SM (0 = automatic)
+    int tile_records = 1024;          // RT_TILE_RECORDS
+    int direct_spheres = 1;           // RT_DIRECT_SPHERES
+    int common_origin = 1;            // RT_COMMON_ORIGIN
+    int reduce = 0;                   // multi-device rt_render: 0 = NVLink peer loads inside the resolve kernel, 1 = ncclReduce
+    int rows = 0;                     // multi-device partition: 0 = sample slices, 1 = interleaved rows
+};
+
 struct rt_ctx {
     std::mutex mu;
     std::string err;
     std::vector<DeviceBuffers> devs;
+    Options opt;
     bool has_scene = false, has_cam = false;
-    int n_spheres = 0;
+    int n_spheres = 0;            // world primitives
+    int n_total = 0;              // + boundary primitives of media
     int n_list = 0, n_cull = 0;   // spheres in the cull list / cull records (padded)
     int cull_cap = 0, preloaded = 0;
+    int generic = 0;              // some leaf is not a plain sphere (rt_set_scene_ex)
+    int accel = RT_ACCEL_BRUTE_FORCE;
     // time window [win_lo, win_hi] the movers' bounding spheres cover; grown (and the cull records rebuilt)
     // when a camera shutter interval or a traced ray's time falls outside
     double win_lo = 0.0, win_hi = 0.0;
-    std::vector<float> h_c0r, h_c1, h_t0t1;   // geometry in cull order
+    std::vector<float> h_c0r, h_c1, h_t0t1;   // geometry in cull order (world primitives, then boundary primitives)
     std::vector<unsigned> h_flags;
+    // world-space bounding sphere of every world leaf, cull order: centre at t0 / t1 (equal unless moving), radius
+    std::vector<double> h_bs_c0, h_bs_c1, h_bs_r;
     DevCamera cam{};
     std::atomic<uint64_t> n_launches{0};
     std::mutex err_mu;
@@ -146,9 +172,7 @@ int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
     return RT_OK;
 }
 
-constexpr size_t kWaveCapacity = 1u << 24;  // paths in flight per device (all lanes together; ~5 GB of queues at full size)
 constexpr int kWaveChunk = 4;           // iterations enqueued between two polls of the queue count
-constexpr unsigned kTailEntries = 1u << 19;   // queue length at which the per-CTA tail kernel takes over
 
 void free_lane(DeviceBuffers::WaveLane& L) {
     if (L.queue) cudaFree(L.queue);
@@ -230,11 +254,30 @@ int configure_kernel(rt_ctx* ctx, Kern kern, size_t smem, int* blocks_per_sm) {
     return RT_OK;
 }
 
-// tuning knobs (environment, read once): RT_WAVE_BLOCK = 128 | 256 threads per CTA, RT_WAVE_M = queue
-// capacity in 32*R-entry batches per warp
-int env_int(const char* name, int dflt) {
+long long env_ll(const char* name, long long dflt) {
     const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
+    return (v && *v) ? atoll(v) : dflt;
+}
+int env_int(const char* name, int dflt) { return (int)env_ll(name, dflt); }
+
+Options options_from_env() {
+    Options o;
+    o.wave_lanes = env_int("RT_WAVE_LANES", o.wave_lanes);
+    o.wave_capacity = env_ll("RT_WAVE_CAPACITY", o.wave_capacity);
+    o.cull_claims = env_int("RT_CULL_CLAIMS", o.cull_claims);
+    o.cull_ctas_per_sm = env_int("RT_CULL_CTAS_PER_SM", o.cull_ctas_per_sm);
+    const char* shape = getenv("RT_CULL_SHAPE");
+    if (shape && !strcmp(shape, "128x6")) o.cull_shape = 1;
+    if (shape && !strcmp(shape, "256x2")) o.cull_shape = 2;
+    o.light_block = env_int("RT_LIGHT_BLOCK", o.light_block);
+    o.tail_entries = env_ll("RT_TAIL_ENTRIES", o.tail_entries);
+    o.tail_ctas_per_sm = env_int("RT_TAIL_CTAS_PER_SM", o.tail_ctas_per_sm);
+    o.tile_records = env_int("RT_TILE_RECORDS", o.tile_records);
+    o.direct_spheres = env_int("RT_DIRECT_SPHERES", o.direct_spheres);
+    o.common_origin = env_int("RT_COMMON_ORIGIN", o.common_origin);
+    o.reduce = env_int("RT_REDUCE", o.reduce);
+    o.rows = env_int("RT_ROWS", o.rows);
+    return o;
 }
 
 // Wavefront render of one device's share: enqueue iterations (cull, refine, shade) ahead of the
@@ -259,40 +302,44 @@ int cull_config(rt_ctx* ctx, size_t* smem, int* bps, void (**kern)(const WavePar
 // iterations per lane ahead of the GPU and polls each lane's queue count; when the work counter is
 // exhausted and a lane's queue is short, one wf_tail launch finishes that lane (every CTA on its own slice).
 int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned long long, cudaStream_t stream) {
-    // CTA shape of the cull kernel (threads x register-cap CTAs/SM); RT_CULL_SHAPE = "128x5" (default) | "128x6" | "256x2"
-    static const std::string shape = getenv("RT_CULL_SHAPE") ? getenv("RT_CULL_SHAPE") : "128x5";
+    // CTA shape of the cull kernel (threads x register-cap CTAs/SM): 128x5 (default) | 128x6 | 256x2
+    const Options& opt = ctx->opt;
     void (*cull)(const WaveParams) = nullptr;
     size_t smem = 0;
     int bps = 0, cull_block = 256, rc;
-    if (shape == "256x2") rc = cull_config<256, 2>(ctx, &smem, &bps, &cull);
-    else if (shape == "128x6") { rc = cull_config<128, 6>(ctx, &smem, &bps, &cull); cull_block = 128; }
+    if (opt.cull_shape == 2) rc = cull_config<256, 2>(ctx, &smem, &bps, &cull);
+    else if (opt.cull_shape == 1) { rc = cull_config<128, 6>(ctx, &smem, &bps, &cull); cull_block = 128; }
     else { rc = cull_config<128, 5>(ctx, &smem, &bps, &cull); cull_block = 128; }
     if (rc) return rc;
-    static const int cull_ctas_env = env_int("RT_CULL_CTAS_PER_SM", 4);   // one fewer than the occupancy limit leaves
+    const int cull_ctas_env = opt.cull_ctas_per_sm;                       // one fewer than the occupancy limit leaves
     if (cull_ctas_env > 0) bps = std::min(bps, cull_ctas_env);           // room for the other lane's light kernels
-    static const size_t cap_env = (size_t)std::max(64, env_int("RT_WAVE_CAPACITY", (int)kWaveCapacity));
-    static const int lanes_env = std::max(1, std::min(kMaxLanes, env_int("RT_WAVE_LANES", 2)));
+    const size_t cap_env = (size_t)std::max<long long>(64, opt.wave_capacity);
+    const int lanes_env = std::max(1, std::min(kMaxLanes, opt.wave_lanes));
     const int n_lanes = (ctx->profile || P.total_work < 65536) ? 1 : lanes_env;   // stage timing wants one lane
     const size_t capacity = align_up((size_t)std::min<unsigned long long>(cap_env / n_lanes, (P.total_work + n_lanes - 1) / n_lanes), 32);
 
     // tail kernel: one CTA per SM per lane (two lanes' tails run side by side)
-    static const unsigned tail_entries = (unsigned)std::max(0, env_int("RT_TAIL_ENTRIES", (int)kTailEntries));
+    const unsigned tail_entries = (unsigned)std::max<long long>(0, opt.tail_entries);
     const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<1, 256>::LIST_BYTES;
     int tail_bps = 0;
-    RT_CUDA(ctx, cudaFuncSetAttribute(wf_tail<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_bps, wf_tail<256>, 256, tail_smem));
-    static const int tail_ctas = std::max(1, env_int("RT_TAIL_CTAS_PER_SM", 0));
-    const int tail_grid = d.sm_count * (env_int("RT_TAIL_CTAS_PER_SM", 0) > 0 ? tail_ctas : (n_lanes > 1 ? 1 : std::max(1, std::min(tail_bps, 2))));
+    // GEN = false instantiations hold none of the generic-leaf / extended-texture code (registers, I-cache)
+    const bool gen = ctx->generic != 0;
+    void (*k_tail)(const WaveParams) = gen ? wf_tail<256, true> : wf_tail<256, false>;
+    void (*k_refine)(const WaveParams) = gen ? wf_refine<true> : wf_refine<false>;
+    void (*k_shade)(const WaveParams) = gen ? wf_shade<true> : wf_shade<false>;
+    RT_CUDA(ctx, cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_bps, k_tail, 256, tail_smem));
+    const int tail_grid = d.sm_count * (opt.tail_ctas_per_sm > 0 ? opt.tail_ctas_per_sm : (n_lanes > 1 ? 1 : std::max(1, std::min(tail_bps, 2))));
     const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile;
 
-    static const int light_block = std::max(64, std::min(256, env_int("RT_LIGHT_BLOCK", 128) / 32 * 32));   // <= a cull CTA in every resource
+    const int light_block = std::max(64, std::min(256, opt.light_block / 32 * 32));   // <= a cull CTA in every resource
     const int light_grid = d.sm_count * 8 * 256 / light_block;
     const int cull_grid = d.sm_count * bps;
     // RT_CULL_CLAIMS = k > 0 (resident scenes): cull warps retire after k batches — the cull becomes many short CTAs, SM
     // slots turn over every few tens of microseconds, and the OTHER lane's refine / tie-break / shade kernels, launched
     // on a high-priority stream, take the freed slots at once instead of waiting for the whole persistent cull to end.
     // 0 = persistent cull warps, one stream per lane.
-    static const int claims_env = std::max(0, env_int("RT_CULL_CLAIMS", 2));
+    const int claims_env = std::max(0, opt.cull_claims);
     const int claims = (ctx->profile || !ctx->preloaded || n_lanes < 2) ? 0 : claims_env;
     const int cull_warps = cull_block / 32, resident_warps = cull_grid * cull_warps;
     unsigned n_bound[kMaxLanes];   // upper bound of each lane's queue length (sizes the short-CTA grids)
@@ -378,11 +425,11 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     RT_CUDA(ctx, cudaEventRecord(L.ev_culled, st[l]));
                     RT_CUDA(ctx, cudaStreamWaitEvent(L.stage_stream, L.ev_culled, 0));
                     W[l].trace = trace_slot("refine", l, iter_no[l]);
-                    wf_refine<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    k_refine<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
                     W[l].trace = trace_slot("tiebreak", l, iter_no[l]);
                     wf_tiebreak<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
                     W[l].trace = trace_slot("shade", l, iter_no[l]);
-                    wf_shade<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    k_shade<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
                     RT_CUDA(ctx, cudaEventRecord(L.ev_shaded, L.stage_stream));
                     RT_CUDA(ctx, cudaStreamWaitEvent(st[l], L.ev_shaded, 0));
                 } else {
@@ -390,13 +437,13 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[1], st[l]);
                     W[l].trace = trace_slot("refine", l, iter_no[l]);
-                    wf_refine<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                    k_refine<<<light_grid, light_block, 0, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[2], st[l]);
                     W[l].trace = trace_slot("tiebreak", l, iter_no[l]);
                     wf_tiebreak<<<light_grid, light_block, 0, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[3], st[l]);
                     W[l].trace = trace_slot("shade", l, iter_no[l]);
-                    wf_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                    k_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[4], st[l]);
                 }
                 W[l].cur ^= 1;
@@ -420,7 +467,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 } else if (tail_ok && snap.exhausted && snap.cnt[W[l].cur][1] == 0 && snap.cnt[W[l].cur][0] <= tail_entries) {
                     // no new work can appear and the queue is short: one launch finishes this lane
                     W[l].trace = trace_slot("tail", l, iter_no[l]);
-                    wf_tail<256><<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
+                    k_tail<<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
                     RT_CUDA(ctx, cudaGetLastError());
                     ctx->n_launches += 1;
                     done[l] = true;
@@ -447,13 +494,11 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     return RT_OK;
 }
 
+int launch_params(rt_ctx* ctx, DeviceBuffers& d, RenderParams& P, int variant, cudaStream_t stream);
+
 // Launch the render kernels for one device's share of the work (async on d.stream).
 int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begin, int sample_count, int row_offset,
                   int row_stride, int max_depth, uint64_t seed, int variant, float* d_sum, cudaStream_t stream) {
-    if (variant != RT_VARIANT_MEGAKERNEL && variant != RT_VARIANT_WAVEFRONT)
-        return fail(ctx, RT_ERR_ARG, "unknown render variant");
-    if (variant == RT_VARIANT_WAVEFRONT && max_depth > 255)
-        return fail(ctx, RT_ERR_ARG, "the wavefront variant packs the depth in 8 bits: max_depth <= 255");
     RenderParams P{};
     P.sc = d.sc;
     P.cam = ctx->cam;
@@ -470,18 +515,30 @@ int launch_render(rt_ctx* ctx, DeviceBuffers& d, int nx, int ny, int sample_begi
     P.counters = d.d_counters;
     P.work_counter = d.d_counters + DC_COUNT;
     P.total_work = (unsigned long long)sample_count * (unsigned long long)nx * (unsigned long long)P.rows_in_shard;
+    if ((sample_begin + sample_count) >= (1 << 24)) return fail(ctx, RT_ERR_ARG, "sample index must stay below 2^24");
+    return launch_params(ctx, d, P, variant, stream);
+}
+
+// P: scene-independent fields filled by the caller (frame, work, seed, outputs); the rest is completed here
+int launch_params(rt_ctx* ctx, DeviceBuffers& d, RenderParams& P, int variant, cudaStream_t stream) {
+    if (variant != RT_VARIANT_MEGAKERNEL && variant != RT_VARIANT_WAVEFRONT)
+        return fail(ctx, RT_ERR_ARG, "unknown render variant");
+    if (variant == RT_VARIANT_WAVEFRONT && P.max_depth > 255)
+        return fail(ctx, RT_ERR_ARG, "the wavefront variant packs the depth in 8 bits: max_depth <= 255");
+    P.sc = d.sc;
+    P.cam = ctx->cam;
+    P.counters = d.d_counters;
+    P.work_counter = d.d_counters + DC_COUNT;
     P.cull_cap = ctx->cull_cap;
     P.preloaded = ctx->preloaded;
-    static const int common_env = env_int("RT_COMMON_ORIGIN", 1);
-    P.common_origin = (common_env && (ctx->cam.type == CAM_PINHOLE || ctx->cam.lens_radius == 0.f)) ? 1 : 0;
+    P.common_origin = (ctx->opt.common_origin && (ctx->cam.type == CAM_PINHOLE || ctx->cam.lens_radius == 0.f)) ? 1 : 0;
     RT_CUDA(ctx, cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long), stream));
     if (P.total_work == 0) return RT_OK;
-    if ((sample_begin + sample_count) >= (1 << 24)) return fail(ctx, RT_ERR_ARG, "sample index must stay below 2^24");
     size_t smem = mega_smem_bytes(ctx->cull_cap);
     unsigned long long want = (P.total_work + (unsigned long long)kBlock * kR - 1) / ((unsigned long long)kBlock * kR);
     int bps = 0;
     if (variant == RT_VARIANT_MEGAKERNEL) {
-        auto kern = mega_kernel<kR, kBlock, kMinBlocks>;
+        void (*kern)(const RenderParams) = ctx->generic ? mega_kernel<kR, kBlock, kMinBlocks, true> : mega_kernel<kR, kBlock, kMinBlocks, false>;
         int rc = configure_kernel(ctx, kern, smem, &bps);
         if (rc) return rc;
         int grid = (int)std::min<unsigned long long>((unsigned long long)d.sm_count * bps, want);
@@ -507,13 +564,15 @@ void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* 
     for (int i = 0; i < ctx->n_spheres; ++i) {
         // listed spheres at [0, n_list); the direct spheres' records follow the padding, at n_cull + (i - n_list)
         float* cull_a = i < ctx->n_list ? cull_all : cull_all + 4 * (size_t)(ctx->n_cull - ctx->n_list);
-        double r = std::fabs((double)ctx->h_c0r[4 * i + 3]);
+        // the leaf's world-space bounding sphere (a sphere: itself; a rectangle / triangle / medium: the sphere around it,
+        // carried through the leaf's wrappers at upload)
+        double r = std::fabs(ctx->h_bs_r[(size_t)i]);
         double mid[3], half2 = 0.0, cmax = 0.0;
         const bool moving = (ctx->h_flags[i] & RT_SPHERE_MOVING) != 0;
         for (int c = 0; c < 3; ++c) {
-            double p0 = ctx->h_c0r[4 * i + c];
+            double p0 = ctx->h_bs_c0[3 * (size_t)i + c];
             if (moving) {
-                double p1 = ctx->h_c1[4 * i + c], t0 = ctx->h_t0t1[2 * i], t1 = ctx->h_t0t1[2 * i + 1];
+                double p1 = ctx->h_bs_c1[3 * (size_t)i + c], t0 = ctx->h_t0t1[2 * i], t1 = ctx->h_t0t1[2 * i + 1];
                 double fa = (win_lo - t0) / (t1 - t0), fb = (win_hi - t0) / (t1 - t0);
                 double pa = p0 * (1.0 - fa) + p1 * fa, pb = p0 * (1.0 - fb) + p1 * fb;
                 mid[c] = 0.5 * (pa + pb);
@@ -524,7 +583,8 @@ void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* 
             cmax = std::max(cmax, std::fabs(mid[c]));
         }
         double rb = r + std::sqrt(half2);
-        double e = moving ? std::ldexp(1.0, -21) * (cmax + rb) : 0.0;   // float rounding of the midpoint (+ margin)
+        // float rounding of the midpoint (+ margin); generic leaves: also the rounding of the transformed centre / radius
+        double e = (moving || ctx->generic) ? std::ldexp(1.0, -21) * (cmax + rb) : 0.0;
         double cc = 0.0;
         for (int c = 0; c < 3; ++c) {
             const float neg = (float)(-mid[c]);       // negated: the chains are seeded FFMAs on -c
@@ -555,7 +615,7 @@ int ensure_window(rt_ctx* ctx, double lo, double hi) {
     if (cull.empty()) return RT_OK;
     for (auto& d : ctx->devs) {
         RT_CUDA(ctx, cudaSetDevice(d.dev));
-        RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        RT_CUDA(ctx, cudaDeviceSynchronize());   // a render enqueued with sync = 0 on a caller's stream may still read the records
         RT_CUDA(ctx, cudaMemcpy((void*)d.sc.cull_a, cull.data(), cull.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     cudaSetDevice(ctx->devs[0].dev);
@@ -594,6 +654,7 @@ int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
         return fail(nullptr, RT_ERR_NODEVICE,
                     std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
     rt_ctx* ctx = new rt_ctx();
+    ctx->opt = options_from_env();
     ctx->devs.resize(n_devices);
     ctx->peer_ok.assign(n_devices, false);
     for (int i = 0; i < n_devices; ++i) {
@@ -648,6 +709,7 @@ void rt_destroy(rt_ctx* ctx) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
         if (d.scene_blob) cudaFree(d.scene_blob);
+        if (d.scene_stage) cudaFreeHost(d.scene_stage);
         if (d.d_sum) cudaFree(d.d_sum);
         if (d.d_mean) cudaFree(d.d_mean);
         if (d.d_rgb8) cudaFree(d.d_rgb8);
@@ -671,40 +733,135 @@ int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, char name[64]) {
     return RT_OK;
 }
 
-// Upload: validate, reorder to cull order (static spheres, then moving), build the FP32 cull
+// a point carried out of a leaf's wrapper chain (object space -> world), the way the hit point travels
+// (hitable.clj:398-400, :443-449): last op first
+static void xform_point_back(const rt_scene_ext* x, int xf, double p[3]) {
+    if (xf < 0) return;
+    int nops = 0;
+    while (nops < RT_XFORM_MAX_OPS && x->xform_ops[RT_XFORM_MAX_OPS * xf + nops] != RT_XOP_NONE) ++nops;
+    for (int q = nops - 1; q >= 0; --q) {
+        const float* pr = x->xform_params + 4 * (size_t)(RT_XFORM_MAX_OPS * xf + q);
+        const int op = x->xform_ops[RT_XFORM_MAX_OPS * xf + q];
+        if (op == RT_XOP_TRANSLATE) { p[0] += pr[0]; p[1] += pr[1]; p[2] += pr[2]; }
+        else if (op == RT_XOP_ROTATE_Y) {
+            const double sn = pr[0], cs = pr[1], px = p[0], pz = p[2];
+            p[0] = cs * px + sn * pz;
+            p[2] = -(sn * px) + cs * pz;
+        }
+    }
+}
+
+// object-space bounding sphere of leaf i (caller's index): centre at t0 / t1, radius.  Media: see below.
+static void leaf_bounds(const rt_scene_desc* s, const rt_scene_ext* x, int i, double c0[3], double c1[3], double* r) {
+    const int type = (x && x->prim_type) ? x->prim_type[i] : RT_PRIM_SPHERE;
+    const float* q = (x && x->prim_params) ? x->prim_params + 12 * (size_t)i : nullptr;
+    if (type == RT_PRIM_SPHERE) {
+        const bool moving = s->sphere_flags && (s->sphere_flags[i] & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
+        for (int c = 0; c < 3; ++c) {
+            c0[c] = s->center0_r[4 * i + c];
+            c1[c] = moving ? s->center1[4 * i + c] : c0[c];
+        }
+        *r = std::fabs((double)s->center0_r[4 * i + 3]);
+    } else if (type == RT_PRIM_TRIANGLE) {
+        double lo[3], hi[3];
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = std::min({(double)q[c], (double)q[3 + c], (double)q[6 + c]});
+            hi[c] = std::max({(double)q[c], (double)q[3 + c], (double)q[6 + c]});
+            c0[c] = c1[c] = 0.5 * (lo[c] + hi[c]);
+        }
+        double r2 = 0.0;
+        for (int v = 0; v < 3; ++v) {
+            double d2 = 0.0;
+            for (int c = 0; c < 3; ++c) d2 += (q[3 * v + c] - c0[c]) * (q[3 * v + c] - c0[c]);
+            r2 = std::max(r2, d2);
+        }
+        *r = std::sqrt(r2) * (1.0 + 1e-6) + 1e-6;
+    } else {   // rectangles: q = a0 b0 a1 b1 k
+        const int axis = type == RT_PRIM_RECT_XY ? 2 : (type == RT_PRIM_RECT_XZ ? 1 : 0);
+        const int A = type == RT_PRIM_RECT_YZ ? 1 : 0, B = type == RT_PRIM_RECT_XY ? 1 : 2;
+        c0[A] = 0.5 * ((double)q[0] + q[2]); c0[B] = 0.5 * ((double)q[1] + q[3]); c0[axis] = q[4];
+        for (int c = 0; c < 3; ++c) c1[c] = c0[c];
+        const double da = 0.5 * ((double)q[2] - q[0]), db = 0.5 * ((double)q[3] - q[1]);
+        *r = std::sqrt(da * da + db * db) * (1.0 + 1e-6) + 1e-6;
+    }
+}
+
+// Upload: validate, reorder to cull order (listed leaves, then the "direct" spheres), build the FP32 cull
 // records with their conservative inflation, and copy one blob per device.
-int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
+int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* s, const rt_scene_ext* x) {
     if (!ctx) return RT_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!s) return fail(ctx, RT_ERR_ARG, "scene is null");
+    if (x && x->struct_bytes != (int32_t)sizeof(rt_scene_ext)) return fail(ctx, RT_ERR_ARG, "rt_scene_ext.struct_bytes does not match this library (ABI 2: 120 bytes)");
     const int n = s->n_spheres, nm_ = s->n_materials, nt = s->n_textures;
-    if (n <= 0 || !s->center0_r || !s->material_id) return fail(ctx, RT_ERR_ARG, "scene needs at least one sphere");
+    const int nb = x ? x->n_boundary : 0, n_total = n + nb;
+    if (n <= 0 || !s->center0_r || !s->material_id) return fail(ctx, RT_ERR_ARG, "scene needs at least one primitive");
+    if (nb < 0) return fail(ctx, RT_ERR_ARG, "n_boundary is negative");
     if (nm_ <= 0 || !s->mat_type || !s->mat_param || !s->mat_tex) return fail(ctx, RT_ERR_ARG, "material table missing");
     if (nt < 0 || (nt > 0 && (!s->tex_type || !s->tex_params || !s->tex_children)))
         return fail(ctx, RT_ERR_ARG, "texture table missing");
+    const int max_tex = x ? RT_TEX_IMAGE_MAP : RT_TEX_CHECKERBOARD, max_mat = x ? RT_MAT_ISOTROPIC : RT_MAT_DIFFUSE_LIGHT;
+    bool uses_perlin = false;
     for (int t = 0; t < nt; ++t) {
         int ty = s->tex_type[t];
-        if (ty != RT_TEX_CONSTANT && ty != RT_TEX_UV_GRADIENT && ty != RT_TEX_CHECKERBOARD)
-            return fail(ctx, RT_ERR_UNSUPPORTED, "texture type outside the accelerated path (texture.clj:60-138)");
-        if (ty == RT_TEX_CHECKERBOARD)
-            for (int c = 0; c < 2; ++c) {
-                int ch = s->tex_children[2 * t + c];
-                if (ch < 0 || ch >= t) return fail(ctx, RT_ERR_ARG, "checkerboard child must be an earlier texture id");
-            }
+        if (ty < RT_TEX_CONSTANT || ty > max_tex)
+            return fail(ctx, RT_ERR_UNSUPPORTED, x ? "unknown texture type" : "texture type needs rt_set_scene_ex (texture.clj:60-138)");
+        const int n_children = ty == RT_TEX_CHECKERBOARD ? 2 : ((ty == RT_TEX_FLIP_U || ty == RT_TEX_FLIP_V) ? 1 : 0);
+        for (int c = 0; c < n_children; ++c) {
+            int ch = s->tex_children[2 * t + c];
+            if (ch < 0 || ch >= t) return fail(ctx, RT_ERR_ARG, "a texture's child must be an earlier texture id");
+        }
+        if (ty == RT_TEX_PERLIN_NOISE || ty == RT_TEX_PERLIN_TURB || ty == RT_TEX_MARBLE) uses_perlin = true;
+        if (ty == RT_TEX_IMAGE_MAP) {
+            const int im = (int)s->tex_params[12 * t];
+            if (im < 0 || im >= x->n_images || !x->image_wh || !x->image_offset || !x->image_rgb || x->image_wh[2 * im] <= 0 ||
+                x->image_wh[2 * im + 1] <= 0)
+                return fail(ctx, RT_ERR_ARG, "image texture refers to a missing image");
+        }
     }
+    if (uses_perlin && (!x->perlin_vectors || !x->perlin_perm)) return fail(ctx, RT_ERR_ARG, "Perlin textures need the marshalled tables (perlin.clj:6-17)");
     for (int m = 0; m < nm_; ++m) {
         int ty = s->mat_type[m];
-        if (ty < RT_MAT_LAMBERTIAN || ty > RT_MAT_DIFFUSE_LIGHT)
-            return fail(ctx, RT_ERR_UNSUPPORTED, "material type outside the accelerated path (shader.clj:129-143)");
+        if (ty < RT_MAT_LAMBERTIAN || ty > max_mat)
+            return fail(ctx, RT_ERR_UNSUPPORTED, x ? "unknown material type" : "material type needs rt_set_scene_ex (shader.clj:129-143)");
         if (ty != RT_MAT_DIELECTRIC && (s->mat_tex[m] < 0 || s->mat_tex[m] >= nt))
             return fail(ctx, RT_ERR_ARG, "material texture id out of range");
     }
+    const int tie_rule = x ? x->tie_rule : RT_TIE_HITLIST;
+    if (tie_rule != RT_TIE_HITLIST && tie_rule != RT_TIE_BVH) return fail(ctx, RT_ERR_ARG, "unknown tie rule");
+    int generic = uses_perlin ? 1 : 0;
+    for (int t = 0; t < nt; ++t) if (s->tex_type[t] > RT_TEX_CHECKERBOARD) generic = 1;
+    for (int m = 0; m < nm_; ++m) if (s->mat_type[m] == RT_MAT_ISOTROPIC) generic = 1;
+    if (x && (x->prim_type || x->prim_xform)) {
+        if ((x->prim_type && !x->prim_params) || (x->n_xforms > 0 && (!x->xform_ops || !x->xform_params)) || x->n_xforms < 0)
+            return fail(ctx, RT_ERR_ARG, "primitive / transform tables missing");
+        for (int i = 0; i < n_total; ++i) {
+            const int ty = x->prim_type ? x->prim_type[i] : RT_PRIM_SPHERE;
+            if (ty < RT_PRIM_SPHERE || ty > RT_PRIM_MEDIUM) return fail(ctx, RT_ERR_UNSUPPORTED, "unknown primitive type");
+            const int xf = x->prim_xform ? x->prim_xform[i] : -1;
+            if (xf < -1 || xf >= x->n_xforms) return fail(ctx, RT_ERR_ARG, "transform index out of range");
+            if (ty != RT_PRIM_SPHERE || xf >= 0) generic = 1;
+            if (ty == RT_PRIM_MEDIUM) {
+                if (i >= n) return fail(ctx, RT_ERR_ARG, "a medium cannot bound a medium");
+                if (!x->prim_aux) return fail(ctx, RT_ERR_ARG, "prim_aux missing");
+                const int first = x->prim_aux[2 * i], count = x->prim_aux[2 * i + 1];
+                if (first < n || count < 1 || first + count > n_total) return fail(ctx, RT_ERR_ARG, "medium boundary out of range");
+                if (!(x->prim_params[12 * (size_t)i] > 0.f)) return fail(ctx, RT_ERR_ARG, "medium density must be positive");
+            }
+        }
+        for (int q = 0; q < x->n_xforms * RT_XFORM_MAX_OPS; ++q)
+            if (x->xform_ops[q] < RT_XOP_NONE || x->xform_ops[q] > RT_XOP_FLIP) return fail(ctx, RT_ERR_UNSUPPORTED, "unknown transform op");
+    } else if (nb > 0) {
+        return fail(ctx, RT_ERR_ARG, "boundary primitives without a primitive table");
+    }
+    auto ptype = [&](int i) { return (x && x->prim_type) ? x->prim_type[i] : RT_PRIM_SPHERE; };
     double win_lo = INFINITY, win_hi = -INFINITY;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n_total; ++i) {
         unsigned fl = s->sphere_flags ? s->sphere_flags[i] : 0u;
+        if (ptype(i) != RT_PRIM_SPHERE) fl = 0u;
         bool moving = (fl & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
         if (fl & ~(RT_SPHERE_UV | RT_SPHERE_MOVING)) return fail(ctx, RT_ERR_UNSUPPORTED, "unknown sphere flag");
-        if (s->material_id[i] < 0 || s->material_id[i] >= nm_) return fail(ctx, RT_ERR_ARG, "material id out of range");
+        if (i < n && (s->material_id[i] < 0 || s->material_id[i] >= nm_)) return fail(ctx, RT_ERR_ARG, "material id out of range");
         if (moving) {
             double t0 = s->t0t1[2 * i], t1 = s->t0t1[2 * i + 1];
             if (!(t1 != t0)) return fail(ctx, RT_ERR_ARG, "moving sphere with t1 == t0");
@@ -729,8 +886,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     {
         std::vector<char> direct((size_t)n, 0);
         double direct_centroid[3] = {0, 0, 0};
-        static const int direct_env = env_int("RT_DIRECT_SPHERES", 1);
-        if (n > 16 && direct_env) {
+        if (n > 16 && ctx->opt.direct_spheres && !generic) {
             std::vector<double> radii((size_t)n);
             for (int i = 0; i < n; ++i) radii[(size_t)i] = std::fabs((double)s->center0_r[4 * i + 3]);
             std::vector<double> sorted = radii;
@@ -748,7 +904,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
             for (int i = 0; i < n; ++i) {
                 if (radii[(size_t)i] < big) continue;
                 double d2 = 0.0;
-                for (int c = 0; c < 3; ++c) { double x = s->center0_r[4 * i + c] - cen[c]; d2 += x * x; }
+                for (int c = 0; c < 3; ++c) { double xx = s->center0_r[4 * i + c] - cen[c]; d2 += xx * xx; }
                 if (std::sqrt(d2) <= 1.05 * radii[(size_t)i]) cand.emplace_back(-radii[(size_t)i], i);
             }
             std::sort(cand.begin(), cand.end());
@@ -762,7 +918,7 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         for (int i = 0; i < n; ++i)
             if (direct[(size_t)i]) {
                 double d2 = 0.0;
-                for (int c = 0; c < 3; ++c) { double x = s->center0_r[4 * i + c] - direct_centroid[c]; d2 += x * x; }
+                for (int c = 0; c < 3; ++c) { double xx = s->center0_r[4 * i + c] - direct_centroid[c]; d2 += xx * xx; }
                 order.emplace_back(-std::sqrt(d2) / std::max(1e-30, std::fabs((double)s->center0_r[4 * i + 3])), i);
             }
         std::sort(order.begin(), order.end());
@@ -770,50 +926,100 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
     }
     const int n_list = n - n_direct;
     const int n_cull = (int)align_up((size_t)n_list, CULL_PAD);
+    // source index of entry k of the device arrays: world leaves in cull order, then the boundary leaves as given
+    auto src = [&](int k) { return k < n ? perm[(size_t)k] : k; };
 
     // host copy of the geometry (cull order): the cull records are rebuilt when the time window has to grow
-    ctx->h_c0r.assign(4 * (size_t)n, 0.f);
-    ctx->h_c1.assign(4 * (size_t)n, 0.f);
-    ctx->h_t0t1.assign(2 * (size_t)n, 0.f);
-    ctx->h_flags.assign((size_t)n, 0u);
-    std::vector<int> h_mat((size_t)n);
-    for (int k = 0; k < n; ++k) {
-        const int i = perm[(size_t)k];
-        unsigned fl = s->sphere_flags ? s->sphere_flags[i] : 0u;
+    ctx->h_c0r.assign(4 * (size_t)n_total, 0.f);
+    ctx->h_c1.assign(4 * (size_t)n_total, 0.f);
+    ctx->h_t0t1.assign(2 * (size_t)n_total, 0.f);
+    ctx->h_flags.assign((size_t)n_total, 0u);
+    ctx->h_bs_c0.assign(3 * (size_t)n, 0.0);
+    ctx->h_bs_c1.assign(3 * (size_t)n, 0.0);
+    ctx->h_bs_r.assign((size_t)n, 0.0);
+    std::vector<int> h_mat((size_t)n_total, 0);
+    for (int k = 0; k < n_total; ++k) {
+        const int i = src(k);
+        unsigned fl = (s->sphere_flags && ptype(i) == RT_PRIM_SPHERE) ? s->sphere_flags[i] : 0u;
         bool moving = (fl & RT_SPHERE_MOVING) && s->center1 && s->t0t1;
         ctx->h_flags[k] = moving ? fl : (fl & ~RT_SPHERE_MOVING);
         for (int c = 0; c < 4; ++c) ctx->h_c0r[4 * k + c] = s->center0_r[4 * i + c];
         for (int c = 0; c < 3; ++c) ctx->h_c1[4 * k + c] = moving ? s->center1[4 * i + c] : s->center0_r[4 * i + c];
         ctx->h_t0t1[2 * k] = moving ? s->t0t1[2 * i] : 0.f;
         ctx->h_t0t1[2 * k + 1] = moving ? s->t0t1[2 * i + 1] : 1.f;
-        h_mat[(size_t)k] = s->material_id[i];
+        h_mat[(size_t)k] = k < n ? s->material_id[i] : 0;
+    }
+    // world-space bounding spheres of the world leaves (what the FP32 cull tests)
+    for (int k = 0; k < n; ++k) {
+        const int i = src(k);
+        double c0[3], c1[3], r = 0.0;
+        if (ptype(i) == RT_PRIM_MEDIUM) {
+            // the sphere around its boundary leaves, each carried out of its own wrappers, then out of the medium's
+            const int first = x->prim_aux[2 * i], count = x->prim_aux[2 * i + 1];
+            std::vector<double> cs((size_t)count * 3), rs((size_t)count);
+            double cen[3] = {0, 0, 0};
+            for (int b = 0; b < count; ++b) {
+                double b0[3], b1[3], br;
+                leaf_bounds(s, x, first + b, b0, b1, &br);
+                const int bxf = x->prim_xform ? x->prim_xform[first + b] : -1;
+                xform_point_back(x, bxf, b0);
+                xform_point_back(x, bxf, b1);
+                double half = 0.0;
+                for (int c = 0; c < 3; ++c) { cs[3 * (size_t)b + c] = 0.5 * (b0[c] + b1[c]); half += 0.25 * (b1[c] - b0[c]) * (b1[c] - b0[c]); cen[c] += cs[3 * (size_t)b + c] / count; }
+                rs[(size_t)b] = br + std::sqrt(half);
+            }
+            for (int b = 0; b < count; ++b) {
+                double d2 = 0.0;
+                for (int c = 0; c < 3; ++c) d2 += (cs[3 * (size_t)b + c] - cen[c]) * (cs[3 * (size_t)b + c] - cen[c]);
+                r = std::max(r, std::sqrt(d2) + rs[(size_t)b]);
+            }
+            for (int c = 0; c < 3; ++c) c0[c] = c1[c] = cen[c];
+            r = r * (1.0 + 1e-6) + 1e-6;
+        } else {
+            leaf_bounds(s, x, i, c0, c1, &r);
+        }
+        const int xf = (x && x->prim_xform) ? x->prim_xform[i] : -1;
+        if (xf >= 0) { xform_point_back(x, xf, c0); xform_point_back(x, xf, c1); r = r * (1.0 + 1e-6) + 1e-6 * (1.0 + std::fabs(c0[0]) + std::fabs(c0[1]) + std::fabs(c0[2])); }
+        for (int c = 0; c < 3; ++c) { ctx->h_bs_c0[3 * (size_t)k + c] = c0[c]; ctx->h_bs_c1[3 * (size_t)k + c] = c1[c]; }
+        ctx->h_bs_r[(size_t)k] = r;
     }
     ctx->n_list = n_list;
     ctx->n_cull = n_cull;
     ctx->n_spheres = n;
+    ctx->n_total = n_total;
+    ctx->generic = generic;
 
     // blob layout
     size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + std::max<size_t>(bytes, 16), 256); return o; };
     size_t o_cull_a = take((size_t)(n_cull + n_direct) * 16);
-    size_t o_c0r = take((size_t)n * 16), o_c1 = take((size_t)n * 16), o_t0t1 = take((size_t)n * 8);
-    size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n * 4), o_mat = take((size_t)n * 4);
+    size_t o_c0r = take((size_t)n_total * 16), o_c1 = take((size_t)n_total * 16), o_t0t1 = take((size_t)n_total * 8);
+    size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n_total * 4), o_mat = take((size_t)n_total * 4);
     size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);
-    size_t o_srec = take((size_t)n * 16), o_scol = take((size_t)n * 16);
+    size_t o_srec = take((size_t)n * 16), o_scol = take((size_t)n * 16), o_tie = take((size_t)n * 4);
     size_t o_ttype = take((size_t)std::max(nt, 1) * 4), o_tparam = take((size_t)std::max(nt, 1) * 48), o_tchild = take((size_t)std::max(nt, 1) * 8);
+    const int nxf = x ? std::max(0, x->n_xforms) : 0;
+    size_t o_ptype = take((size_t)n_total * 4), o_pq = take((size_t)n_total * 48), o_paux = take((size_t)n_total * 8), o_pxf = take((size_t)n_total * 4);
+    size_t o_xops = take((size_t)nxf * RT_XFORM_MAX_OPS * 4), o_xp = take((size_t)nxf * RT_XFORM_MAX_OPS * 16);
+    size_t o_pvec = take(uses_perlin ? 256 * 16 : 0), o_pperm = take(uses_perlin ? 768 * 4 : 0);
+    const int n_img = x ? std::max(0, x->n_images) : 0;
+    size_t img_bytes = 0;
+    for (int i = 0; i < n_img; ++i) img_bytes = std::max(img_bytes, (size_t)x->image_offset[i] + (size_t)x->image_wh[2 * i] * x->image_wh[2 * i + 1] * 3);
+    size_t o_iwh = take((size_t)n_img * 8), o_ioff = take((size_t)n_img * 8), o_irgb = take(img_bytes);
     std::vector<unsigned char> blob(off, 0);
     build_cull_records(ctx, win_lo, win_hi, (float*)(blob.data() + o_cull_a));
-    memcpy(blob.data() + o_c0r, ctx->h_c0r.data(), (size_t)n * 16);
-    memcpy(blob.data() + o_c1, ctx->h_c1.data(), (size_t)n * 16);
-    memcpy(blob.data() + o_t0t1, ctx->h_t0t1.data(), (size_t)n * 8);
-    memcpy(blob.data() + o_flags, ctx->h_flags.data(), (size_t)n * 4);
+    memcpy(blob.data() + o_c0r, ctx->h_c0r.data(), (size_t)n_total * 16);
+    memcpy(blob.data() + o_c1, ctx->h_c1.data(), (size_t)n_total * 16);
+    memcpy(blob.data() + o_t0t1, ctx->h_t0t1.data(), (size_t)n_total * 8);
+    memcpy(blob.data() + o_flags, ctx->h_flags.data(), (size_t)n_total * 4);
     int* orig = (int*)(blob.data() + o_orig);
     int* cull_of = (int*)(blob.data() + o_cull_of);
     for (int k = 0; k < n; ++k) { orig[k] = perm[(size_t)k]; cull_of[perm[(size_t)k]] = k; }
-    memcpy(blob.data() + o_mat, h_mat.data(), (size_t)n * 4);
-    {   // per-sphere shading records: material and (constant) texture resolved once, here
+    memcpy(blob.data() + o_mat, h_mat.data(), (size_t)n_total * 4);
+    {   // per-leaf shading records (material and constant texture resolved once, here) and tie-break keys
         int* srec = (int*)(blob.data() + o_srec);
         float* scol = (float*)(blob.data() + o_scol);
+        unsigned* tie = (unsigned*)(blob.data() + o_tie);
         for (int k = 0; k < n; ++k) {
             const int m = h_mat[(size_t)k], tex = s->mat_tex[m];
             const bool has_tex = s->mat_type[m] != RT_MAT_DIELECTRIC && tex >= 0 && tex < nt;
@@ -824,6 +1030,12 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
             srec[4 * k + 3] = (int)ctx->h_flags[(size_t)k];
             scol[4 * k + 0] = s->mat_param[m];
             for (int c = 0; c < 3; ++c) scol[4 * k + 1 + c] = tex_type == RT_TEX_CONSTANT ? s->tex_params[12 * tex + c] : 0.f;
+            // exact ties in t (coincident geometry): the smallest key wins.  Hitlist world (hitable.clj:17-26): the first
+            // strict-range leaf (sphere) in caller order, but a later inclusive-range leaf (rectangle / triangle / medium)
+            // replaces an equal earlier hit; bvh-node world (hitable.clj:99-105, right child wins): the last leaf.
+            const unsigned o_ = (unsigned)perm[(size_t)k];
+            const bool strict = ptype(perm[(size_t)k]) == RT_PRIM_SPHERE;
+            tie[k] = (tie_rule == RT_TIE_HITLIST && strict) ? (0x80000000u | o_) : (0x7fffffffu - o_);
         }
     }
     memcpy(blob.data() + o_mtype, s->mat_type, (size_t)nm_ * 4);
@@ -834,16 +1046,52 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         memcpy(blob.data() + o_tparam, s->tex_params, (size_t)nt * 48);
         memcpy(blob.data() + o_tchild, s->tex_children, (size_t)nt * 8);
     }
+    if (generic) {
+        int* pt = (int*)(blob.data() + o_ptype);
+        float* pq = (float*)(blob.data() + o_pq);
+        int* pa = (int*)(blob.data() + o_paux);
+        int* pxf = (int*)(blob.data() + o_pxf);
+        for (int k = 0; k < n_total; ++k) {
+            const int i = src(k);
+            pt[k] = ptype(i);
+            if (x && x->prim_params) memcpy(pq + 12 * (size_t)k, x->prim_params + 12 * (size_t)i, 48);
+            if (x && x->prim_aux) { pa[2 * k] = x->prim_aux[2 * i]; pa[2 * k + 1] = x->prim_aux[2 * i + 1]; }
+            pxf[k] = (x && x->prim_xform) ? x->prim_xform[i] : -1;
+        }
+        if (nxf) {
+            memcpy(blob.data() + o_xops, x->xform_ops, (size_t)nxf * RT_XFORM_MAX_OPS * 4);
+            memcpy(blob.data() + o_xp, x->xform_params, (size_t)nxf * RT_XFORM_MAX_OPS * 16);
+        }
+    }
+    if (uses_perlin) {
+        float* pv = (float*)(blob.data() + o_pvec);
+        for (int i = 0; i < 256; ++i)
+            for (int c = 0; c < 3; ++c) pv[4 * i + c] = x->perlin_vectors[3 * i + c];
+        memcpy(blob.data() + o_pperm, x->perlin_perm, 768 * 4);
+    }
+    if (n_img) {
+        memcpy(blob.data() + o_iwh, x->image_wh, (size_t)n_img * 8);
+        memcpy(blob.data() + o_ioff, x->image_offset, (size_t)n_img * 8);
+        memcpy(blob.data() + o_irgb, x->image_rgb, img_bytes);
+    }
     for (auto& d : ctx->devs) {
         RT_CUDA(ctx, cudaSetDevice(d.dev));
-        RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
-        if (d.scene_blob) cudaFree(d.scene_blob);
-        d.scene_blob = nullptr;
-        RT_CUDA(ctx, cudaMalloc(&d.scene_blob, blob.size()));
-        RT_CUDA(ctx, cudaMemcpyAsync(d.scene_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, d.stream));
+        RT_CUDA(ctx, cudaDeviceSynchronize());   // renders enqueued with sync = 0 on a caller's stream may still read the old scene
+        if (d.scene_bytes < blob.size()) {       // the blob (and its pinned staging copy) is reused by the next upload
+            if (d.scene_blob) cudaFree(d.scene_blob);
+            if (d.scene_stage) cudaFreeHost(d.scene_stage);
+            d.scene_blob = nullptr; d.scene_stage = nullptr; d.scene_bytes = 0;
+            const size_t cap = align_up(blob.size() + blob.size() / 4, 4096);
+            RT_CUDA(ctx, cudaMalloc(&d.scene_blob, cap));
+            RT_CUDA(ctx, cudaHostAlloc(&d.scene_stage, cap, cudaHostAllocDefault));
+            d.scene_bytes = cap;
+        }
+        memcpy(d.scene_stage, blob.data(), blob.size());
+        RT_CUDA(ctx, cudaMemcpyAsync(d.scene_blob, d.scene_stage, blob.size(), cudaMemcpyHostToDevice, d.stream));
         RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
         char* b = (char*)d.scene_blob;
         DevScene& sc = d.sc;
+        sc = DevScene{};
         sc.n = n;
         sc.n_list = n_list;
         sc.n_cull = n_cull;
@@ -854,17 +1102,56 @@ int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) {
         sc.shade_rec = (const int4*)(b + o_srec); sc.shade_col = (const float4*)(b + o_scol);
         sc.mat_type = (const int*)(b + o_mtype); sc.mat_param = (const float*)(b + o_mparam); sc.mat_tex = (const int*)(b + o_mtex);
         sc.tex_type = (const int*)(b + o_ttype); sc.tex_params = (const float*)(b + o_tparam); sc.tex_child = (const int*)(b + o_tchild);
+        sc.generic = generic;
+        sc.n_total = n_total;
+        sc.tie_hi = (const unsigned*)(b + o_tie);
+        sc.prim_type = (const int*)(b + o_ptype); sc.prim_q = (const float4*)(b + o_pq); sc.prim_aux = (const int2*)(b + o_paux);
+        sc.prim_xform = (const int*)(b + o_pxf); sc.xform_ops = (const int*)(b + o_xops); sc.xform_p = (const float4*)(b + o_xp);
+        sc.perlin_vec = (const float4*)(b + o_pvec); sc.perlin_perm = (const int*)(b + o_pperm);
+        sc.image_wh = (const int2*)(b + o_iwh); sc.image_off = (const long long*)(b + o_ioff); sc.image_rgb = (const unsigned char*)(b + o_irgb);
     }
     cudaSetDevice(ctx->devs[0].dev);
-    ctx->n_spheres = n;
-    // resident up to kTileCap records; beyond that the list is streamed through a smaller tile (RT_TILE_RECORDS,
+    // resident up to kTileCap records; beyond that the list is streamed through a smaller tile (tile_records,
     // a multiple of 512) so that several CTAs still fit on an SM
-    static const int tile_records = std::max(CHUNK, std::min(kTileCap, env_int("RT_TILE_RECORDS", 1024) / CHUNK * CHUNK));
+    const int tile_records = std::max(CHUNK, std::min(kTileCap, ctx->opt.tile_records / CHUNK * CHUNK));
     ctx->preloaded = n_cull <= kTileCap ? 1 : 0;
     ctx->cull_cap = ctx->preloaded ? std::max(n_cull, CULL_PAD) : tile_records;
     ctx->win_lo = win_lo;
     ctx->win_hi = win_hi;
     ctx->has_scene = true;
+    return RT_OK;
+}
+
+int rt_set_scene(rt_ctx* ctx, const rt_scene_desc* s) { return rt_set_scene_ex(ctx, s, nullptr); }
+
+int rt_set_accel(rt_ctx* ctx, int accel) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (accel != RT_ACCEL_BRUTE_FORCE && accel != RT_ACCEL_BVH) return fail(ctx, RT_ERR_ARG, "unknown accelerator");
+    ctx->accel = accel;
+    return RT_OK;
+}
+
+int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!name) return fail(ctx, RT_ERR_ARG, "option name is null");
+    Options& o = ctx->opt;
+    const std::string k(name);
+    if (k == "wave_lanes") o.wave_lanes = (int)value;
+    else if (k == "wave_capacity") o.wave_capacity = value;
+    else if (k == "cull_claims") o.cull_claims = (int)value;
+    else if (k == "cull_ctas_per_sm") o.cull_ctas_per_sm = (int)value;
+    else if (k == "cull_shape") o.cull_shape = (int)value;
+    else if (k == "light_block") o.light_block = (int)value;
+    else if (k == "tail_entries") o.tail_entries = value;
+    else if (k == "tail_ctas_per_sm") o.tail_ctas_per_sm = (int)value;
+    else if (k == "tile_records") o.tile_records = (int)value;   // takes effect at the next rt_set_scene
+    else if (k == "direct_spheres") o.direct_spheres = (int)value;   // takes effect at the next rt_set_scene
+    else if (k == "common_origin") o.common_origin = (int)value;
+    else if (k == "reduce") o.reduce = (int)value;
+    else if (k == "rows") o.rows = (int)value;
+    else return fail(ctx, RT_ERR_ARG, "unknown option: " + k);
     return RT_OK;
 }
 
@@ -958,8 +1245,14 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
         std::vector<std::thread> workers;
         for (int g = 0; g < G; ++g) workers.emplace_back([&, g] { rcs[(size_t)g] = device_work(g); });
         for (auto& w : workers) w.join();
+        int bad = RT_OK;
         for (int g = 0; g < G; ++g)
-            if (rcs[(size_t)g]) return rcs[(size_t)g];
+            if (rcs[(size_t)g] && !bad) bad = rcs[(size_t)g];
+        if (bad) {   // the other devices may still be rendering into buffers the next call reuses: drain them first
+            for (auto& dv : ctx->devs) { cudaSetDevice(dv.dev); cudaDeviceSynchronize(); }
+            cudaSetDevice(ctx->devs[0].dev);
+            return bad;
+        }
     }
     // combine on the root device: the resolve kernel reads the peers' sums over NVLink
     DeviceBuffers& root = ctx->devs[0];
@@ -997,6 +1290,81 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
     return RT_OK;
 }
 
+int rt_trace_paths(rt_ctx* ctx, int nx, int ny, int n, const int32_t* pixel, const int32_t* sample, int max_depth, uint64_t seed,
+                   int variant, float* out_radiance, int32_t* out_nrays, int32_t* out_term, int log_bounces, rt_path_bounce* out_log) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = check_camera_times(ctx))) return rc;
+    if (nx <= 0 || ny <= 0 || n < 0 || max_depth < 0 || log_bounces < 0 || (n > 0 && (!pixel || !sample || !out_radiance || !out_nrays || !out_term)) ||
+        (log_bounces > 0 && n > 0 && !out_log))
+        return fail(ctx, RT_ERR_ARG, "bad trace_paths arguments");
+    if ((long long)nx * ny > 0x7fffffffLL / 3) return fail(ctx, RT_ERR_ARG, "image too large");
+    if (n == 0) return RT_OK;
+    for (int q = 0; q < n; ++q)
+        if (pixel[q] < 0 || pixel[q] >= nx * ny || sample[q] < 0 || sample[q] >= (1 << 24))
+            return fail(ctx, RT_ERR_ARG, "pixel / sample index out of range");
+    static_assert(sizeof(rt_path_bounce) == sizeof(PathBounce) && sizeof(PathBounce) == 40, "rt_path_bounce layout");
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    const size_t b_i = align_up((size_t)n * 4, 256), b_f = align_up((size_t)n * 12, 256), b_l = align_up((size_t)n * log_bounces * sizeof(PathBounce), 256);
+    char* buf = nullptr;   // its own allocation: the render below may grow the context's scratch
+    RT_CUDA(ctx, cudaMalloc(&buf, 4 * b_i + b_f + b_l + 256));
+    int* d_pix = (int*)buf;
+    int* d_smp = (int*)(buf + b_i);
+    int* d_nr = (int*)(buf + 2 * b_i);
+    int* d_term = (int*)(buf + 3 * b_i);
+    float* d_rad = (float*)(buf + 4 * b_i);
+    PathBounce* d_log = log_bounces > 0 ? (PathBounce*)(buf + 4 * b_i + b_f) : nullptr;
+    auto cleanup = [&](int code) { cudaStreamSynchronize(d.stream); cudaFree(buf); return code; };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_pix, pixel, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_smp, sample, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(d_nr, 0, 2 * b_i + b_f, d.stream)) != cudaSuccess ||
+        (d_log && (e = cudaMemsetAsync(d_log, 0xff, (size_t)n * log_bounces * sizeof(PathBounce), d.stream)) != cudaSuccess))
+        return cleanup(fail(ctx, RT_ERR_CUDA, std::string("trace_paths upload: ") + cudaGetErrorString(e)));
+    RenderParams P{};
+    P.nx = nx; P.ny = ny;
+    P.sample_begin = 0; P.sample_count = 1;
+    P.row_offset = 0; P.row_stride = 1; P.rows_in_shard = ny;
+    P.max_depth = max_depth;
+    P.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    P.sum = d_rad;
+    P.total_work = (unsigned long long)n;
+    P.path_pixel = d_pix; P.path_sample = d_smp; P.path_nrays = d_nr; P.path_term = d_term;
+    P.path_log = d_log; P.path_log_n = log_bounces;
+    if ((rc = launch_params(ctx, d, P, variant, d.stream))) return cleanup(rc);
+    if ((e = cudaMemcpyAsync(out_radiance, d_rad, (size_t)n * 12, cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(out_nrays, d_nr, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(out_term, d_term, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess ||
+        (d_log && (e = cudaMemcpyAsync(out_log, d_log, (size_t)n * log_bounces * sizeof(PathBounce), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess) ||
+        (e = cudaStreamSynchronize(d.stream)) != cudaSuccess)
+        return cleanup(fail(ctx, RT_ERR_CUDA, std::string("trace_paths: ") + cudaGetErrorString(e)));
+    // a logged slot that was never written (0xff fill) = the path had ended before that bounce
+    if (out_log)
+        for (size_t q = 0; q < (size_t)n * log_bounces; ++q)
+            if (out_log[q].hit_id == -1 && std::isnan(out_log[q].t)) { memset(&out_log[q], 0, sizeof(rt_path_bounce)); out_log[q].hit_id = -2; }
+    d.timed = false;
+    return cleanup(RT_OK);
+}
+
+int rt_sample_device(rt_ctx* ctx, int kind, int n, uint64_t seed, float* out) {
+    if (!ctx) return RT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((kind != 0 && kind != 1) || n < 0 || (n > 0 && !out)) return fail(ctx, RT_ERR_ARG, "bad sample_device arguments");
+    if (n == 0) return RT_OK;
+    DeviceBuffers& d = ctx->devs[0];
+    RT_CUDA(ctx, cudaSetDevice(d.dev));
+    const int dim = kind == 0 ? 3 : 2;
+    int rc;
+    if ((rc = ensure_scratch(ctx, d, (size_t)n * dim * 4))) return rc;
+    sampler_kernel<<<(n + 255) / 256, 256, 0, d.stream>>>(kind, n, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), (float*)d.scratch);
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaMemcpyAsync(out, d.scratch, (size_t)n * dim * 4, cudaMemcpyDeviceToHost, d.stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return RT_OK;
+}
+
 int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs, const float* times, double tmin,
                      double tmax, double* out_t, int32_t* out_id) {
     int rc = check_ready(ctx);
@@ -1029,7 +1397,7 @@ int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs
     TraceParams P{};
     P.sc = d.sc; P.n = n; P.origins = d_o; P.dirs = d_d; P.times = times ? d_tm : nullptr;
     P.tmin = tmin; P.tmax = tmax; P.out_t = d_t; P.out_id = d_id; P.cull_cap = ctx->cull_cap; P.preloaded = ctx->preloaded;
-    auto kern = trace_kernel<kR, kBlock>;
+    void (*kern)(const TraceParams) = ctx->generic ? trace_kernel<kR, kBlock, true> : trace_kernel<kR, kBlock, false>;
     size_t smem = mega_smem_bytes(ctx->cull_cap);
     int bps = 0;
     if ((rc = configure_kernel(ctx, kern, smem, &bps))) return rc;
@@ -1238,6 +1606,7 @@ int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]) {
     out[RT_CTR_TERM_MISS] = total[DC_TERM_MISS];
     out[RT_CTR_KERNEL_NS] = (uint64_t)((double)max_ms * 1e6);
     out[RT_CTR_CANDIDATES] = total[DC_CANDIDATES];
+    out[RT_CTR_DIRECT_TESTS] = total[DC_DIRECT];
     out[RT_CTR_KERNEL_LAUNCHES] = ctx->n_launches.load();
     out[RT_CTR_CULL_NS] = (uint64_t)(ctx->stage_ms[0] * 1e6);
     out[RT_CTR_REFINE_NS] = (uint64_t)(ctx->stage_ms[1] * 1e6);

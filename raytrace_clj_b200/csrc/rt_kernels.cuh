@@ -22,6 +22,15 @@ namespace rt {
 
 #define RT_FOR_R _Pragma("unroll") for (int r = 0; r < R; ++r)
 
+// one logged ray of rt_trace_paths (= rt_path_bounce of the C ABI)
+struct PathBounce {
+    float o[3];
+    float time;
+    float d[3];
+    int hit_id;
+    double t;
+};
+
 struct RenderParams {
     DevScene sc;
     DevCamera cam;
@@ -37,7 +46,50 @@ struct RenderParams {
     int cull_cap;                         // float4 slots of the shared-memory sphere tile
     int preloaded;                        // 1: whole scene fits one tile (loaded once per CTA)
     int common_origin;                    // 1: every camera ray starts at cam.origin (pinhole, or aperture 0)
+    // rt_trace_paths: work item w IS path w of a caller-given list instead of the w-th (sample, pixel) of the frame;
+    // the queue record's "pixel" field then holds w, `sum` has 3 floats per PATH, and the path's counters / bounce log
+    // are kept per path.  All null / 0 in a render.
+    const int* path_pixel;                // [total_work] j * nx + i
+    const int* path_sample;               // [total_work]
+    int* path_nrays;                      // [total_work]
+    int* path_term;                       // [total_work]
+    PathBounce* path_log;                 // [total_work * path_log_n] or null
+    int path_log_n;
 };
+
+// the Philox "pixel" of the path whose queue record carries `slot` in its pixel field
+__device__ __forceinline__ uint32_t rng_pixel(const RenderParams& P, uint32_t slot) {
+    return P.path_pixel ? (uint32_t)__ldg(&P.path_pixel[slot]) : slot;
+}
+// rt_trace_paths bookkeeping for ray number `ray_no` (0-based) of path `slot`
+__device__ __forceinline__ void path_log_ray(const RenderParams& P, uint32_t slot, int ray_no, float4 a, float4 b, int k, double t) {
+    if (P.path_log && ray_no < P.path_log_n) {
+        PathBounce& L = P.path_log[(size_t)slot * P.path_log_n + ray_no];
+        L.o[0] = a.x; L.o[1] = a.y; L.o[2] = a.z; L.time = a.w;
+        L.d[0] = b.x; L.d[1] = b.y; L.d[2] = b.z;
+        L.hit_id = k < 0 ? -1 : __ldg(&P.sc.orig_id[k]);
+        L.t = t;
+    }
+}
+__device__ __forceinline__ void path_log_end(const RenderParams& P, uint32_t slot, int n_rays, int reason) {
+    if (P.path_nrays) {
+        P.path_nrays[slot] = n_rays;
+        P.path_term[slot] = reason;
+    }
+}
+
+// exact test of (ray, leaf k): the sphere formula, or the generic leaves of a scene marshalled through rt_set_scene_ex.
+// path context (for the `rand` of a ConstantMedium): Philox key / pixel / sample / bounce, or has_ctx = false (u = 0.5).
+template <bool GEN>
+__device__ __forceinline__ double refine_leaf(const DevScene* sc, int k, float ox, float oy, float oz, float dx, float dy, float dz,
+                                              float time, double tmin, double tmax, bool has_ctx, uint2 key, uint32_t pixel,
+                                              uint32_t sample, uint32_t bounce) {
+    if (!GEN)
+        return refine_candidate(sc->ex_c0r, sc->ex_c1, sc->ex_t0t1, sc->flags, k, ox, oy, oz, dx, dy, dz, time, tmin, tmax);
+    float mu = 0.5f;
+    if (has_ctx && __ldg(&sc->prim_type[k]) == PRIM_MEDIUM) mu = medium_uniform(key, pixel, sample, bounce, __ldg(&sc->orig_id[k]));
+    return refine_generic(sc, k, ox, oy, oz, dx, dy, dz, time, tmin, tmax, mu);
+}
 
 // ------------------------------------------------------------------------------------------
 // Culler: the FP32 test, per (ray, sphere), 9 FP32-pipe instructions (8 FFMA + 1 FADD) + 1 funnel shift.  The 17-flop
@@ -278,42 +330,51 @@ struct SurvivorIter {
 // registers (trace kernel, megakernel).  It owns the rays as given (origin, un-normalised
 // direction, time); the Culler only holds what the FP32 test needs.
 // ------------------------------------------------------------------------------------------
-template <int R, int BLOCK>
+template <int R, int BLOCK, bool GEN = false>
 struct RefineSink {
     float ox[R], oy[R], oz[R];     // origin
     float dx[R], dy[R], dz[R];     // direction as given (un-normalised, util.clj:13-16)
     float tm[R];                   // ray time
     double best_t[R];
-    int best_k[R], best_orig[R];
+    int best_k[R];
+    unsigned best_tie[R];          // DevScene::tie_hi of the running winner
     unsigned ncand;
     double tmin, tmax;
     const DevScene* sc;
+    // path context of the rays (megakernel): what a ConstantMedium needs for its `rand`; has_ctx = false in rt_trace_primary
+    bool has_ctx;
+    uint2 key;
+    uint32_t pix[R], smp[R], bounce[R];
 
     __device__ __forceinline__ void begin() {
         RT_FOR_R {
             best_t[r] = CUDART_INF;
             best_k[r] = -1;
-            best_orig[r] = 0x7fffffff;
+            best_tie[r] = 0xffffffffu;
         }
     }
 
-    // exact test of (ray r, sphere k): closest t wins, exact ties go to the lower caller index (hitable.clj:17-26)
+    // exact test of (ray r, leaf k): closest t wins, exact ties by DevScene::tie_hi (hitable.clj:17-26 / :99-105)
     __device__ __forceinline__ void refine(int r, int k) {
         float sox = ox[0], soy = oy[0], soz = oz[0], sdx = dx[0], sdy = dy[0], sdz = dz[0], stm = tm[0];
+        uint32_t spix = 0, ssmp = 0, sb = 0;
+        if (has_ctx) { spix = pix[0]; ssmp = smp[0]; sb = bounce[0]; }
 #pragma unroll
         for (int q = 1; q < R; ++q)
-            if (r == q) { sox = ox[q]; soy = oy[q]; soz = oz[q]; sdx = dx[q]; sdy = dy[q]; sdz = dz[q]; stm = tm[q]; }
-        const double t = refine_candidate(sc->ex_c0r, sc->ex_c1, sc->ex_t0t1, sc->flags, k, sox, soy, soz, sdx, sdy, sdz, stm,
-                                          tmin, tmax);
+            if (r == q) {
+                sox = ox[q]; soy = oy[q]; soz = oz[q]; sdx = dx[q]; sdy = dy[q]; sdz = dz[q]; stm = tm[q];
+                if (has_ctx) { spix = pix[q]; ssmp = smp[q]; sb = bounce[q]; }
+            }
+        const double t = refine_leaf<GEN>(sc, k, sox, soy, soz, sdx, sdy, sdz, stm, tmin, tmax, has_ctx, key, spix, ssmp, sb);
         ncand++;
         if (t < CUDART_INF) {
-            const int orig = __ldg(&sc->orig_id[k]);
+            const unsigned tie = __ldg(&sc->tie_hi[k]);
 #pragma unroll
             for (int q = 0; q < R; ++q)
-                if (r == q && (t < best_t[q] || (t == best_t[q] && orig < best_orig[q]))) {
+                if (r == q && (t < best_t[q] || (t == best_t[q] && tie < best_tie[q]))) {
                     best_t[q] = t;
                     best_k[q] = k;
-                    best_orig[q] = orig;
+                    best_tie[q] = tie;
                 }
         }
     }
@@ -326,10 +387,13 @@ struct RefineSink {
     }
 
     // the spheres that bypass the cull (DevScene::n_list .. n): tested directly for the rays in `live` (bit r)
-    __device__ __forceinline__ void direct(unsigned live) {
+    __device__ __forceinline__ unsigned direct(unsigned live) {
+        unsigned nd = 0;
         for (int k = sc->n_list; k < sc->n; ++k)
             for (int r = 0; r < R; ++r)
-                if ((live >> r) & 1u) refine(r, k);
+                if ((live >> r) & 1u) { refine(r, k); ++nd; }
+        ncand -= nd;
+        return nd;
     }
 };
 
@@ -458,11 +522,19 @@ __device__ __forceinline__ void make_path(const RenderParams& P, unsigned long l
     int j = P.row_offset + row_local * P.row_stride;
     uint32_t pix = (uint32_t)j * (uint32_t)P.nx + (uint32_t)i;
     uint32_t smp = (uint32_t)(P.sample_begin + (int)s_local);
+    uint32_t slot = pix;
+    if (P.path_pixel) {                       // rt_trace_paths: work item w is path w of the caller's list
+        pix = (uint32_t)__ldg(&P.path_pixel[w]);
+        smp = (uint32_t)__ldg(&P.path_sample[w]);
+        j = (int)(pix / (uint32_t)P.nx);
+        i = (int)(pix - (uint32_t)j * (uint32_t)P.nx);
+        slot = (uint32_t)w;
+    }
     float3 o, d;
     float tmv;
     generate_ray(P.cam, P.nx, P.ny, i, j, pix, smp, P.key, o, d, tmv, nullptr);
     a = make_float4(o.x, o.y, o.z, tmv);
-    b = make_float4(d.x, d.y, d.z, __uint_as_float(pix));
+    b = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
     c = make_float4(1.f, 1.f, 1.f, __uint_as_float((smp << 8) | (uint32_t)P.max_depth));
 }
 
@@ -470,7 +542,7 @@ __device__ __forceinline__ void make_path(const RenderParams& P, unsigned long l
 // (the host has already advanced the shared work counter past every lane's first fill: wf_init)
 __global__ void wf_init(unsigned long long* work_counter, unsigned long long value) { *work_counter = value; }
 
-__global__ void __launch_bounds__(256) wf_generate(const WaveParams W, unsigned long long first, unsigned count) {
+__global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ WaveParams W, unsigned long long first, unsigned count) {
     TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     const unsigned e0 = P.common_origin ? (unsigned)W.capacity - count : 0u;   // camera rays: the common-origin region
@@ -659,7 +731,7 @@ __device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int
 }
 
 template <int R, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const WaveParams W) {
+__global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const __grid_constant__ WaveParams W) {
     TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
@@ -687,7 +759,9 @@ __device__ __forceinline__ unsigned wf_cand_region(const WaveParams& W, unsigned
     return ((W.pair_cap + total_warps * 32u - 1u) / (total_warps * 32u)) * 32u;   // pairs one warp can see
 }
 
-__device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, int cur) {
+// scp: the scene in the kernel's (grid-constant) parameter space — never the address of a local copy of the parameters
+template <bool GEN>
+__device__ __forceinline__ void wf_refine_body(const WaveParams& W, const DevScene* scp, Scope sc_, int cur) {
     const RenderParams& P = W.base;
     const unsigned npairs = min(W.st->npairs, W.pair_cap);
     const unsigned lane = threadIdx.x & 31u;
@@ -695,7 +769,7 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, i
         W.st->batch = 0;               // wf_cull is done with it
         W.st->cnt[cur ^ 1][0] = 0;     // wf_shade appends to both regions of the other queue next
         W.st->cnt[cur ^ 1][1] = 0;
-        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);   // + the direct spheres' exact tests, counted by wf_shade
+        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);   // the direct spheres' exact tests are counted apart (DC_DIRECT)
     }
     const unsigned total_warps = sc_.nblk * (blockDim.x >> 5);
     const unsigned warp_id = sc_.bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -716,8 +790,19 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, i
             const float4* qc = cur ? W.queue[1] : W.queue[0];
             const float4 a = qc[3 * (size_t)pr.x], b = qc[3 * (size_t)pr.x + 1];
             const unsigned long long seen = __ldcg(&W.best_t[pr.x]);
-            t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, (int)pr.y, a.x, a.y, a.z, b.x, b.y, b.z,
-                                 a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
+            if (!GEN) {
+                t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, (int)pr.y, a.x, a.y, a.z, b.x, b.y, b.z,
+                                     a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
+            } else {
+                uint32_t pixq = 0, smpq = 0, bq = 0;
+                if (__ldg(&P.sc.prim_type[pr.y]) == PRIM_MEDIUM) {   // its `rand` is keyed by the path (hitable.clj:529)
+                    const uint32_t sd = __float_as_uint(qc[3 * (size_t)pr.x + 2].w);
+                    pixq = rng_pixel(P, __float_as_uint(b.w));
+                    smpq = sd >> 8;
+                    bq = (uint32_t)(P.max_depth - (int)(sd & 255u) + 1);
+                }
+                t = refine_leaf<true>(scp, (int)pr.y, a.x, a.y, a.z, b.x, b.y, b.z, a.w, 0.001, (double)FLT_MAX, true, P.key, pixq, smpq, bq);
+            }
             const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
             if (t < CUDART_INF && tb <= seen) {
                 atomicMin(&W.best_t[pr.x], tb);
@@ -734,9 +819,10 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, Scope sc_, i
     }
     if (lane == 0) W.cand_count[warp_id] = cnt;
 }
-__global__ void __launch_bounds__(256) wf_refine(const WaveParams W) {
+template <bool GEN>
+__global__ void __launch_bounds__(256) wf_refine(const __grid_constant__ WaveParams W) {
     TraceScope trace(W.trace);
-    wf_refine_body(W, grid_scope(), W.cur);
+    wf_refine_body<GEN>(W, &W.base.sc, grid_scope(), W.cur);
 }
 
 // exact ties go to the lower caller index, the Hitlist rule (hitable.clj:17-26): candidates that own the final
@@ -751,25 +837,27 @@ __device__ __forceinline__ void wf_tiebreak_body(const WaveParams& W, Scope sc_)
     for (unsigned j = lane; j < cnt; j += 32) {
         const uint2 pr = W.cands[region + j];
         if ((unsigned long long)__double_as_longlong(W.cand_t[region + j]) == W.best_t[pr.x])
-            atomicMin(&W.best_key[pr.x], (((unsigned long long)(__ldg(&P.sc.orig_id[pr.y]) + 1)) << 32) | pr.y);
+            atomicMin(&W.best_key[pr.x], (((unsigned long long)__ldg(&P.sc.tie_hi[pr.y])) << 32) | pr.y);
     }
 }
-__global__ void __launch_bounds__(256) wf_tiebreak(const WaveParams W) {
+__global__ void __launch_bounds__(256) wf_tiebreak(const __grid_constant__ WaveParams W) {
     TraceScope trace(W.trace);
     wf_tiebreak_body(W, grid_scope());
 }
 
 // exact closest hit of one ray by brute force in FP64 (only for entries whose pairs overflowed the pair buffer)
-__device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, float oy, float oz, float dx, float dy, float dz,
-                                               float tm, double* out_t, int* out_k) {
+template <bool GEN>
+__device__ __noinline__ void exact_closest_hit(const DevScene* sc, float ox, float oy, float oz, float dx, float dy, float dz,
+                                               float tm, uint2 key, uint32_t pixel, uint32_t sample, uint32_t bounce, double* out_t,
+                                               int* out_k) {
     double best = CUDART_INF;
-    int bk = -1, borig = 0x7fffffff;
-    for (int k = 0; k < sc.n; ++k) {
-        double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, ox, oy, oz, dx, dy, dz, tm, 0.001,
-                                    (double)FLT_MAX);
+    int bk = -1;
+    unsigned btie = 0xffffffffu;
+    for (int k = 0; k < sc->n; ++k) {
+        double t = refine_leaf<GEN>(sc, k, ox, oy, oz, dx, dy, dz, tm, 0.001, (double)FLT_MAX, true, key, pixel, sample, bounce);
         if (t < CUDART_INF) {
-            int orig = __ldg(&sc.orig_id[k]);
-            if (t < best || (t == best && orig < borig)) { best = t; bk = k; borig = orig; }
+            unsigned tie = __ldg(&sc->tie_hi[k]);
+            if (t < best || (t == best && tie < btie)) { best = t; bk = k; btie = tie; }
         }
     }
     *out_t = best;
@@ -777,7 +865,8 @@ __device__ __noinline__ void exact_closest_hit(const DevScene sc, float ox, floa
 }
 
 // s_ctr: shared counters of the calling kernel (DC_COUNT slots, zeroed by the caller); returns samples generated
-__device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_, int cur, unsigned* s_ctr) {
+template <bool GEN>
+__device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, const DevScene* scp, Scope sc_, int cur, unsigned* s_ctr) {
     const RenderParams& P = W.base;
     const unsigned n_g = W.st->cnt[cur][0], n_p = W.st->cnt[cur][1], n = n_g + n_p;
     const unsigned lane = threadIdx.x & 31u;
@@ -800,13 +889,15 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_
         if (have) {
             a = qc[3 * (size_t)idx]; b = qc[3 * (size_t)idx + 1]; c = qc[3 * (size_t)idx + 2];
             unsigned long long key = W.best_key[idx];
-            const uint32_t pix = __float_as_uint(b.w), sd = __float_as_uint(c.w);
+            const uint32_t slot = __float_as_uint(b.w), sd = __float_as_uint(c.w);   // slot: the pixel (a render) / the path (rt_trace_paths)
+            const uint32_t pix = rng_pixel(P, slot);
             const uint32_t smp = sd >> 8;
             const int depth = (int)(sd & 255u);
+            const uint32_t bounce = (uint32_t)(P.max_depth - depth + 1);
             int k = (int)(unsigned)key;
             double td = __longlong_as_double((long long)W.best_t[idx]);
             if (key == BEST_KEY_OVERFLOW) {                 // overflow mark: exact brute force for this entry
-                exact_closest_hit(P.sc, a.x, a.y, a.z, b.x, b.y, b.z, a.w, &td, &k);
+                exact_closest_hit<GEN>(scp, a.x, a.y, a.z, b.x, b.y, b.z, a.w, P.key, pix, smp, bounce, &td, &k);
                 key = k < 0 ? BEST_KEY_MISS : 1ull;
             } else {
                 // the spheres that bypass the cull (enclosing spheres: the cull would pass them for nearly every
@@ -815,7 +906,7 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_
                     ++n_direct;
                     const double t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, kd, a.x, a.y, a.z, b.x,
                                                       b.y, b.z, a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
-                    const unsigned long long kk = (((unsigned long long)(__ldg(&P.sc.orig_id[kd]) + 1)) << 32) | (unsigned)kd;
+                    const unsigned long long kk = (((unsigned long long)__ldg(&P.sc.tie_hi[kd])) << 32) | (unsigned)kd;
                     if (t < td || (t < CUDART_INF && t == td && kk < key)) {
                         td = t;
                         key = kk;
@@ -823,27 +914,32 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_
                     }
                 }
             }
-            if (key == BEST_KEY_MISS) {                     // core.clj:40-41 miss -> accum (black)
+            const bool hit = key != BEST_KEY_MISS;
+            if (P.path_pixel) path_log_ray(P, slot, (int)bounce - 1, a, b, hit ? k : -1, hit ? td : CUDART_INF);
+            if (!hit) {                                     // core.clj:40-41 miss -> accum (black)
                 atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
+                if (P.path_pixel) path_log_end(P, slot, (int)bounce, TERM_MISS);
             } else {
                 float3 o = f3(a.x, a.y, a.z), d = f3(b.x, b.y, b.z);
                 float3 att, em;
                 int reason = TERM_NONE;
-                ScatterRng rng{P.key, pix, smp, (uint32_t)(P.max_depth - depth + 1), nullptr, nullptr};
-                cont = shade_hit(P.sc, k, (float)td, o, d, a.w, depth > 0, rng, att, em, reason);
+                float tmv = a.w;
+                ScatterRng rng{P.key, pix, smp, bounce, nullptr, nullptr};
+                cont = shade_hit<GEN>(P.sc, scp, k, (float)td, o, d, tmv, depth > 0, rng, att, em, reason);
                 if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
-                    float* dst = P.sum + (size_t)pix * 3;
+                    float* dst = P.sum + (size_t)slot * 3;
                     atomicAdd(dst + 0, c.x * em.x);
                     atomicAdd(dst + 1, c.y * em.y);
                     atomicAdd(dst + 2, c.z * em.z);
                 }
                 if (cont) {
-                    a = make_float4(o.x, o.y, o.z, a.w);
+                    a = make_float4(o.x, o.y, o.z, tmv);
                     b = make_float4(d.x, d.y, d.z, b.w);
                     c = make_float4(c.x * att.x, c.y * att.y, c.z * att.z, __uint_as_float((smp << 8) | (uint32_t)(depth - 1)));
                 } else {
                     atomicAdd(&s_ctr[reason == TERM_LIGHT ? DC_TERM_LIGHT
                                      : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
+                    if (P.path_pixel) path_log_end(P, slot, (int)bounce, reason);
                 }
             }
         }
@@ -873,17 +969,18 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, Scope sc_
             }
         }
     }
-    if (n_direct) atomicAdd(&s_ctr[DC_CANDIDATES], n_direct);
+    if (n_direct) atomicAdd(&s_ctr[DC_DIRECT], n_direct);
     return n_samples;
 }
 
-__global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
+template <bool GEN>
+__global__ void __launch_bounds__(256, GEN ? 1 : 0) wf_shade(const __grid_constant__ WaveParams W) {
     TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     __shared__ unsigned s_ctr[DC_COUNT];
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned n_samples = wf_shade_body(W, grid_scope(), W.cur, s_ctr);
+    const unsigned n_samples = wf_shade_body<GEN>(W, &W.base.sc, grid_scope(), W.cur, s_ctr);
     atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
     __syncthreads();
     if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
@@ -896,8 +993,8 @@ __global__ void __launch_bounds__(256) wf_shade(const WaveParams W) {
 // iteration) or grid.sync() (the cooperative form of this kernel: ~20 us per iteration, 0.75 ms per render).
 // The slices are the CTA's ranges of the lane's own buffers, so a slice's population can only shrink in place.
 constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 1.5)
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
+template <int BLOCK, bool GEN>
+__global__ void __launch_bounds__(BLOCK, GEN ? 1 : 2) wf_tail(const __grid_constant__ WaveParams W) {
     TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
@@ -945,11 +1042,11 @@ __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
         if (n == 0) break;
         wf_cull_body<1, BLOCK>(L, solo, cur, n, 0u, s_cull, nullptr, s_list);
         __syncthreads();
-        wf_refine_body(L, solo, cur);
+        wf_refine_body<GEN>(L, &W.base.sc, solo, cur);
         __syncthreads();
         wf_tiebreak_body(L, solo);
         __syncthreads();
-        n_samples += wf_shade_body(L, solo, cur, s_ctr);
+        n_samples += wf_shade_body<GEN>(L, &W.base.sc, solo, cur, s_ctr);
         cur ^= 1;
     }
     atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
@@ -964,8 +1061,8 @@ __global__ void __launch_bounds__(BLOCK, 2) wf_tail(const WaveParams W) {
 // ballot + prefix popc) so the intersect loop runs with full lanes until the work runs out.
 // Warps run asynchronously through generate / intersect / refine / shade code.
 // ------------------------------------------------------------------------------------------
-template <int R, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P) {
+template <int R, int BLOCK, int MINB, bool GEN>
+__global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
@@ -975,18 +1072,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
     __syncthreads();
 
     Culler<R, BLOCK> K;
-    RefineSink<R, BLOCK> I;
+    RefineSink<R, BLOCK, GEN> I;
     I.tmin = 0.001;               // core.clj:25
     I.tmax = (double)FLT_MAX;     // Float/MAX_VALUE
     I.ncand = 0;
     I.sc = &P.sc;
+    I.has_ctx = true;
+    I.key = P.key;
 
     float ar[R], ag[R], ab[R];    // attenuation (core.clj:23 `atten`); the rays themselves live in the sink
-    uint32_t pix[R], smp[R];
+    uint32_t slot[R];             // where the path's radiance goes: the pixel (a render) / the path (rt_trace_paths)
+    uint32_t (&pix)[R] = I.pix, (&smp)[R] = I.smp;
     int depth[R];
     bool alive[R];
-    RT_FOR_R { alive[r] = false; I.ox[r] = I.oy[r] = I.oz[r] = I.tm[r] = 0.f; I.dx[r] = 1.f; I.dy[r] = I.dz[r] = 0.f; }
-    unsigned n_rays = 0, n_samples = 0;
+    RT_FOR_R { alive[r] = false; I.ox[r] = I.oy[r] = I.oz[r] = I.tm[r] = 0.f; I.dx[r] = 1.f; I.dy[r] = I.dz[r] = 0.f; pix[r] = smp[r] = slot[r] = 0u; I.bounce[r] = 0u; }
+    unsigned n_rays = 0, n_samples = 0, n_direct = 0;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned pshard = (unsigned)P.nx * (unsigned)P.rows_in_shard;
 
@@ -1008,6 +1108,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                     int j = P.row_offset + row_local * P.row_stride;
                     pix[r] = (uint32_t)j * (uint32_t)P.nx + (uint32_t)i;
                     smp[r] = (uint32_t)(P.sample_begin + (int)s_local);
+                    slot[r] = pix[r];
+                    if (P.path_pixel) {                       // rt_trace_paths: work item w is path w of the caller's list
+                        pix[r] = (uint32_t)__ldg(&P.path_pixel[w]);
+                        smp[r] = (uint32_t)__ldg(&P.path_sample[w]);
+                        j = (int)(pix[r] / (uint32_t)P.nx);
+                        i = (int)(pix[r] - (uint32_t)j * (uint32_t)P.nx);
+                        slot[r] = (uint32_t)w;
+                    }
                     float3 o, d;
                     generate_ray(P.cam, P.nx, P.ny, i, j, pix[r], smp[r], P.key, o, d, I.tm[r], nullptr);
                     I.ox[r] = o.x; I.oy[r] = o.y; I.oz[r] = o.z;
@@ -1034,26 +1142,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
         RT_FOR_R {
             if (alive[r]) { K.set_ray(r, I.ox[r], I.oy[r], I.oz[r], I.dx[r], I.dy[r], I.dz[r]); n_rays++; live |= 1u << r; }
             else K.kill(r);
+            I.bounce[r] = (uint32_t)(P.max_depth - depth[r] + 1);
         }
         I.begin();
         K.run(P.sc, s_cull, P.cull_cap, P.preloaded != 0, s_list, I);
-        I.direct(live);
+        n_direct += I.direct(live);
 
         // ---- shade ------------------------------------------------------------------------------
         RT_FOR_R {
             if (alive[r]) {
+                if (P.path_pixel)
+                    path_log_ray(P, slot[r], (int)I.bounce[r] - 1, make_float4(I.ox[r], I.oy[r], I.oz[r], I.tm[r]),
+                                 make_float4(I.dx[r], I.dy[r], I.dz[r], 0.f), I.best_k[r], I.best_t[r]);
                 if (I.best_k[r] < 0) {                       // core.clj:40-41 miss -> accum (black)
                     alive[r] = false;
                     atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
+                    if (P.path_pixel) path_log_end(P, slot[r], (int)I.bounce[r], TERM_MISS);
                 } else {
                     float3 o = f3(I.ox[r], I.oy[r], I.oz[r]), d = f3(I.dx[r], I.dy[r], I.dz[r]);
                     float3 att, em;
                     int reason = TERM_NONE;
-                    ScatterRng rng{P.key, pix[r], smp[r], (uint32_t)(P.max_depth - depth[r] + 1), nullptr, nullptr};
-                    bool cont = shade_hit(P.sc, I.best_k[r], (float)I.best_t[r], o, d, I.tm[r], depth[r] > 0, rng, att, em,
+                    ScatterRng rng{P.key, pix[r], smp[r], I.bounce[r], nullptr, nullptr};
+                    bool cont = shade_hit<GEN>(P.sc, &P.sc, I.best_k[r], (float)I.best_t[r], o, d, I.tm[r], depth[r] > 0, rng, att, em,
                                           reason);
                     if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
-                        float* dst = P.sum + (size_t)pix[r] * 3;
+                        float* dst = P.sum + (size_t)slot[r] * 3;
                         atomicAdd(dst + 0, ar[r] * em.x);
                         atomicAdd(dst + 1, ag[r] * em.y);
                         atomicAdd(dst + 2, ab[r] * em.z);
@@ -1067,6 +1180,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
                         alive[r] = false;
                         atomicAdd(&s_ctr[reason == TERM_LIGHT ? DC_TERM_LIGHT
                                          : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
+                        if (P.path_pixel) path_log_end(P, slot[r], (int)I.bounce[r], reason);
                     }
                 }
             }
@@ -1076,6 +1190,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const RenderParams P)
     atomicAdd(&s_ctr[DC_RAYS], n_rays);
     atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
     atomicAdd(&s_ctr[DC_CANDIDATES], I.ncand);
+    atomicAdd(&s_ctr[DC_DIRECT], n_direct);
     __syncthreads();
     if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
 }
@@ -1095,19 +1210,20 @@ struct TraceParams {
     int cull_cap, preloaded;
 };
 
-template <int R, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
+template <int R, int BLOCK, bool GEN>
+__global__ void __launch_bounds__(BLOCK) trace_kernel(const __grid_constant__ TraceParams P) {
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
     __syncthreads();
     Culler<R, BLOCK> K;
-    RefineSink<R, BLOCK> I;
+    RefineSink<R, BLOCK, GEN> I;
     I.tmin = P.tmin;
     I.tmax = P.tmax;
     I.ncand = 0;
     I.sc = &P.sc;
+    I.has_ctx = false;            // no path behind these rays: a ConstantMedium draws 0.5
     for (long long base = (long long)blockIdx.x * BLOCK * R; base < P.n; base += (long long)gridDim.x * BLOCK * R) {
         unsigned live = 0;
         RT_FOR_R {
@@ -1131,7 +1247,7 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
             long long idx = base + (long long)r * BLOCK + threadIdx.x;
             if (idx < P.n) {
                 P.out_t[idx] = I.best_t[r];
-                P.out_id[idx] = (I.best_k[r] >= 0) ? I.best_orig[r] : -1;
+                P.out_id[idx] = (I.best_k[r] >= 0) ? __ldg(&P.sc.orig_id[I.best_k[r]]) : -1;
             }
         }
     }
@@ -1143,7 +1259,7 @@ __global__ void __launch_bounds__(BLOCK) trace_kernel(const TraceParams P) {
 // The cull's contract, checked pair by pair: every (ray, listed sphere) whose exact FP64 test accepts a root in
 // (tmin, tmax) must have a clear sign bit in the FP32 key computed by the very code of the hot loop.
 // out[0] = pairs the cull would have lost (must be 0), out[1] = cull survivors, out[2] = exact candidates.
-__global__ void __launch_bounds__(128) cull_check_kernel(const DevScene sc, int n, const float* origins, const float* dirs,
+__global__ void __launch_bounds__(128) cull_check_kernel(const __grid_constant__ DevScene sc, int n, const float* origins, const float* dirs,
                                                          const float* times, double tmin, double tmax,
                                                          unsigned long long* out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1157,7 +1273,8 @@ __global__ void __launch_bounds__(128) cull_check_kernel(const DevScene sc, int 
         K.pin();
         for (int k = 0; k < sc.n_list; ++k) {
             const bool culled = (K.key_bits(__ldg(&sc.cull_a[k]), 0) >> 31) != 0u;
-            const double t = refine_candidate(sc.ex_c0r, sc.ex_c1, sc.ex_t0t1, sc.flags, k, ox, oy, oz, dx, dy, dz, tm, tmin, tmax);
+            const double t = sc.generic ? refine_leaf<true>(&sc, k, ox, oy, oz, dx, dy, dz, tm, tmin, tmax, false, make_uint2(0u, 0u), 0u, 0u, 0u)
+                                        : refine_leaf<false>(&sc, k, ox, oy, oz, dx, dy, dz, tm, tmin, tmax, false, make_uint2(0u, 0u), 0u, 0u, 0u);
             surv += culled ? 0u : 1u;
             if (t < CUDART_INF) {
                 cand++;
@@ -1168,6 +1285,19 @@ __global__ void __launch_bounds__(128) cull_check_kernel(const DevScene sc, int 
     if (lost) atomicAdd(&out[0], lost);
     if (surv) atomicAdd(&out[1], surv);
     if (cand) atomicAdd(&out[2], cand);
+}
+
+// rt_sample_device: the closed-form samplers by themselves (util.clj:32-52), keyed (pixel = index, sample 0)
+__global__ void sampler_kernel(int kind, int n, uint2 key, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (kind == 0) {
+        const float3 p = rand_in_unit_sphere(key, (uint32_t)i, 0u, 1u, 1u);
+        out[3 * i] = p.x; out[3 * i + 1] = p.y; out[3 * i + 2] = p.z;
+    } else {
+        const float2 p = rand_in_unit_disk(key, (uint32_t)i, 0u, 1u);
+        out[2 * i] = p.x; out[2 * i + 1] = p.y;
+    }
 }
 
 __global__ void genrays_kernel(DevCamera cam, int n, int nx, int ny, const int* ij, const int* s, uint2 key, float* out_o,
@@ -1186,7 +1316,7 @@ __global__ void genrays_kernel(DevCamera cam, int n, int nx, int ny, const int* 
         for (int k = 0; k < 5; ++k) out_rnd[5 * idx + k] = rnd[k];
 }
 
-__global__ void shade_kernel(DevScene sc, int n, const float* origins, const float* dirs, const float* times,
+__global__ void shade_kernel(const __grid_constant__ DevScene sc, int n, const float* origins, const float* dirs, const float* times,
                              const int* hit_id, const double* hit_t, const float* ball, const float* u01v, float* out_o,
                              float* out_d, float* out_att, float* out_em, int* out_flags) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1200,7 +1330,9 @@ __global__ void shade_kernel(DevScene sc, int n, const float* origins, const flo
         int k = sc.cull_of_orig[id];
         int reason = TERM_NONE;
         ScatterRng rng{make_uint2(0u, 0u), 0u, 0u, 0u, ball + 3 * idx, u01v + idx};
-        bool cont = shade_hit(sc, k, (float)hit_t[idx], o, d, times ? times[idx] : 0.f, true, rng, att, em, reason);
+        float tmv = times ? times[idx] : 0.f;
+        bool cont = sc.generic ? shade_hit<true>(sc, &sc, k, (float)hit_t[idx], o, d, tmv, true, rng, att, em, reason)
+                               : shade_hit<false>(sc, &sc, k, (float)hit_t[idx], o, d, tmv, true, rng, att, em, reason);
         flag = cont ? 1 : 0;
         if (!cont) {
             o = f3(0.f, 0.f, 0.f); d = o; att = o;

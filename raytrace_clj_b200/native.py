@@ -16,17 +16,31 @@ import numpy as np
 
 from . import camera as cam
 from . import hitable as hit
+from . import perlin
 from . import shader as shad
 from . import texture as tex
 
 RT_SPHERE_UV, RT_SPHERE_MOVING = 1, 2
-RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT = 0, 1, 2, 3
+RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 0, 1, 2, 3, 4
 RT_TEX_CONSTANT, RT_TEX_UV_GRADIENT, RT_TEX_CHECKERBOARD = 0, 1, 2
+RT_TEX_PERLIN_NOISE, RT_TEX_PERLIN_TURB, RT_TEX_MARBLE, RT_TEX_FLIP_U, RT_TEX_FLIP_V, RT_TEX_IMAGE_MAP = 3, 4, 5, 6, 7, 8
+RT_PRIM_SPHERE, RT_PRIM_RECT_XY, RT_PRIM_RECT_XZ, RT_PRIM_RECT_YZ, RT_PRIM_TRIANGLE, RT_PRIM_MEDIUM = 0, 1, 2, 3, 4, 5
+RT_XOP_NONE, RT_XOP_TRANSLATE, RT_XOP_ROTATE_Y, RT_XOP_FLIP = 0, 1, 2, 3
+RT_XFORM_MAX_OPS = 4
+RT_TIE_HITLIST, RT_TIE_BVH = 0, 1
+RT_ACCEL_BRUTE_FORCE, RT_ACCEL_BVH = 0, 1
 RT_CAM_PINHOLE, RT_CAM_THIN_LENS = 0, 1
 RT_VARIANT_MEGAKERNEL, RT_VARIANT_WAVEFRONT = 0, 1
-RT_CTR_COUNT = 16
+RT_TERM_LIGHT, RT_TERM_ABSORB, RT_TERM_DEPTH, RT_TERM_MISS = 1, 2, 3, 4
+RT_CTR_COUNT = 24
 COUNTER_NAMES = ["rays", "sphere_tests", "samples", "term_light", "term_absorb", "term_depth", "term_miss",
-                 "kernel_ns", "candidates", "kernel_launches", "cull_ns", "refine_ns", "tiebreak_ns", "shade_ns"]
+                 "kernel_ns", "candidates", "kernel_launches", "cull_ns", "refine_ns", "tiebreak_ns", "shade_ns",
+                 "direct_tests", "bvh_node_tests", "reduce_ns"]
+
+# one logged bounce of rt_trace_paths (struct rt_path_bounce, 40 bytes)
+PATH_BOUNCE_DTYPE = np.dtype([("o", np.float32, 3), ("time", np.float32), ("d", np.float32, 3), ("hit_id", np.int32),
+                              ("t", np.float64)])
+assert PATH_BOUNCE_DTYPE.itemsize == 40
 
 
 class UnsupportedSceneError(ValueError):
@@ -39,7 +53,9 @@ class NativeError(RuntimeError):
 
 @dataclass
 class FlatScene:
-    """The marshalled scene: exactly the buffers of ``rt_scene_desc``."""
+    """The marshalled scene: exactly the buffers of ``rt_scene_desc`` (+ ``rt_scene_ext`` when anything beyond
+    spheres / the three basic textures is present).  Per-primitive arrays hold the ``n_spheres`` world primitives
+    in flatten order, then ``n_boundary`` boundary primitives of media."""
     center0_r: np.ndarray      # [n,4] f32
     center1: np.ndarray        # [n,4] f32
     t0t1: np.ndarray           # [n,2] f32
@@ -51,55 +67,94 @@ class FlatScene:
     tex_type: np.ndarray       # [t]   i32
     tex_params: np.ndarray     # [t,12] f32
     tex_children: np.ndarray   # [t,2] i32
+    # ---- rt_scene_ext (None / 0 => plain sphere scene, rt_set_scene) ----
+    n_boundary: int = 0
+    prim_type: np.ndarray | None = None      # [n]    i32 RT_PRIM_*
+    prim_params: np.ndarray | None = None    # [n,12] f32
+    prim_aux: np.ndarray | None = None       # [n,2]  i32
+    prim_xform: np.ndarray | None = None     # [n]    i32
+    xform_ops: np.ndarray | None = None      # [x,4]  i32
+    xform_params: np.ndarray | None = None   # [x,4,4] f32
+    tie_rule: int = RT_TIE_HITLIST
+    perlin_vectors: np.ndarray | None = None  # [256,3] f32
+    perlin_perm: np.ndarray | None = None     # [3,256] i32
+    image_wh: np.ndarray | None = None        # [k,2] i32
+    image_offset: np.ndarray | None = None    # [k]   i64
+    image_rgb: np.ndarray | None = None       # bytes
 
     @property
     def n_spheres(self):
-        return int(self.center0_r.shape[0])
+        """World primitives (the name is the C struct's field: spheres only in ABI v1)."""
+        return int(self.center0_r.shape[0]) - int(self.n_boundary)
+
+    @property
+    def has_ext(self):
+        return self.prim_type is not None or self.tie_rule != RT_TIE_HITLIST or self.perlin_vectors is not None \
+            or self.image_wh is not None
+
+    def copy(self):
+        return FlatScene(**{k: (getattr(self, k).copy() if isinstance(getattr(self, k), np.ndarray) else getattr(self, k))
+                            for k in self.__dataclass_fields__})
+
+    def nbytes(self):
+        return int(sum(getattr(self, k).nbytes for k in self.__dataclass_fields__ if isinstance(getattr(self, k), np.ndarray)))
 
 
-def flatten_world(world):
-    """Leaves of the container tree, left to right, de-duplicated by identity."""
+_LEAF_TYPES = (hit.Sphere, hit.MovingSphere, hit.RectXY, hit.RectXZ, hit.RectYZ, hit.Triangle, hit.ConstantMedium)
+
+
+def flatten_world(world, with_ops=False):
+    """Leaves of the container tree, left to right.  A 1-element bvh-node stores the same object as both
+    children (hitable.clj:113-114): it is visited once.  Wrappers (FlipNormals / Translate / RotateY,
+    hitable.clj:375-486) are folded into a per-leaf op chain, outermost first; a Box (hitable.clj:491-511)
+    contributes its six rectangles.  with_ops: return (leaf, ops) pairs instead of the bare leaves."""
     out, seen = [], set()
 
-    def walk(h):
+    def walk(h, ops):
         if isinstance(h, hit.BvhNode):
-            walk(h.left)
-            walk(h.right)
+            walk(h.left, ops)
+            if h.right is not h.left:
+                walk(h.right, ops)
         elif isinstance(h, hit.Hitlist):
             for it in h.items:
-                walk(it)
-        elif isinstance(h, (hit.Sphere, hit.MovingSphere)):
-            if id(h) not in seen:
-                seen.add(id(h))
-                out.append(h)
+                walk(it, ops)
+        elif isinstance(h, hit.Box):
+            walk(h.sides, ops)
+        elif isinstance(h, hit.FlipNormals):
+            walk(h.item, ops + ((RT_XOP_FLIP, (0.0, 0.0, 0.0, 0.0)),))
+        elif isinstance(h, hit.Translate):
+            o = h.offset
+            walk(h.item, ops + ((RT_XOP_TRANSLATE, (float(o[0]), float(o[1]), float(o[2]), 0.0)),))
+        elif isinstance(h, hit.RotateY):
+            walk(h.obj, ops + ((RT_XOP_ROTATE_Y, (float(h.sin_theta), float(h.cos_theta), 0.0, 0.0)),))
+        elif isinstance(h, _LEAF_TYPES):
+            key = (id(h), ops)
+            if key not in seen:
+                seen.add(key)
+                out.append((h, ops))
         else:
-            raise UnsupportedSceneError(
-                f"{type(h).__name__} is outside the accelerated path (spheres only); no CPU fallback")
+            raise UnsupportedSceneError(f"{type(h).__name__} is outside the accelerated path; no CPU fallback")
 
     # iterative-safe for deep trees
     import sys
     old = sys.getrecursionlimit()
     sys.setrecursionlimit(max(old, 10000))
     try:
-        walk(world)
+        walk(world, ())
     finally:
         sys.setrecursionlimit(old)
-    return out
+    return out if with_ops else [h for h, _ in out]
 
 
-def marshal_world(world) -> FlatScene:
-    leaves = flatten_world(world)
-    n = len(leaves)
-    if n == 0:
+def marshal_world(world, perlin_tables=None) -> FlatScene:
+    leaves = flatten_world(world, with_ops=True)
+    if len(leaves) == 0:
         raise UnsupportedSceneError("empty world")
-    c0r = np.zeros((n, 4), np.float32)
-    c1 = np.zeros((n, 4), np.float32)
-    t0t1 = np.zeros((n, 2), np.float32)
-    t0t1[:, 1] = 1.0
-    flags = np.zeros(n, np.uint32)
-    mat_id = np.zeros(n, np.int32)
     mats, mat_index = [], {}
     texs, tex_index = [], {}
+    images = []
+    xforms, xform_index = [], {}
+    uses = {"perlin": False, "ext": False}
 
     def add_tex(t):
         if id(t) in tex_index:
@@ -116,8 +171,25 @@ def marshal_world(world) -> FlatScene:
             ty = RT_TEX_CHECKERBOARD
             p[0] = t.scale
             ch = [add_tex(t.tex0), add_tex(t.tex1)]
+        elif isinstance(t, tex.PerlinNoise):
+            ty, p[0] = RT_TEX_PERLIN_NOISE, t.scale
+            uses["perlin"] = True
+        elif isinstance(t, tex.PerlinTurbulence):
+            ty, p[0], p[1] = RT_TEX_PERLIN_TURB, t.scale, t.depth
+            uses["perlin"] = True
+        elif isinstance(t, tex.Marble):
+            ty, p[0], p[1] = RT_TEX_MARBLE, t.scale, t.depth
+            uses["perlin"] = True
+        elif isinstance(t, (tex.FlipTextureU, tex.FlipTextureV)):
+            ty = RT_TEX_FLIP_U if isinstance(t, tex.FlipTextureU) else RT_TEX_FLIP_V
+            ch = [add_tex(t.tex), -1]
+        elif isinstance(t, tex.ImageMap):
+            ty, p[0] = RT_TEX_IMAGE_MAP, len(images)
+            images.append(np.ascontiguousarray(t.image, np.uint8))
         else:
             raise UnsupportedSceneError(f"texture {type(t).__name__} is outside the accelerated path")
+        if ty > RT_TEX_CHECKERBOARD:
+            uses["ext"] = True
         tex_index[id(t)] = len(texs)
         texs.append((ty, p, ch))
         return tex_index[id(t)]
@@ -133,32 +205,112 @@ def marshal_world(world) -> FlatScene:
             rec = (RT_MAT_DIELECTRIC, m.ri, -1)
         elif isinstance(m, shad.DiffuseLight):
             rec = (RT_MAT_DIFFUSE_LIGHT, 0.0, add_tex(m.tex))
+        elif isinstance(m, shad.Isotropic):
+            rec = (RT_MAT_ISOTROPIC, 0.0, add_tex(m.albedo))
+            uses["ext"] = True
         else:
             raise UnsupportedSceneError(f"material {type(m).__name__} is outside the accelerated path")
         mat_index[id(m)] = len(mats)
         mats.append(rec)
         return mat_index[id(m)]
 
-    for i, s in enumerate(leaves):
-        if isinstance(s, hit.MovingSphere):
-            c0r[i, :3], c0r[i, 3] = s.center0, s.radius
-            c1[i, :3] = s.center1
-            t0t1[i] = (s.t0, s.t1)
-            flags[i] = RT_SPHERE_MOVING
-        else:
-            c0r[i, :3], c0r[i, 3] = s.center, s.radius
-            c1[i, :3] = s.center
-            flags[i] = RT_SPHERE_UV if isinstance(s, hit.UVSphere) else 0
-        mat_id[i] = add_mat(s.material)
+    def add_xform(ops):
+        if not ops:
+            return -1
+        if len(ops) > RT_XFORM_MAX_OPS:
+            raise UnsupportedSceneError(f"more than {RT_XFORM_MAX_OPS} nested wrappers around one leaf")
+        if ops not in xform_index:
+            xform_index[ops] = len(xforms)
+            xforms.append(ops)
+        uses["ext"] = True
+        return xform_index[ops]
 
-    return FlatScene(
-        c0r, c1, t0t1, flags, mat_id,
+    rows = []          # world primitives
+    boundary = []      # boundary primitives of media (appended after the world)
+
+    def prim_row(s, ops, material=True):
+        r = dict(c0r=np.zeros(4, np.float32), c1=np.zeros(4, np.float32), tt=np.array([0, 1], np.float32), flags=0,
+                 type=RT_PRIM_SPHERE, q=np.zeros(12, np.float32), aux=[0, 0], xform=add_xform(ops),
+                 mat=add_mat(s.material) if material else 0)
+        if isinstance(s, hit.MovingSphere):
+            r["c0r"][:3], r["c0r"][3] = s.center0, s.radius
+            r["c1"][:3] = s.center1
+            r["tt"][:] = (s.t0, s.t1)
+            r["flags"] = RT_SPHERE_MOVING
+        elif isinstance(s, hit.Sphere):
+            r["c0r"][:3], r["c0r"][3] = s.center, s.radius
+            r["c1"][:3] = s.center
+            r["flags"] = RT_SPHERE_UV if isinstance(s, hit.UVSphere) else 0
+        elif isinstance(s, hit.RectXY):
+            r["type"], r["q"][:5] = RT_PRIM_RECT_XY, (s.x0, s.y0, s.x1, s.y1, s.k)
+        elif isinstance(s, hit.RectXZ):
+            r["type"], r["q"][:5] = RT_PRIM_RECT_XZ, (s.x0, s.z0, s.x1, s.z1, s.k)
+        elif isinstance(s, hit.RectYZ):
+            r["type"], r["q"][:5] = RT_PRIM_RECT_YZ, (s.y0, s.z0, s.y1, s.z1, s.k)
+        elif isinstance(s, hit.Triangle):
+            r["type"] = RT_PRIM_TRIANGLE
+            r["q"][0:3], r["q"][3:6], r["q"][6:9] = s.v0, s.v1, s.v2
+        else:
+            raise UnsupportedSceneError(f"{type(s).__name__} cannot bound a medium / be a leaf here")
+        if r["type"] != RT_PRIM_SPHERE:
+            uses["ext"] = True
+        return r
+
+    pending_media = []
+    for s, ops in leaves:
+        if isinstance(s, hit.ConstantMedium):
+            r = dict(c0r=np.zeros(4, np.float32), c1=np.zeros(4, np.float32), tt=np.array([0, 1], np.float32), flags=0,
+                     type=RT_PRIM_MEDIUM, q=np.zeros(12, np.float32), aux=[0, 0], xform=add_xform(ops),
+                     mat=add_mat(s.phase_fn))
+            r["q"][0] = s.density
+            uses["ext"] = True
+            pending_media.append((r, s.boundary))
+            rows.append(r)
+        else:
+            rows.append(prim_row(s, ops))
+    n_world = len(rows)
+    for r, bnd in pending_media:
+        bl = flatten_world(bnd, with_ops=True)
+        if any(isinstance(b, hit.ConstantMedium) for b, _ in bl):
+            raise UnsupportedSceneError("a medium cannot bound a medium")
+        r["aux"] = [n_world + len(boundary), len(bl)]
+        boundary.extend(prim_row(b, bops, material=False) for b, bops in bl)
+    allrows = rows + boundary
+    tie = RT_TIE_BVH if isinstance(world, hit.BvhNode) else RT_TIE_HITLIST
+
+    fs = FlatScene(
+        np.stack([r["c0r"] for r in allrows]), np.stack([r["c1"] for r in allrows]), np.stack([r["tt"] for r in allrows]),
+        np.array([r["flags"] for r in allrows], np.uint32), np.array([r["mat"] for r in allrows], np.int32),
         np.array([m[0] for m in mats], np.int32), np.array([m[1] for m in mats], np.float32),
         np.array([m[2] for m in mats], np.int32),
         np.array([t[0] for t in texs], np.int32).reshape(-1),
         np.array([t[1] for t in texs], np.float32).reshape(-1, 12),
         np.array([t[2] for t in texs], np.int32).reshape(-1, 2),
     )
+    fs.tie_rule = tie
+    if uses["ext"] or uses["perlin"] or images:
+        fs.n_boundary = len(boundary)
+        fs.prim_type = np.array([r["type"] for r in allrows], np.int32)
+        fs.prim_params = np.stack([r["q"] for r in allrows]).astype(np.float32)
+        fs.prim_aux = np.array([r["aux"] for r in allrows], np.int32).reshape(-1, 2)
+        fs.prim_xform = np.array([r["xform"] for r in allrows], np.int32)
+        xo = np.zeros((max(1, len(xforms)), RT_XFORM_MAX_OPS), np.int32)
+        xp = np.zeros((max(1, len(xforms)), RT_XFORM_MAX_OPS, 4), np.float32)
+        for i, ops in enumerate(xforms):
+            for k, (ty, prm) in enumerate(ops):
+                xo[i, k] = ty
+                xp[i, k] = prm
+        fs.xform_ops, fs.xform_params = xo[:len(xforms)], xp[:len(xforms)]
+        if uses["perlin"]:
+            tb = perlin_tables or perlin.TABLES
+            fs.perlin_vectors = np.ascontiguousarray(tb.vectors, np.float32)
+            fs.perlin_perm = np.ascontiguousarray(tb.perm, np.int32)
+        if images:
+            fs.image_wh = np.array([[im.shape[1], im.shape[0]] for im in images], np.int32)
+            offs = np.cumsum([0] + [im.size for im in images])
+            fs.image_offset = np.array(offs[:-1], np.int64)
+            fs.image_rgb = np.concatenate([im.reshape(-1) for im in images]).astype(np.uint8)
+    return fs
 
 
 def marshal_camera(camera):
@@ -197,6 +349,16 @@ class _SceneDesc(C.Structure):
     ]
 
 
+class _SceneExt(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("n_boundary", C.c_int32),
+        ("prim_type", _i32p), ("prim_params", _f32p), ("prim_aux", _i32p), ("prim_xform", _i32p),
+        ("n_xforms", C.c_int32), ("xform_ops", _i32p), ("xform_params", _f32p),
+        ("tie_rule", C.c_int32), ("perlin_vectors", _f32p), ("perlin_perm", _i32p),
+        ("n_images", C.c_int32), ("image_wh", _i32p), ("image_offset", C.POINTER(C.c_int64)), ("image_rgb", _u8p),
+    ]
+
+
 LIB_NAME = "libraytrace_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
@@ -205,6 +367,7 @@ ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_set_scene", "rt_set_camera", "rt_render",
     "rt_render_accumulate_device", "rt_resolve_device", "rt_trace_primary", "rt_generate_rays", "rt_shade_batch",
     "rt_measure_fp32_peak", "rt_get_counters", "rt_reset_counters", "rt_set_profile", "rt_device_info", "rt_cull_check",
+    "rt_set_scene_ex", "rt_trace_paths", "rt_set_accel", "rt_set_option", "rt_sample_device",
 ]
 
 _lib = None
@@ -225,6 +388,12 @@ def load_library():
     L.rt_destroy.argtypes = [C.c_void_p]
     L.rt_destroy.restype = None
     L.rt_set_scene.argtypes = [C.c_void_p, C.POINTER(_SceneDesc)]
+    L.rt_set_scene_ex.argtypes = [C.c_void_p, C.POINTER(_SceneDesc), C.POINTER(_SceneExt)]
+    L.rt_set_accel.argtypes = [C.c_void_p, C.c_int]
+    L.rt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    L.rt_trace_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int, C.c_uint64, C.c_int,
+                                 _f32p, _i32p, _i32p, C.c_int, C.c_void_p]
+    L.rt_sample_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, _f32p]
     L.rt_set_camera.argtypes = [C.c_void_p, C.c_int, _f32p]
     L.rt_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, _f32p, _u8p]
     L.rt_render_accumulate_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -294,10 +463,60 @@ class Renderer:
             mp=np.ascontiguousarray(flat.mat_param, np.float32), mx=np.ascontiguousarray(flat.mat_tex, np.int32),
             tt2=np.ascontiguousarray(flat.tex_type, np.int32), tp=np.ascontiguousarray(flat.tex_params, np.float32),
             tc=np.ascontiguousarray(flat.tex_children, np.int32))
-        d = _SceneDesc(len(k["fl"]), _p(k["c0"], _f32p), _p(k["c1"], _f32p), _p(k["tt"], _f32p), _p(k["fl"], _u32p),
+        d = _SceneDesc(flat.n_spheres, _p(k["c0"], _f32p), _p(k["c1"], _f32p), _p(k["tt"], _f32p), _p(k["fl"], _u32p),
                        _p(k["mi"], _i32p), len(k["mt"]), _p(k["mt"], _i32p), _p(k["mp"], _f32p), _p(k["mx"], _i32p),
                        len(k["tt2"]), _p(k["tt2"], _i32p), _p(k["tp"], _f32p), _p(k["tc"], _i32p))
-        self._check(self.L.rt_set_scene(self.h, C.byref(d)), "rt_set_scene")
+        if not flat.has_ext:
+            self._check(self.L.rt_set_scene(self.h, C.byref(d)), "rt_set_scene")
+            return
+        c = np.ascontiguousarray
+        e = dict(pt=None if flat.prim_type is None else c(flat.prim_type, np.int32),
+                 pp=None if flat.prim_params is None else c(flat.prim_params, np.float32),
+                 pa=None if flat.prim_aux is None else c(flat.prim_aux, np.int32),
+                 px=None if flat.prim_xform is None else c(flat.prim_xform, np.int32),
+                 xo=None if flat.xform_ops is None else c(flat.xform_ops, np.int32),
+                 xp=None if flat.xform_params is None else c(flat.xform_params, np.float32),
+                 pv=None if flat.perlin_vectors is None else c(flat.perlin_vectors, np.float32),
+                 pm=None if flat.perlin_perm is None else c(flat.perlin_perm, np.int32),
+                 iw=None if flat.image_wh is None else c(flat.image_wh, np.int32),
+                 io=None if flat.image_offset is None else c(flat.image_offset, np.int64),
+                 ir=None if flat.image_rgb is None else c(flat.image_rgb, np.uint8))
+        x = _SceneExt(C.sizeof(_SceneExt), int(flat.n_boundary), _p(e["pt"], _i32p), _p(e["pp"], _f32p), _p(e["pa"], _i32p),
+                      _p(e["px"], _i32p), 0 if e["xo"] is None else len(e["xo"]), _p(e["xo"], _i32p), _p(e["xp"], _f32p),
+                      int(flat.tie_rule), _p(e["pv"], _f32p), _p(e["pm"], _i32p),
+                      0 if e["iw"] is None else len(e["iw"]), _p(e["iw"], _i32p), _p(e["io"], C.POINTER(C.c_int64)),
+                      _p(e["ir"], _u8p))
+        self._check(self.L.rt_set_scene_ex(self.h, C.byref(d), C.byref(x)), "rt_set_scene_ex")
+
+    def set_accel(self, accel):
+        """RT_ACCEL_BRUTE_FORCE (the roofline path) or RT_ACCEL_BVH (flattened GPU BVH, hitable.clj:97-123's role)."""
+        self._check(self.L.rt_set_accel(self.h, int(accel)), "rt_set_accel")
+
+    def set_option(self, name, value):
+        """Per-context tuning knob (the RT_* environment variables are only the defaults)."""
+        self._check(self.L.rt_set_option(self.h, name.encode(), C.c_int64(int(value))), "rt_set_option")
+
+    def trace_paths(self, nx, ny, pixel, sample, max_depth=50, seed=1, variant=RT_VARIANT_WAVEFRONT, log_bounces=0):
+        """rt_trace_paths: the production render code run for chosen (pixel, sample) pairs.  Returns
+        (radiance [n,3] f32, nrays [n] i32, term [n] i32, log [n, log_bounces] PATH_BOUNCE_DTYPE | None)."""
+        pix = np.ascontiguousarray(pixel, np.int32)
+        smp = np.ascontiguousarray(sample, np.int32)
+        n = len(pix)
+        rad = np.zeros((n, 3), np.float32)
+        nr = np.zeros(n, np.int32)
+        term = np.zeros(n, np.int32)
+        log = np.zeros((n, log_bounces), PATH_BOUNCE_DTYPE) if log_bounces > 0 else None
+        self._check(self.L.rt_trace_paths(self.h, nx, ny, n, _p(pix, _i32p), _p(smp, _i32p), max_depth, C.c_uint64(seed),
+                                          variant, _p(rad, _f32p), _p(nr, _i32p), _p(term, _i32p), log_bounces,
+                                          None if log is None else log.ctypes.data_as(C.c_void_p)), "rt_trace_paths")
+        return rad, nr, term, log
+
+    def sample_device(self, kind, n, seed=1):
+        """rt_sample_device: n points of the device's rand-in-unit-sphere (kind 0, [n,3]) / rand-in-unit-disk (kind 1, [n,2])."""
+        dim = 3 if kind == 0 else 2
+        out = np.zeros((n, dim), np.float32)
+        self._check(self.L.rt_sample_device(self.h, kind, n, C.c_uint64(seed), _p(out, _f32p)), "rt_sample_device")
+        return out
 
     def set_camera(self, cam_type, camf):
         c = np.ascontiguousarray(camf, np.float32)

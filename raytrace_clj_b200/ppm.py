@@ -30,3 +30,11 @@ def save(path, rgb8: np.ndarray) -> None:
     else:
         from PIL import Image  # noqa: WPS433 (optional dependency, only for non-ppm output)
         Image.fromarray(rgb8, "RGB").save(path)
+
+
+def load(path) -> np.ndarray:
+    """uint8 [ny, nx, 3], row 0 = top: .ppm here, anything else through PIL (texture.clj:135-138 load-image)."""
+    if str(path).lower().endswith(".ppm"):
+        return read_ppm(path)
+    from PIL import Image  # noqa: WPS433
+    return np.asarray(Image.open(path).convert("RGB"), np.uint8)

@@ -1,7 +1,7 @@
 """Material records — mirror of reference src/raytrace_clj/shader.clj.
 
 ``scatter`` / ``emitted`` (shader.clj:22-24) run on the GPU.  Isotropic (shader.clj:129-143) is
-only reachable through ConstantMedium and is outside the accelerated path.
+only reachable through ConstantMedium (hitable.clj:516-543).
 """
 from __future__ import annotations
 
@@ -44,3 +44,12 @@ def dielectric(*, ri):
 
 def diffuse_light(*, tex):
     return DiffuseLight(tex)
+
+
+@dataclass(eq=False)
+class Isotropic:              # shader.clj:129-138 (the scattered ray's time is the hit's t, as written there)
+    albedo: Any
+
+
+def isotropic(*, albedo):
+    return Isotropic(albedo)

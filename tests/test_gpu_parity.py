@@ -514,11 +514,11 @@ def test_error_paths(scene_c2):
         r.set_camera(cam_type, cam)
         with pytest.raises(rt.native.NativeError, match=r"\(-1\)"):       # RT_ERR_ARG
             r.render(0, 8, 1)
-        bad = rt.native.FlatScene(**{k: getattr(flat, k).copy() for k in flat.__dataclass_fields__})
+        bad = flat.copy()
         bad.material_id[3] = 10_000
         with pytest.raises(rt.native.NativeError, match=r"\(-1\)"):
             r.set_scene(bad)
-        bad = rt.native.FlatScene(**{k: getattr(flat, k).copy() for k in flat.__dataclass_fields__})
+        bad = flat.copy()
         bad.mat_type[0] = 9                                               # e.g. Isotropic: outside the path
         with pytest.raises(rt.native.NativeError, match=r"\(-2\)"):       # RT_ERR_UNSUPPORTED
             r.set_scene(bad)

@@ -104,7 +104,7 @@ def test_abi_library_exports_every_declared_symbol():
     for sym in declared:
         assert getattr(lib, sym) is not None
     lib.rt_abi_version.restype = ctypes.c_int
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
