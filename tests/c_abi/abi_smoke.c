@@ -3,11 +3,33 @@
  * answer, one small render.  Exit codes: 0 ok, 3 no CUDA device (the library refuses: there is no CPU fallback),
  * 1 anything else.  Built and run by tests/test_c_abi.py.                                                          */
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "raytrace_b200.h"
+
+/* The JVM binding (clojure/native.clj) fills rt_scene_desc / rt_scene_ext / rt_path_bounce by BYTE OFFSET (JNA Memory
+ * setInt / setPointer).  These literals are the ones native.clj hard-codes: if a field moves, this file stops compiling. */
+#define OFF(type, field, at) _Static_assert(offsetof(type, field) == (at), #type "." #field " moved: update clojure/native.clj")
+_Static_assert(sizeof(rt_scene_desc) == 112, "rt_scene_desc size: update clojure/native.clj");
+OFF(rt_scene_desc, n_spheres, 0);    OFF(rt_scene_desc, center0_r, 8);     OFF(rt_scene_desc, center1, 16);
+OFF(rt_scene_desc, t0t1, 24);        OFF(rt_scene_desc, sphere_flags, 32); OFF(rt_scene_desc, material_id, 40);
+OFF(rt_scene_desc, n_materials, 48); OFF(rt_scene_desc, mat_type, 56);     OFF(rt_scene_desc, mat_param, 64);
+OFF(rt_scene_desc, mat_tex, 72);     OFF(rt_scene_desc, n_textures, 80);   OFF(rt_scene_desc, tex_type, 88);
+OFF(rt_scene_desc, tex_params, 96);  OFF(rt_scene_desc, tex_children, 104);
+_Static_assert(sizeof(rt_scene_ext) == 120, "rt_scene_ext size: update clojure/native.clj");
+OFF(rt_scene_ext, struct_bytes, 0);  OFF(rt_scene_ext, n_boundary, 4);     OFF(rt_scene_ext, prim_type, 8);
+OFF(rt_scene_ext, prim_params, 16);  OFF(rt_scene_ext, prim_aux, 24);      OFF(rt_scene_ext, prim_xform, 32);
+OFF(rt_scene_ext, n_xforms, 40);     OFF(rt_scene_ext, xform_ops, 48);     OFF(rt_scene_ext, xform_params, 56);
+OFF(rt_scene_ext, tie_rule, 64);     OFF(rt_scene_ext, perlin_vectors, 72); OFF(rt_scene_ext, perlin_perm, 80);
+OFF(rt_scene_ext, n_images, 88);     OFF(rt_scene_ext, image_wh, 96);      OFF(rt_scene_ext, image_offset, 104);
+OFF(rt_scene_ext, image_rgb, 112);
+_Static_assert(sizeof(rt_path_bounce) == 40, "rt_path_bounce size");
+OFF(rt_path_bounce, o, 0); OFF(rt_path_bounce, time, 12); OFF(rt_path_bounce, d, 16); OFF(rt_path_bounce, hit_id, 28);
+OFF(rt_path_bounce, t, 32);
+_Static_assert(RT_CTR_COUNT == 24 && RT_ABI_VERSION == 2, "counter block / ABI version: update clojure/native.clj");
 
 #define CHECK(call)                                                                              \
     do {                                                                                         \

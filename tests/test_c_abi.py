@@ -19,12 +19,12 @@ def _build(tmp_path):
     cc = shutil.which("gcc") or shutil.which("cc")
     assert cc, "no C compiler"
     libdir = os.path.dirname(lib)
-    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), SRC,
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), SRC,
                            "-o", exe, "-L", libdir, "-lraytrace_b200", "-lm", f"-Wl,-rpath,{libdir}"])
     return exe
 
 
-def test_header_is_c99_and_library_links_from_c(tmp_path):
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
     exe = _build(tmp_path)
     import torch
 

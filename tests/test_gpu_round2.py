@@ -1,0 +1,451 @@
+"""GPU parity tests added in round 2 (all through the C ABI, against the CPU oracle).
+
+  * DETERMINISTIC multi-bounce parity: rt_trace_paths runs the production kernels (both variants) for chosen
+    (pixel, sample) pairs; the oracle replays the same paths on the same Philox counters (orc_trace_paths).
+    Free-running comparison (bounce count, termination reason, radiance) on >= 1 M paths of BASELINE's own frames,
+    plus a teacher-forced check of every logged bounce (hit id / t bit-exact, scattered ray within FP32 tolerance),
+    which chaos cannot blur.
+  * the device's closed-form ball / disk samplers against the reference's rejection sampling (util.clj:32-52), KS.
+  * a full 1200x800x10 spp frame (BASELINE config 2) and a 256x256 crop of the 3840x2160 frame at 1024 spp
+    (config 3) through the Monte-Carlo RMSE bound.
+  * rectangles / triangles / wrappers / boxes / media / Perlin / image textures (hitable.clj:269-581,
+    texture.clj:60-138): closest hit id equal and t within 1e-5 (bit-exact for everything but media, whose
+    log() differs in the last ulp), shading within FP32 tolerance, renders inside the RMSE bound, both variants.
+"""
+import math
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+import raytrace_clj_b200 as rt
+from raytrace_clj_b200 import hitable as hit
+from raytrace_clj_b200 import shader as shad
+from raytrace_clj_b200 import texture as tex
+from raytrace_clj_b200.util import vec3
+
+from helpers import RNG_DOMAIN, philox4x32_10, u01
+
+pytestmark = pytest.mark.gpu
+
+FMAX = float(np.finfo(np.float32).max)
+
+
+@pytest.fixture(scope="module")
+def renderer():
+    r = rt.native.Renderer([0])
+    yield r
+    r.close()
+
+
+def _rmse(a, b):
+    return float(np.sqrt(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2)))
+
+
+def _load(renderer, sc):
+    flat = rt.native.marshal_world(sc["world"])
+    cam_type, cam = rt.native.marshal_camera(sc["camera"])
+    renderer.set_scene(flat)
+    renderer.set_camera(cam_type, cam)
+    return flat, cam_type, cam, oracle.Scene(flat)
+
+
+def _compare_paths(g, o, label, min_same=0.999, min_close=0.999):
+    """g, o = (radiance, nrays, term, log) of the GPU and of the oracle replay."""
+    same = (g[1] == o[1]) & (g[2] == o[2])
+    ref = o[0]
+    err = np.abs(g[0].astype(np.float64) - ref).max(axis=1)
+    scale = np.maximum(np.abs(ref).max(axis=1), 1e-2)
+    close = same & (err <= 1e-3 * scale)
+    print(f"[paths] {label}: {len(same)} paths, same (bounces, termination) {same.mean():.5f}, "
+          f"of those radiance within 1e-3 rel {close.sum() / max(1, same.sum()):.5f}; mean rays/path gpu {g[1].mean():.3f} "
+          f"oracle {o[1].mean():.3f}; mean radiance gpu {g[0].mean():.5f} oracle {ref.mean():.5f}")
+    assert same.mean() >= min_same, (label, same.mean())
+    assert close.sum() / max(1, same.sum()) >= min_close, (label, close.sum() / same.sum())
+    # the paths that diverged (a hit / miss or a Schlick coin decided differently in FP32) are unbiased
+    assert abs(g[0].mean() - ref.mean()) < 0.01 * max(ref.mean(), 1e-3) + 5 * ref.std() / math.sqrt(len(ref))
+    return same
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("workload", ["c2", "c4"])
+def test_trace_paths_replay_on_baseline_frames(renderer, workload, variant):
+    """>= 1 M sampled paths of BASELINE config 2 (1200x800 random spheres) / config 4 (metal / glass heavy), depth 50:
+    the production kernels and the oracle replay agree path for path."""
+    nx, ny = 1200, 800
+    if workload == "c2":
+        sc, spp = rt.scene.make_random_scene(nx, ny, 11, True, random.Random(1)), 10
+    else:
+        sc, spp = rt.scene.make_material_stress_scene(nx, ny, 11, random.Random(4)), 64
+    flat, cam_type, cam, S = _load(renderer, sc)
+    n = 1_048_576 if variant == 1 else 262_144
+    g = np.random.default_rng(17 + variant)
+    pix = g.integers(0, nx * ny, n).astype(np.int32)
+    smp = g.integers(0, spp, n).astype(np.int32)
+    got = renderer.trace_paths(nx, ny, pix, smp, 50, seed=7, variant=variant)
+    ref = S.trace_paths(cam_type, cam, nx, ny, pix, smp, 50, seed=7)
+    # C4's long specular chains amplify FP32 rounding bounce after bounce: the free-running agreement is lower there
+    # (the teacher-forced test below checks every bounce on its own)
+    _compare_paths(got, ref, f"{workload} variant {variant}", min_same=0.999 if workload == "c2" else 0.99,
+                   min_close=0.999 if workload == "c2" else 0.99)
+    assert got[1].min() >= 1 and got[1].max() <= 51 and set(np.unique(got[2])) <= {1, 2, 3, 4}
+
+
+def _ball_from_philox(seed, pixel, sample, bounce):
+    """the device's rand_in_unit_sphere / scatter rand of (pixel, sample, bounce): block 1 (rt_device.cuh)."""
+    n = len(pixel)
+    ctr = np.stack([np.asarray(pixel, np.uint32), np.asarray(sample, np.uint32),
+                    (np.asarray(bounce, np.uint32) << np.uint32(16)) | np.uint32(1), np.full(n, RNG_DOMAIN, np.uint32)], axis=1)
+    key = np.tile(np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], np.uint32), (n, 1))
+    b = philox4x32_10(ctr, key)
+    ux, uy, uz, uw = (u01(b[:, k]).astype(np.float64) for k in range(4))
+    rad, z = np.cbrt(ux), 1.0 - 2.0 * uy
+    s = np.sqrt(np.maximum(0.0, 1.0 - z * z)) * rad
+    phi = 2.0 * np.pi * uz
+    return np.stack([s * np.cos(phi), s * np.sin(phi), z * rad], axis=1).astype(np.float32), uw.astype(np.float32)
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_bounce_log_teacher_forced(renderer, variant):
+    """Every logged bounce of the production kernels checked ON ITS OWN (no error accumulates along the path): the
+    oracle's hit? on the logged ray gives the logged (id, t) bit for bit; the oracle's scatter fed the same Philox
+    draws gives the next logged ray within FP32 shading tolerance; the path ends where the oracle ends it."""
+    nx, ny = 1200, 800
+    sc = rt.scene.make_material_stress_scene(nx, ny, 11, random.Random(4))
+    flat, cam_type, cam, S = _load(renderer, sc)
+    n, LB = 150_000, 12
+    g = np.random.default_rng(23)
+    pix = g.integers(0, nx * ny, n).astype(np.int32)
+    smp = g.integers(0, 64, n).astype(np.int32)
+    rad, nr, term, log = renderer.trace_paths(nx, ny, pix, smp, 50, seed=11, variant=variant, log_bounces=LB)
+    valid = log["hit_id"] != -2
+    assert np.array_equal(valid.sum(axis=1), np.minimum(nr, LB))               # exactly the rays the path traced
+    q, b = np.nonzero(valid)
+    o, d, tm = log["o"][q, b], log["d"][q, b], log["time"][q, b]
+    t_ref, id_ref = S.hit(o, d, tm, 0.001, FMAX)
+    assert np.array_equal(id_ref, log["hit_id"][q, b])
+    hitm = id_ref >= 0
+    assert np.array_equal(t_ref[hitm], log["t"][q, b][hitm]) and np.all(np.isinf(log["t"][q, b][~hitm]))
+    # first logged ray = get-ray of (pixel, sample) (camera.clj:35-48)
+    go, gd, gt, _ = renderer.generate_rays(nx, ny, np.stack([pix % nx, pix // nx], axis=1), smp, seed=11)
+    assert np.array_equal(log["o"][:, 0], go) and np.array_equal(log["d"][:, 0], gd) and np.array_equal(log["time"][:, 0], gt)
+    # scatter: bounces that have a successor in the log
+    has_next = np.zeros_like(valid)
+    has_next[:, :-1] = valid[:, 1:]
+    q, b = np.nonzero(valid & has_next)
+    ball, uw = _ball_from_philox(11, pix[q], smp[q], b + 1)
+    ref = S.shade_batch(log["o"][q, b], log["d"][q, b], log["time"][q, b], log["hit_id"][q, b], ball, uw)
+    no, nd = log["o"][q, b + 1], log["d"][q, b + 1]
+    cont = ref["flags"] == 1
+    # a continuing path the oracle would have ended (grazing metal reflection) or a flipped Schlick coin: FP32 threshold cases
+    scale = np.maximum(1.0, np.linalg.norm(ref["dir"], axis=1))
+    good = cont & (np.abs(nd - ref["dir"]).max(axis=1) <= 3e-4 * scale) & (np.abs(no - ref["origin"]).max(axis=1) <= 3e-4)
+    print(f"[teacher-forced] variant {variant}: {len(q)} scatters checked, {1 - good.mean():.2e} threshold flips")
+    assert good.mean() > 0.9995
+    # the last ray of each finished path: the oracle ends it the same way
+    fin = np.nonzero(nr <= LB)[0]
+    lb = nr[fin] - 1
+    lo, ld, lt, lid = log["o"][fin, lb], log["d"][fin, lb], log["time"][fin, lb], log["hit_id"][fin, lb]
+    assert np.array_equal(lid < 0, term[fin] == rt.native.RT_TERM_MISS)
+    ball, uw = _ball_from_philox(11, pix[fin], smp[fin], lb + 1)
+    ref = S.shade_batch(lo, ld, lt, lid, ball, uw)
+    ended = (ref["flags"] == 0) | (lid < 0) | (nr[fin] == 51)
+    assert ended.mean() > 0.9995
+    types = np.where(lid >= 0, flat.mat_type[flat.material_id[np.maximum(lid, 0)]], -1)
+    assert np.all(types[term[fin] == rt.native.RT_TERM_LIGHT] == rt.native.RT_MAT_DIFFUSE_LIGHT)
+    absorbed = term[fin] == rt.native.RT_TERM_ABSORB
+    assert absorbed.sum() > 100 and np.all(types[absorbed] == rt.native.RT_MAT_METAL)
+
+
+def _ks(a, b):
+    a, b = np.sort(a), np.sort(b)
+    allv = np.concatenate([a, b])
+    return float(np.abs(np.searchsorted(a, allv, side="right") / len(a) - np.searchsorted(b, allv, side="right") / len(b)).max())
+
+
+def test_device_samplers_match_rejection_sampling(renderer):
+    """rand_in_unit_sphere / rand_in_unit_disk of rt_device.cuh (closed form, one Philox block) against the reference's
+    rejection loops (util.clj:32-52) run by the oracle: KS on radius, cos(theta), phi and the Cartesian marginals; and
+    point for point against the oracle's closed-form map on the same counters."""
+    n = 400_000
+    crit = 1.95 * math.sqrt(2.0 / n)
+    dev = renderer.sample_device(0, n, seed=3).astype(np.float64)
+    rej = oracle.sample_ball(n, seed=99, replay=False)
+    assert np.linalg.norm(dev, axis=1).max() < 1.0
+    for f in (lambda p: np.linalg.norm(p, axis=1), lambda p: p[:, 2] / np.linalg.norm(p, axis=1),
+              lambda p: np.arctan2(p[:, 1], p[:, 0]), lambda p: p[:, 0], lambda p: p[:, 1], lambda p: p[:, 2]):
+        assert _ks(f(dev), f(rej)) < crit
+    assert np.abs(dev - oracle.sample_ball(n, seed=3, replay=True)).max() < 2e-6
+    dev = renderer.sample_device(1, n, seed=5).astype(np.float64)
+    rej = oracle.sample_disk(n, seed=77, replay=False)
+    assert np.linalg.norm(dev, axis=1).max() < 1.0
+    for f in (lambda p: np.linalg.norm(p, axis=1), lambda p: np.arctan2(p[:, 1], p[:, 0]), lambda p: p[:, 0], lambda p: p[:, 1]):
+        assert _ks(f(dev), f(rej)) < crit
+    assert np.abs(dev - oracle.sample_disk(n, seed=5, replay=True)).max() < 2e-6
+
+
+def _rmse_bound_check(g1, g2, o1, o2, label, npix):
+    r_gg, r_oo = _rmse(g1, g2), _rmse(o1, o2)
+    cross = [_rmse(g, o) for g in (g1, g2) for o in (o1, o2)]
+    bound = 1.25 * math.sqrt((r_gg ** 2 + r_oo ** 2) / 2)
+    print(f"[parity] {label}: RMSE cross {max(cross):.4f} <= bound {bound:.4f} (R_gg {r_gg:.4f}, R_oo {r_oo:.4f})")
+    assert max(cross) <= bound, (cross, r_gg, r_oo)
+    assert 0.8 < r_gg / r_oo < 1.25
+    ax = tuple(range(g1.ndim - 1))
+    sigma = np.sqrt(((o1 - o2) ** 2).mean(axis=ax) / 2 + ((g1 - g2) ** 2).mean(axis=ax) / 2)
+    mean_diff = np.abs((g1 + g2).mean(axis=ax) / 2 - (o1 + o2).mean(axis=ax) / 2)
+    assert np.all(mean_diff <= 3 * sigma / math.sqrt(npix) + 2e-4), (mean_diff, sigma)
+
+
+def test_full_c2_frame_matches_oracle(renderer):
+    """BASELINE config 2 at its own size: 1200x800, 10 spp, depth 50 (9.6 M paths per render), wavefront variant."""
+    nx, ny, ns = 1200, 800, 10
+    flat, cam_type, cam, S = _load(renderer, rt.scene.make_random_scene(nx, ny, 11, True, random.Random(1)))
+    g1, _ = renderer.render(nx, ny, ns, 50, seed=101, rgb8=False)
+    g2, _ = renderer.render(nx, ny, ns, 50, seed=202, rgb8=False)
+    o1 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, 50, seed=303)[0] / ns
+    o2 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, 50, seed=404)[0] / ns
+    _rmse_bound_check(g1, g2, o1, o2, "c2 full frame 1200x800x10", nx * ny)
+    # and the SAME frame sample for sample: the oracle replaying the GPU's Philox counters (seed 101)
+    o3 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, 50, seed=101, replay=True)[0] / ns
+    d = np.abs(g1 - o3).max(axis=2)
+    print(f"[parity] c2 full frame, replay of the same seed: pixels within 1e-3: {(d <= 1e-3).mean():.5f}, RMSE {_rmse(g1, o3):.5f}")
+    assert (d <= 1e-3).mean() > 0.99 and _rmse(g1, o3) < 0.25 * _rmse(g1, o1)
+
+
+def test_c3_crop_1024spp_matches_oracle(renderer):
+    """BASELINE config 3's frame (3840x2160, 1024 spp): a 256x256 crop around the three hero spheres, all 1024 samples
+    of every pixel of the crop, through rt_trace_paths (the production kernels) vs the oracle, RMSE bound."""
+    nx, ny, ns, C = 3840, 2160, 1024, 256
+    flat, cam_type, cam, S = _load(renderer, rt.scene.make_random_scene(nx, ny, 11, True, random.Random(1)))
+    i0, j0 = nx // 2 - C // 2, ny // 2 - C // 2 - 100
+    jj, ii = np.meshgrid(np.arange(j0, j0 + C), np.arange(i0, i0 + C), indexing="ij")
+    crop_pix = (jj * nx + ii).reshape(-1).astype(np.int32)
+
+    def crop(fn, seed):
+        acc = np.zeros((C * C, 3), np.float64)
+        step = 64
+        for s0 in range(0, ns, step):
+            pix = np.repeat(crop_pix, step)
+            smp = np.tile(np.arange(s0, s0 + step, dtype=np.int32), C * C)
+            rad = fn(pix, smp, seed)
+            acc += np.asarray(rad, np.float64).reshape(C * C, step, 3).sum(axis=1)
+        return (acc / ns).reshape(C, C, 3)
+
+    gpu = lambda pix, smp, seed: renderer.trace_paths(nx, ny, pix, smp, 50, seed=seed)[0]          # noqa: E731
+    cpu = lambda pix, smp, seed: S.trace_paths(cam_type, cam, nx, ny, pix, smp, 50, seed=seed)[0]   # noqa: E731
+    g1, g2 = crop(gpu, 1), crop(gpu, 2)
+    o1, o2 = crop(cpu, 3), crop(cpu, 4)
+    _rmse_bound_check(g1, g2, o1, o2, "c3 256x256 crop at 1024 spp", C * C)
+
+
+# ---- f-2: rectangles, triangles, boxes, wrappers ------------------------------------------------------------------
+def _assert_hits(t_gpu, id_gpu, t_ref, id_ref, exact=True):
+    assert np.array_equal(id_gpu, id_ref), f"{int((id_gpu != id_ref).sum())} of {len(id_ref)} ids differ"
+    h = id_ref >= 0
+    assert np.all(np.isinf(t_gpu[~h]))
+    rel = np.abs(t_gpu[h] - t_ref[h]) / np.abs(t_ref[h])
+    assert rel.max(initial=0.0) <= 1e-5
+    if exact:
+        assert np.array_equal(t_gpu[h], t_ref[h])
+
+
+def _rays_at(flat, S, g, n, origin_box, jitter=1e-6):
+    """n rays from random origins aimed at random points of random leaves' bounding boxes — including their edges and
+    corners (+- jitter), where the inclusive / strict tests decide."""
+    k = g.integers(0, flat.n_spheres, n)
+    bb = np.array([S.prim_bbox(i) for i in range(flat.n_spheres)])
+    lo, hi = bb[k, :3], bb[k, 3:]
+    w = g.random((n, 3))
+    snap = g.random((n, 3))
+    w = np.where(snap < 0.15, 0.0, np.where(snap > 0.85, 1.0, w))       # 30 % of the coordinates sit ON a box face / edge
+    target = lo + w * (hi - lo) + g.normal(scale=jitter, size=(n, 3)) * (hi - lo + 1e-3)
+    o = g.uniform(origin_box[0], origin_box[1], size=(n, 3))
+    d = (target - o) * g.uniform(0.3, 3.0, size=(n, 1))
+    return o.astype(np.float32), d.astype(np.float32), g.random(n).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["cornell", "triangles", "light", "boxes"])
+def test_trace_primary_new_primitives(renderer, name):
+    """id equal and t bit-identical to the oracle on >= 200 k rays per scene, incl. edge-on and edge-grazing rays."""
+    rng = random.Random(3)
+    if name == "cornell":
+        sc, box = rt.scene.make_cornell_box(100, 100, True, rng), ((-100, -100, -900), (655, 655, 655))
+    elif name == "triangles":
+        sc, box = rt.scene.make_two_triangles(100, 100, rng), ((-3, -3, -12), (5, 5, 12))
+    elif name == "light":
+        sc, box = rt.scene.make_example_light(100, 100, rng), ((-15, -2, -15), (15, 12, 15))
+    else:   # many small rotated / translated boxes + triangles in a Hitlist: hundreds of generic leaves through the cull
+        items = []
+        m = shad.lambertian(albedo=tex.constant(color=vec3(.7, .7, .7)))
+        for _ in range(60):
+            p1 = vec3(rng.uniform(.2, 1.5), rng.uniform(.2, 1.5), rng.uniform(.2, 1.5))
+            b = hit.box(p0=vec3(0, 0, 0), p1=p1, material=m)
+            items.append(hit.translate(item=hit.rotate_y(item=b, theta=rng.uniform(-90, 90)),
+                                       offset=vec3(rng.uniform(-10, 10), rng.uniform(0, 3), rng.uniform(-10, 10))))
+        for _ in range(60):
+            v0 = vec3(rng.uniform(-10, 10), rng.uniform(0, 4), rng.uniform(-10, 10))
+            items.append(hit.triangle(v0=v0, v1=v0 + vec3(rng.uniform(-1, 1), rng.uniform(.2, 1), rng.uniform(-1, 1)),
+                                      v2=v0 + vec3(rng.uniform(.2, 1), rng.uniform(-1, 1), rng.uniform(-1, 1)), material=m))
+        items.append(hit.sphere(center=vec3(0, -1000, 0), radius=1000, material=m))
+        sc = {"world": hit.hitlist(items=items), "camera": rt.scene.make_two_spheres(100, 100)["camera"]}
+        box = ((-14, -1, -14), (14, 8, 14))
+    flat, cam_type, cam, S = _load(renderer, sc)
+    g = np.random.default_rng(5)
+    n = 220_000
+    o, d, tm = _rays_at(flat, S, g, n, box)
+    t_ref, id_ref = S.hit(o, d, tm, 0.001, FMAX)
+    t_gpu, id_gpu = renderer.trace_primary(o, d, tm, 0.001, FMAX)
+    _assert_hits(t_gpu, id_gpu, t_ref, id_ref)
+    assert (id_ref >= 0).mean() > 0.3
+    kinds = set(flat.prim_type[np.unique(id_ref[id_ref >= 0])].tolist())
+    assert kinds >= {"cornell": {1, 2, 3}, "triangles": {0, 4}, "light": {0, 1}, "boxes": {0, 1, 2, 3, 4}}[name]
+    # edge-on: rays lying IN a rectangle's plane (t = 0/0 or +-inf: the reference's comparisons reject them)
+    if name == "cornell":
+        oo = np.array([[278, 0, -800], [0, 278, -800], [278, 555, -800]], np.float32)
+        dd = np.array([[0, 0, 1], [0, 0, 1], [0.1, 0, 1]], np.float32)
+        _assert_hits(*renderer.trace_primary(oo, dd, None, 0.001, FMAX), *S.hit(oo, dd, None, 0.001, FMAX))
+    # secondary rays from the hit points (self-intersection at t_min = 0.001 on flat primitives)
+    h = id_ref >= 0
+    p = (o[h].astype(np.float64) + t_ref[h][:, None] * d[h].astype(np.float64)).astype(np.float32)
+    nd = g.normal(size=p.shape).astype(np.float32)
+    _assert_hits(*renderer.trace_primary(p, nd, tm[h], 0.001, FMAX), *S.hit(p, nd, tm[h], 0.001, FMAX))
+    # the FP32 cull (bounding spheres of the leaves) never loses a pair the exact test accepts
+    lost, surv, cand = renderer.cull_check(o[:60000], d[:60000], tm[:60000], 0.001, FMAX)
+    assert lost == 0 and surv >= cand
+
+
+def test_shade_batch_new_primitives(renderer):
+    """hit records of rectangles / triangles / wrapped boxes (p, normal through RotateY / FlipNormals, uv) feeding the
+    scatter functions: scattered ray, attenuation, emitted vs the oracle with caller-given randoms."""
+    flat, cam_type, cam, S = _load(renderer, rt.scene.make_cornell_box(100, 100, True, random.Random(3)))
+    g = np.random.default_rng(6)
+    o, d, tm = _rays_at(flat, S, g, 60_000, ((100, 100, -800), (455, 455, 500)), jitter=0)
+    t, ids = S.hit(o, d, tm)
+    keep = ids >= 0
+    o, d, tm, t, ids = o[keep], d[keep], tm[keep], t[keep], ids[keep]
+    ball = g.uniform(-1, 1, size=(len(o), 3))
+    ball *= (g.random(len(o)) ** (1 / 3) / np.linalg.norm(ball, axis=1))[:, None]
+    u = g.random(len(o)).astype(np.float32)
+    got = renderer.shade_batch(o, d, tm, ids, t, ball.astype(np.float32), u)
+    ref = S.shade_batch(o, d, tm, ids, ball.astype(np.float32), u)
+    assert np.array_equal(got["flags"], ref["flags"])
+    c = ref["flags"] == 1
+    assert c.sum() > 10_000 and (~c).sum() > 50                   # Lambertian walls scatter, the light does not
+    assert np.allclose(got["dir"][c], ref["dir"][c], atol=2e-4)
+    assert np.allclose(got["origin"][c], ref["origin"][c], rtol=1e-6, atol=2e-3)   # coordinates up to 555
+    assert np.allclose(got["atten"][c], ref["atten"][c], atol=1e-6) and np.allclose(got["emitted"], ref["emitted"], atol=1e-6)
+    assert len(np.unique(ids)) >= 15                             # walls, light and both rotated blocks' faces
+
+
+def _render_parity(renderer, sc, nx, ny, ns, variant, label, depth=50):
+    flat, cam_type, cam, S = _load(renderer, sc)
+    g1, img = renderer.render(nx, ny, ns, depth, seed=101, variant=variant)
+    g2, _ = renderer.render(nx, ny, ns, depth, seed=202, variant=variant)
+    o1 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, depth, seed=303)[0] / ns
+    o2 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, depth, seed=404)[0] / ns
+    assert np.isfinite(g1).all()
+    _rmse_bound_check(g1, g2, o1, o2, f"{label} {nx}x{ny}x{ns} variant {variant}", nx * ny)
+    return flat, cam_type, cam, S
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("name", ["cornell", "triangles", "light"])
+def test_render_new_primitive_scenes(renderer, name, variant):
+    """make-cornell-box classic (scene.clj:230), make-two-triangles (:80), make-example-light (:191)."""
+    rng = random.Random(2)
+    if name == "cornell":
+        _render_parity(renderer, rt.scene.make_cornell_box(96, 96, True, rng), 96, 96, 256, variant, "cornell box")
+    elif name == "triangles":
+        _render_parity(renderer, rt.scene.make_two_triangles(120, 80, rng), 120, 80, 64, variant, "two triangles")
+    else:
+        _render_parity(renderer, rt.scene.make_example_light(120, 80, rng), 120, 80, 256, variant, "example light")
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_cornell_paths_replay(renderer, variant):
+    """Deterministic path replay on the Cornell box (long diffuse paths between rectangles and rotated boxes)."""
+    nx = ny = 200
+    flat, cam_type, cam, S = _load(renderer, rt.scene.make_cornell_box(nx, ny, True, random.Random(2)))
+    g = np.random.default_rng(31)
+    n = 200_000
+    pix = g.integers(0, nx * ny, n).astype(np.int32)
+    smp = g.integers(0, 256, n).astype(np.int32)
+    got = renderer.trace_paths(nx, ny, pix, smp, 50, seed=5, variant=variant)
+    ref = S.trace_paths(cam_type, cam, nx, ny, pix, smp, 50, seed=5)
+    _compare_paths(got, ref, f"cornell variant {variant}", min_same=0.995, min_close=0.995)
+
+
+# ---- f-4: media, Perlin, image maps ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("name", ["perlin", "earth", "subsurface", "smoke", "final"])
+def test_render_volume_and_texture_scenes(renderer, name, variant):
+    rng = random.Random(2)
+    if name == "perlin":
+        _render_parity(renderer, rt.scene.make_two_perlin_spheres(120, 80, rng), 120, 80, 64, variant, "two perlin spheres")
+    elif name == "earth":
+        _render_parity(renderer, rt.scene.make_textured_sphere(120, 80, rng), 120, 80, 64, variant, "textured sphere")
+    elif name == "subsurface":
+        _render_parity(renderer, rt.scene.make_subsurface_sphere(120, 80, rng), 120, 80, 128, variant, "subsurface sphere")
+    elif name == "smoke":
+        _render_parity(renderer, rt.scene.make_cornell_box(80, 80, False, rng), 80, 80, 256, variant, "cornell smoke")
+    else:
+        _render_parity(renderer, rt.scene.make_final(96, 96, rng, nb=8, ns=200), 96, 96, 256, variant, "final (book 2)")
+
+
+def test_texture_samples_on_device(renderer):
+    """Perlin turbulence / marble / flipped image map evaluated by the shading kernel vs the oracle (FP32 noise)."""
+    img = rt.scene.synthetic_earth(64, 32)
+    mats = [shad.lambertian(albedo=tex.perlin_turbulence(scale=4, depth=7)),
+            shad.lambertian(albedo=tex.marble(scale=0.1, depth=4)),
+            shad.lambertian(albedo=tex.perlin_noise(scale=3)),
+            shad.lambertian(albedo=tex.flip_texture_v(tex=tex.image_map(image=img)))]
+    items = [hit.uv_sphere(center=vec3(3.0 * k, 0, 0), radius=1, material=m) for k, m in enumerate(mats)]
+    flat = rt.native.marshal_world(hit.hitlist(items=items))
+    renderer.set_scene(flat)
+    S = oracle.Scene(flat)
+    g = np.random.default_rng(8)
+    n = 40_000
+    k = g.integers(0, 4, n)
+    dirs = g.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    o = (np.stack([3.0 * k, 0 * k, 0 * k], axis=1) + 4.0 * dirs).astype(np.float32)
+    d = (-dirs).astype(np.float32)
+    tm = np.zeros(n, np.float32)
+    t, ids = S.hit(o, d, tm)
+    assert np.array_equal(ids, k)
+    ball = np.zeros((n, 3), np.float32)
+    got = renderer.shade_batch(o, d, tm, ids, t, ball, np.zeros(n, np.float32))
+    ref = S.shade_batch(o, d, tm, ids, ball, np.zeros(n, np.float32))
+    err = np.abs(got["atten"] - ref["atten"]).max(axis=1)
+    for kk, tol in ((0, 5e-3), (1, 5e-3), (2, 1e-4)):
+        assert err[k == kk].max() < tol, (kk, err[k == kk].max())
+        assert ref["atten"][k == kk].std() > 0.02                 # the texture really varies
+    # image map: a texel boundary may fall between the FP32 and the double uv: all but a sliver agree exactly
+    assert (err[k == 3] < 1e-6).mean() > 0.995
+
+
+def test_medium_hits_on_device(renderer):
+    """ConstantMedium.hit? (hitable.clj:516-543) in the FP64 refine: a fog ball and a fog box (rotated, translated),
+    rays from outside, from inside, grazing; the medium's `rand` is 0.5 without a path (as in the oracle)."""
+    ball = hit.sphere(center=vec3(0, 0, 0), radius=2, material=shad.dielectric(ri=1.5))
+    blk = hit.translate(item=hit.rotate_y(item=hit.box(p0=vec3(0, 0, 0), p1=vec3(2, 3, 2), material=None), theta=30.0),
+                        offset=vec3(5, -1, 0))
+    world = hit.hitlist(items=[hit.constant_medium(boundary=ball, density=0.4, albedo=tex.constant(color=vec3(.2, .4, .9))),
+                               hit.constant_medium(boundary=blk, density=0.7, albedo=tex.constant(color=vec3(1, 1, 1)))])
+    flat = rt.native.marshal_world(world)
+    renderer.set_scene(flat)
+    S = oracle.Scene(flat)
+    g = np.random.default_rng(4)
+    n = 100_000
+    o = g.uniform(-6, 10, size=(n, 3)).astype(np.float32)
+    o[: n // 4] = (g.normal(size=(n // 4, 3)) * 0.8).astype(np.float32)                 # inside the ball
+    target = np.where(g.random((n, 1)) < 0.5, [0, 0, 0], [6, 0.5, 1]) + g.normal(scale=1.0, size=(n, 3))
+    d = ((target - o) * g.uniform(0.2, 2.0, size=(n, 1))).astype(np.float32)
+    t_ref, id_ref = S.hit(o, d, None, 0.001, FMAX)
+    t_gpu, id_gpu = renderer.trace_primary(o, d, None, 0.001, FMAX)
+    assert (id_ref == 0).sum() > 5000 and (id_ref == 1).sum() > 5000 and (id_ref < 0).sum() > 5000
+    _assert_hits(t_gpu, id_gpu, t_ref, id_ref, exact=False)        # log() may differ in the last ulp: 1e-5 relative, not bit-exact
+    h = id_ref >= 0
+    assert (t_gpu[h] == t_ref[h]).mean() > 0.9
