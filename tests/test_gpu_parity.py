@@ -338,6 +338,7 @@ def _render_parity(renderer, flat, cam_type, cam, nx, ny, ns, depth=50, variant=
     renderer.set_camera(cam_type, cam)
     g1, img1 = renderer.render(nx, ny, ns, depth, seed=101, variant=variant)
     g2, _ = renderer.render(nx, ny, ns, depth, seed=202, variant=variant)
+    g1, g2 = g1.astype(np.float64), g2.astype(np.float64)      # reduce in double (float32 sums over many pixels drift)
     o1 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, depth, seed=303)[0] / ns
     o2 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, depth, seed=404)[0] / ns
     r_gg, r_oo = _rmse(g1, g2), _rmse(o1, o2)

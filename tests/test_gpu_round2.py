@@ -60,11 +60,12 @@ def _compare_paths(g, o, label, min_same=0.999, min_close=0.999):
     close = same & (err <= 1e-3 * scale)
     print(f"[paths] {label}: {len(same)} paths, same (bounces, termination) {same.mean():.5f}, "
           f"of those radiance within 1e-3 rel {close.sum() / max(1, same.sum()):.5f}; mean rays/path gpu {g[1].mean():.3f} "
-          f"oracle {o[1].mean():.3f}; mean radiance gpu {g[0].mean():.5f} oracle {ref.mean():.5f}")
+          f"oracle {o[1].mean():.3f}; mean radiance gpu {g[0].astype(np.float64).mean():.6f} oracle {ref.mean():.6f}")
     assert same.mean() >= min_same, (label, same.mean())
     assert close.sum() / max(1, same.sum()) >= min_close, (label, close.sum() / same.sum())
     # the paths that diverged (a hit / miss or a Schlick coin decided differently in FP32) are unbiased
-    assert abs(g[0].mean() - ref.mean()) < 0.01 * max(ref.mean(), 1e-3) + 5 * ref.std() / math.sqrt(len(ref))
+    dm = np.abs((g[0].astype(np.float64) - ref).mean(axis=0))
+    assert np.all(dm < 5 * ref.std(axis=0) / math.sqrt(len(ref)) + 1e-5), dm
     return same
 
 
@@ -186,6 +187,7 @@ def test_device_samplers_match_rejection_sampling(renderer):
 
 
 def _rmse_bound_check(g1, g2, o1, o2, label, npix):
+    g1, g2, o1, o2 = (np.asarray(x, np.float64) for x in (g1, g2, o1, o2))   # float32 sums over ~1e6 pixels lose 1e-3
     r_gg, r_oo = _rmse(g1, g2), _rmse(o1, o2)
     cross = [_rmse(g, o) for g in (g1, g2) for o in (o1, o2)]
     bound = 1.25 * math.sqrt((r_gg ** 2 + r_oo ** 2) / 2)
@@ -209,7 +211,7 @@ def test_full_c2_frame_matches_oracle(renderer):
     _rmse_bound_check(g1, g2, o1, o2, "c2 full frame 1200x800x10", nx * ny)
     # and the SAME frame sample for sample: the oracle replaying the GPU's Philox counters (seed 101)
     o3 = S.render_accumulate(cam_type, cam, nx, ny, 0, ns, 50, seed=101, replay=True)[0] / ns
-    d = np.abs(g1 - o3).max(axis=2)
+    d = np.abs(g1.astype(np.float64) - o3).max(axis=2)
     print(f"[parity] c2 full frame, replay of the same seed: pixels within 1e-3: {(d <= 1e-3).mean():.5f}, RMSE {_rmse(g1, o3):.5f}")
     assert (d <= 1e-3).mean() > 0.99 and _rmse(g1, o3) < 0.25 * _rmse(g1, o1)
 
@@ -401,7 +403,7 @@ def test_texture_samples_on_device(renderer):
             shad.lambertian(albedo=tex.marble(scale=0.1, depth=4)),
             shad.lambertian(albedo=tex.perlin_noise(scale=3)),
             shad.lambertian(albedo=tex.flip_texture_v(tex=tex.image_map(image=img)))]
-    items = [hit.uv_sphere(center=vec3(3.0 * k, 0, 0), radius=1, material=m) for k, m in enumerate(mats)]
+    items = [hit.uv_sphere(center=vec3(20.0 * k, 0, 0), radius=1, material=m) for k, m in enumerate(mats)]
     flat = rt.native.marshal_world(hit.hitlist(items=items))
     renderer.set_scene(flat)
     S = oracle.Scene(flat)
@@ -410,7 +412,7 @@ def test_texture_samples_on_device(renderer):
     k = g.integers(0, 4, n)
     dirs = g.normal(size=(n, 3))
     dirs /= np.linalg.norm(dirs, axis=1)[:, None]
-    o = (np.stack([3.0 * k, 0 * k, 0 * k], axis=1) + 4.0 * dirs).astype(np.float32)
+    o = (np.stack([20.0 * k, 0 * k, 0 * k], axis=1) + 4.0 * dirs).astype(np.float32)
     d = (-dirs).astype(np.float32)
     tm = np.zeros(n, np.float32)
     t, ids = S.hit(o, d, tm)
