@@ -33,8 +33,6 @@ constexpr int kTileCap = 4096; // float4 slots of the shared-memory sphere tile 
 
 thread_local std::string g_create_error;
 
-constexpr int kMaxLanes = 2;
-
 struct DeviceBuffers {
     int dev = 0;
     cudaStream_t stream = nullptr;
@@ -59,13 +57,14 @@ struct DeviceBuffers {
         double* cand_t = nullptr;
         unsigned* cand_count = nullptr;
         WaveState* state = nullptr;
-        WaveState* h_state = nullptr;       // pinned, 2 snapshots
-        cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+        LaneStatus* h_status = nullptr;     // pinned + mapped: written by the device (publish_status), polled by the host
+        LaneStatus* d_status = nullptr;     // its device address
         cudaEvent_t ev_done = nullptr;
         cudaStream_t stream = nullptr;      // lane 0 runs on the caller's stream, the others on their own
         cudaStream_t stage_stream = nullptr;   // high priority: refine / tie-break / shade of this lane (RT_CULL_CLAIMS > 0)
         cudaEvent_t ev_culled = nullptr, ev_shaded = nullptr;
         size_t entries = 0;
+        bool best_clean = false;            // every closest-hit word is (+inf, MISS): true after a render ran to completion
     } lanes[kMaxLanes];
     cudaEvent_t ev_lane_start = nullptr;
     // timeline trace (RT_TRACE): one record per wavefront kernel launch of the last render
@@ -99,6 +98,7 @@ struct Options {
     int common_origin = 1;            // RT_COMMON_ORIGIN
     int reduce = 0;                   // multi-device rt_render: 0 = NVLink peer loads inside the resolve kernel, 1 = ncclReduce
     int rows = 0;                     // multi-device partition: 0 = sample slices, 1 = interleaved rows
+    int wave_depth = 3;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
 };
 
 struct rt_ctx {
@@ -172,7 +172,6 @@ int ensure_frame(rt_ctx* ctx, DeviceBuffers& d, size_t px) {
     return RT_OK;
 }
 
-constexpr int kWaveChunk = 4;           // iterations enqueued between two polls of the queue count
 
 void free_lane(DeviceBuffers::WaveLane& L) {
     if (L.queue) cudaFree(L.queue);
@@ -189,9 +188,7 @@ void free_wave(DeviceBuffers& d) {
     for (auto& L : d.lanes) {
         free_lane(L);
         if (L.state) cudaFree(L.state);
-        if (L.h_state) cudaFreeHost(L.h_state);
-        for (auto& e : L.ev_poll)
-            if (e) cudaEventDestroy(e);
+        if (L.h_status) cudaFreeHost(L.h_status);
         if (L.ev_done) cudaEventDestroy(L.ev_done);
         if (L.stream) cudaStreamDestroy(L.stream);
         if (L.stage_stream) cudaStreamDestroy(L.stage_stream);
@@ -209,8 +206,8 @@ int ensure_lane(rt_ctx* ctx, DeviceBuffers& d, int lane, size_t entries) {
     DeviceBuffers::WaveLane& L = d.lanes[lane];
     if (!L.state) {
         RT_CUDA(ctx, cudaMalloc(&L.state, sizeof(WaveState)));
-        RT_CUDA(ctx, cudaHostAlloc(&L.h_state, 2 * sizeof(WaveState), cudaHostAllocDefault));
-        for (auto& e : L.ev_poll) RT_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        RT_CUDA(ctx, cudaHostAlloc(&L.h_status, sizeof(LaneStatus), cudaHostAllocMapped));
+        RT_CUDA(ctx, cudaHostGetDevicePointer((void**)&L.d_status, L.h_status, 0));
         RT_CUDA(ctx, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
         if (lane > 0) RT_CUDA(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
         int prio_least = 0, prio_greatest = 0;
@@ -231,6 +228,7 @@ int ensure_lane(rt_ctx* ctx, DeviceBuffers& d, int lane, size_t entries) {
     RT_CUDA(ctx, cudaMalloc(&L.cand_t, cand_slots * sizeof(double)));
     RT_CUDA(ctx, cudaMalloc(&L.cand_count, (size_t)d.sm_count * 8 * 8 * sizeof(unsigned)));
     L.entries = entries;
+    L.best_clean = false;
     return RT_OK;
 }
 
@@ -277,6 +275,7 @@ Options options_from_env() {
     o.common_origin = env_int("RT_COMMON_ORIGIN", o.common_origin);
     o.reduce = env_int("RT_REDUCE", o.reduce);
     o.rows = env_int("RT_ROWS", o.rows);
+    o.wave_depth = env_int("RT_WAVE_DEPTH", o.wave_depth);
     return o;
 }
 
@@ -319,6 +318,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     const size_t capacity = align_up((size_t)std::min<unsigned long long>(cap_env / n_lanes, (P.total_work + n_lanes - 1) / n_lanes), 32);
 
     // tail kernel: one CTA per SM per lane (two lanes' tails run side by side)
+    bool done[kMaxLanes] = {};
     const unsigned tail_entries = (unsigned)std::max<long long>(0, opt.tail_entries);
     const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<1, 256>::LIST_BYTES;
     int tail_bps = 0;
@@ -345,7 +345,6 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     unsigned n_bound[kMaxLanes];   // upper bound of each lane's queue length (sizes the short-CTA grids)
     WaveParams W[kMaxLanes];
     cudaStream_t st[kMaxLanes];
-    bool done[kMaxLanes];
     unsigned long long first = 0;
     for (int l = 0; l < n_lanes; ++l) {
         if ((rc = ensure_lane(ctx, d, l, capacity))) return rc;
@@ -355,7 +354,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
         W[l].queue[0] = L.queue;
         W[l].queue[1] = L.queue + 3 * capacity;
         W[l].best_t = L.best;
-        W[l].best_key = L.best + capacity;
+        W[l].best_key = L.best + L.entries;   // fixed split: the words stay reset from one render to the next
         W[l].pairs = L.pairs;
         W[l].cands = L.cands;
         W[l].cand_t = L.cand_t;
@@ -367,7 +366,6 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
         W[l].claims_per_warp = claims;
         W[l].resident_warps = claims ? resident_warps : 0;
         st[l] = l == 0 ? stream : L.stream;
-        done[l] = false;
     }
     // RT_TRACE=<file>: device-side timeline of this render's kernels (dumped by the next rt_get_counters)
     static const char* trace_path = getenv("RT_TRACE");
@@ -393,29 +391,58 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
         total0 += count0[l];
         n_bound[l] = count0[l];
     }
-    wf_init<<<1, 1, 0, stream>>>(P.work_counter, total0);
-    RT_CUDA(ctx, cudaEventRecord(d.ev_lane_start, stream));
+    InitParams I{};
+    I.n_lanes = n_lanes;
+    I.work_counter = P.work_counter;
+    I.counters = P.counters;
+    I.total0 = total0;
+    I.total_work = P.total_work;
     for (int l = 0; l < n_lanes; ++l) {
-        if (l > 0) RT_CUDA(ctx, cudaStreamWaitEvent(st[l], d.ev_lane_start, 0));
-        W[l].trace = trace_slot("generate", l, 0);
-        wf_generate<<<std::max(1, std::min(light_grid, (int)((count0[l] + 255) / 256))), 256, 0, st[l]>>>(W[l], first, count0[l]);
+        DeviceBuffers::WaveLane& L = d.lanes[l];
+        I.st[l] = L.state;
+        I.first[l] = first;
+        I.count[l] = count0[l];
         first += count0[l];
-        ctx->n_launches += 1;
+        if (!L.best_clean) {   // after an allocation / an aborted render; wf_shade keeps the words reset otherwise
+            wf_fill_best<<<d.sm_count * 4, 256, 0, stream>>>(L.best, L.best + L.entries, L.entries);
+            ctx->n_launches += 1;
+        }
+        L.best_clean = false;   // until this render has run to completion
     }
-    ctx->n_launches += 1;   // wf_init
+    wf_init<<<1, 1, 0, stream>>>(I);
+    ctx->n_launches += 1;
     RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaEventRecord(d.ev_lane_start, stream));
+    for (int l = 1; l < n_lanes; ++l) RT_CUDA(ctx, cudaStreamWaitEvent(st[l], d.ev_lane_start, 0));
 
+    // The host only keeps the GPU fed: it queues `depth` iterations ahead per lane (cull, refine, tie-break, shade) and
+    // watches each lane's status record, which the device writes straight into mapped host memory (publish_status: no
+    // copy, no event, nothing in the lane's stream).  How much fresh work an iteration gets and when a lane is finished are
+    // decided on the device; kernels queued past the end return at once.  When the status says that no new work can appear
+    // and the queue is short, ONE wf_tail launch (behind the iterations already queued) finishes the lane.
+    const int depth = std::max(1, std::min(16, opt.wave_depth));
+    int enq[kMaxLanes] = {}, seen[kMaxLanes] = {};
+    bool tailed[kMaxLanes] = {};
+    for (int l = 0; l < n_lanes; ++l) {
+        DeviceBuffers::WaveLane& L = d.lanes[l];
+        memset(L.h_status, 0, sizeof(LaneStatus));
+        W[l].status = L.d_status;
+        if (count0[l] == 0) done[l] = true;
+    }
     std::vector<cudaEvent_t> evs;   // profile mode (one lane): 5 events per iteration
-    for (int chunk = 0;; ++chunk) {
-        bool all_done = true;
+    unsigned idle_spins = 0;
+    for (;;) {
+        bool progressed = false, all_done = true;
         for (int l = 0; l < n_lanes; ++l) {
             if (done[l]) continue;
+            all_done = false;
             DeviceBuffers::WaveLane& L = d.lanes[l];
-            for (int it = 0; it < kWaveChunk; ++it) {
+            while (!tailed[l] && enq[l] - seen[l] < depth) {
                 cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
                 if (ctx->profile)
                     for (auto& x : e) { RT_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
                 if (ctx->profile) cudaEventRecord(e[0], st[l]);
+                W[l].iter = (unsigned)(enq[l] + 1);
                 if (claims) {
                     // every work item of the launch must find a warp: items <= n / (32 R) + 2 resident_warps + 8 (wf_cull_body)
                     const unsigned items = n_bound[l] / (32u * kR) + 2u * (unsigned)resident_warps + 8u;
@@ -446,42 +473,60 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     k_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
                     if (ctx->profile) cudaEventRecord(e[4], st[l]);
                 }
+                RT_CUDA(ctx, cudaGetLastError());
                 W[l].cur ^= 1;
                 ++iter_no[l];
                 ctx->n_launches += 4;
-            }
-            RT_CUDA(ctx, cudaGetLastError());
-            RT_CUDA(ctx, cudaMemcpyAsync(&L.h_state[chunk & 1], L.state, sizeof(WaveState), cudaMemcpyDeviceToHost, st[l]));
-            RT_CUDA(ctx, cudaEventRecord(L.ev_poll[chunk & 1], st[l]));
-        }
-        if (chunk > 0) {   // look at the PREVIOUS chunk's snapshots: every lane always has one chunk queued
-            for (int l = 0; l < n_lanes; ++l) {
-                if (done[l]) continue;
-                DeviceBuffers::WaveLane& L = d.lanes[l];
-                RT_CUDA(ctx, cudaEventSynchronize(L.ev_poll[(chunk - 1) & 1]));
-                const WaveState& snap = L.h_state[(chunk - 1) & 1];
-                if (snap.exhausted)   // from here on a lane's population only shrinks
-                    n_bound[l] = std::min(n_bound[l], snap.cnt[W[l].cur][0] + snap.cnt[W[l].cur][1]);
-                if (snap.cnt[W[l].cur][0] == 0 && snap.cnt[W[l].cur][1] == 0) {   // kWaveChunk is even: same parity
-                    done[l] = true;
-                } else if (tail_ok && snap.exhausted && snap.cnt[W[l].cur][1] == 0 && snap.cnt[W[l].cur][0] <= tail_entries) {
-                    // no new work can appear and the queue is short: one launch finishes this lane
-                    W[l].trace = trace_slot("tail", l, iter_no[l]);
-                    k_tail<<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
-                    RT_CUDA(ctx, cudaGetLastError());
-                    ctx->n_launches += 1;
-                    done[l] = true;
-                }
+                ++enq[l];
+                progressed = true;
             }
         }
-        for (int l = 0; l < n_lanes; ++l) all_done &= done[l];
         if (all_done) break;
+        for (int l = 0; l < n_lanes; ++l) {
+            if (done[l]) continue;
+            DeviceBuffers::WaveLane& L = d.lanes[l];
+            const volatile LaneStatus* hs = L.h_status;
+            const unsigned seq = hs->seq;
+            if ((int)seq == seen[l] && hs->mode != MODE_DONE) continue;
+            std::atomic_thread_fence(std::memory_order_acquire);
+            const unsigned n_next = hs->n_next, n_fresh = hs->n_fresh, exhausted = hs->exhausted, mode = hs->mode;
+            if (hs->seq != seq) continue;   // the device was writing the next record: read it on the next round
+            seen[l] = (int)seq;
+            progressed = true;
+            if (exhausted) n_bound[l] = std::min(n_bound[l], n_next);   // from here on a lane's population only shrinks
+            if (mode == MODE_DONE) { done[l] = true; continue; }
+            if (tail_ok && !tailed[l] && exhausted && n_fresh == 0 && n_next <= tail_entries) {
+                // no new work can appear and the queue is short: one launch, behind the iterations already queued
+                // (they shrink the population further; the tail takes whatever is left), finishes this lane
+                W[l].iter = (unsigned)(enq[l] + 1);
+                W[l].trace = trace_slot("tail", l, iter_no[l]);
+                k_tail<<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
+                RT_CUDA(ctx, cudaGetLastError());
+                ctx->n_launches += 1;
+                tailed[l] = true;
+            }
+        }
+        if (!progressed) {   // nothing to queue, nothing new: spin briefly, then yield the core
+            if (++idle_spins > 200) {
+                if (cudaSuccess != cudaPeekAtLastError()) RT_CUDA(ctx, cudaGetLastError());
+                if (idle_spins > 20000 && (idle_spins % 1000) == 0) {   // a lost lane would spin forever: ask the stream
+                    for (int l = 0; l < n_lanes; ++l)
+                        if (!done[l] && cudaStreamQuery(st[l]) == cudaSuccess && d.lanes[l].h_status->seq == (unsigned)seen[l] &&
+                            enq[l] > seen[l])
+                            return fail(ctx, RT_ERR_CUDA, "wavefront lane finished its queue without reporting status");
+                }
+                std::this_thread::yield();
+            }
+        } else {
+            idle_spins = 0;
+        }
     }
     // the caller's stream continues only after every lane has drained
     for (int l = 1; l < n_lanes; ++l) {
         RT_CUDA(ctx, cudaEventRecord(d.lanes[l].ev_done, st[l]));
         RT_CUDA(ctx, cudaStreamWaitEvent(stream, d.lanes[l].ev_done, 0));
     }
+    for (int l = 0; l < n_lanes; ++l) d.lanes[l].best_clean = true;   // every entry was consumed (and its words reset) by wf_shade / wf_tail
     if (ctx->profile) {
         RT_CUDA(ctx, cudaStreamSynchronize(stream));
         for (size_t i = 0; i + 4 < evs.size(); i += 5)
@@ -1151,6 +1196,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "common_origin") o.common_origin = (int)value;
     else if (k == "reduce") o.reduce = (int)value;
     else if (k == "rows") o.rows = (int)value;
+    else if (k == "wave_depth") o.wave_depth = (int)value;
     else return fail(ctx, RT_ERR_ARG, "unknown option: " + k);
     return RT_OK;
 }

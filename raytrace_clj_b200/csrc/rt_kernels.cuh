@@ -420,16 +420,33 @@ struct RefineSink {
 //                  + prefix popc + one atomic per warp, same for the (sample, pixel) work counter)
 //   The host enqueues iterations ahead and polls the queue count every few iterations.
 // ------------------------------------------------------------------------------------------
-// A queue holds two populations: paths in flight at [0, qcount) and, when every camera ray starts at the same
-// origin (WaveParams::base.common_origin), the fresh camera rays at [capacity - pcount, capacity) — the cull runs
-// its common-origin form over those (Culler<.., COMMON>).
+// A queue holds two populations: paths in flight at [0, cnt[q][0]) and FRESH camera rays at [capacity - cnt[q][1],
+// capacity).  A fresh entry is only a promise: entry capacity - cnt[q][1] + i stands for work item gen_base[q] + i, and
+// the cull kernel GENERATES its ray (get-ray, camera.clj:35-48) when it first needs it, and writes the queue record for the
+// later stages.  When every camera ray starts at the same origin (WaveParams::base.common_origin) the cull runs its
+// common-origin form over the fresh region (Culler<.., COMMON>).  The last CTA of wf_shade hands out the next
+// iteration's fresh work: ONE atomic on the shared (sample, pixel) counter per launch.
 struct alignas(8) WaveState {
-    unsigned cnt[2][2];            // cnt[i][0]: general entries of queue[i]; cnt[i][1]: its common-origin entries, at the
-                                   // top of the queue.  One 64-bit word per queue: wf_shade claims both with ONE atomic.
+    unsigned cnt[2][2];
+    unsigned long long gen_base[2];
     unsigned batch;                // next batch (wf_cull)
     unsigned npairs;               // pairs emitted this iteration
     unsigned exhausted;            // the (sample, pixel) work counter has run past the end
+    unsigned done;                 // CTAs of the running wf_shade launch that have finished (the last one takes the ticket)
+    unsigned mode;                 // MODE_RUN, or MODE_DONE once the lane has drained (set on the device by the last CTA of
+                                   // wf_shade / wf_tail): kernels queued past the end look at it and return at once
     unsigned pad;
+};
+enum { MODE_RUN = 0, MODE_DONE = 2 };
+// What the host needs to know about a lane, written by the device straight into pinned, mapped HOST memory by the last
+// CTA of every wf_shade (and of wf_tail): no copy, no event, nothing in the lane's stream.  `seq` is written last.
+struct LaneStatus {
+    unsigned n_next;               // entries the next iteration will find (paths in flight + fresh)
+    unsigned n_fresh;              // of which fresh
+    unsigned exhausted;            // the (sample, pixel) counter has run out: the population only shrinks from here
+    unsigned mode;
+    unsigned seq;                  // iterations of this render completed on the device
+    unsigned pad[3];
 };
 // entry index of the i-th entry of a queue holding n_g general and n_p common-origin entries
 __device__ __forceinline__ unsigned wf_entry(unsigned i, unsigned n_g, unsigned n_p, unsigned capacity) {
@@ -474,8 +491,20 @@ struct WaveParams {
                                    // after k batches (many short CTAs: the SM's slots turn over, so the other lane's
                                    // high-priority stage kernels get on the SM while this cull is still running)
     int resident_warps;            // wf_cull warps resident on the device at once (sizes the balancing tail); 0 = the grid's
+    volatile LaneStatus* status;   // the lane's status record in mapped host memory (null inside wf_tail's per-CTA views)
+    unsigned iter;                 // 1-based number of this iteration within the render (LaneStatus::seq after its wf_shade)
     TraceRec* trace;               // this launch's timeline record, or null
 };
+__device__ __forceinline__ void publish_status(const WaveParams& W, unsigned n_next, unsigned n_fresh, unsigned exhausted, unsigned mode,
+                                               unsigned seq) {
+    if (!W.status) return;
+    W.status->n_next = n_next;
+    W.status->n_fresh = n_fresh;
+    W.status->exhausted = exhausted;
+    W.status->mode = mode;
+    __threadfence_system();
+    W.status->seq = seq;
+}
 
 constexpr unsigned long long BEST_T_INIT = 0x7ff0000000000000ull;   // +inf
 constexpr unsigned long long BEST_KEY_MISS = ~0ull;
@@ -492,18 +521,6 @@ __device__ __forceinline__ unsigned warp_claim(unsigned* counter, bool pred, uns
         base = __shfl_sync(0xffffffffu, base, leader);
     }
     return base + __popc(m & ((1u << lane) - 1u));
-}
-
-// pull one (sample, pixel) work item for every lane with `want` (one atomic per warp); false when the work ran out
-__device__ __forceinline__ bool take_work(const RenderParams& P, bool want, unsigned lane, unsigned long long& w) {
-    unsigned m = __ballot_sync(0xffffffffu, want);
-    if (!m) return false;
-    int leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(P.work_counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    w = base + __popc(m & ((1u << lane) - 1u));
-    return want && w < P.total_work;
 }
 
 // camera ray of work item w as a queue record
@@ -538,29 +555,36 @@ __device__ __forceinline__ void make_path(const RenderParams& P, unsigned long l
     c = make_float4(1.f, 1.f, 1.f, __uint_as_float((smp << 8) | (uint32_t)P.max_depth));
 }
 
-// first fill of a lane's queue 0: work items [first, first + count) map 1:1 to entries, no atomics
-// (the host has already advanced the shared work counter past every lane's first fill: wf_init)
-__global__ void wf_init(unsigned long long* work_counter, unsigned long long value) { *work_counter = value; }
-
-__global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ WaveParams W, unsigned long long first, unsigned count) {
-    TraceScope trace(W.trace);
-    const RenderParams& P = W.base;
-    const unsigned e0 = P.common_origin ? (unsigned)W.capacity - count : 0u;   // camera rays: the common-origin region
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        float4 a, b, c;
-        make_path(P, first + i, a, b, c);
-        float4* q = W.queue[0] + 3 * (size_t)(e0 + i);
-        q[0] = a; q[1] = b; q[2] = c;
+// Start of a render: every lane's queue 0 holds only fresh entries (work items [first, first + count) of the lane), the
+// shared work counter starts past every lane's first fill.  No ray is generated here: the first cull does that.
+constexpr int kMaxLanes = 2;
+struct InitParams {
+    WaveState* st[kMaxLanes];
+    unsigned long long first[kMaxLanes];
+    unsigned count[kMaxLanes];
+    int n_lanes;
+    unsigned long long* work_counter;
+    unsigned long long* counters;
+    unsigned long long total0, total_work;
+};
+__global__ void wf_init(const InitParams I) {
+    for (int l = 0; l < I.n_lanes; ++l) {
+        WaveState* st = I.st[l];
+        st->cnt[0][0] = 0; st->cnt[0][1] = I.count[l];
+        st->cnt[1][0] = 0; st->cnt[1][1] = 0;
+        st->gen_base[0] = I.first[l]; st->gen_base[1] = 0;
+        st->batch = 0; st->npairs = 0; st->done = 0; st->mode = I.count[l] ? MODE_RUN : MODE_DONE; st->pad = 0;
+        st->exhausted = I.total0 >= I.total_work ? 1u : 0u;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        W.st->cnt[0][0] = P.common_origin ? 0u : count;
-        W.st->cnt[0][1] = P.common_origin ? count : 0u;
-        W.st->cnt[1][0] = 0;
-        W.st->cnt[1][1] = 0;
-        W.st->batch = 0;
-        W.st->npairs = 0;
-        W.st->exhausted = 0;
-        atomicAdd(&P.counters[DC_SAMPLES], (unsigned long long)count);
+    *I.work_counter = I.total0;
+    atomicAdd(&I.counters[DC_SAMPLES], I.total0);
+}
+// closest-hit words of a lane -> (+inf, MISS).  wf_shade leaves them that way (the consumer of an entry's words resets
+// them), so this runs only after an allocation or after a render that did not run to completion.
+__global__ void wf_fill_best(unsigned long long* best_t, unsigned long long* best_key, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        best_t[i] = 0x7ff0000000000000ull;
+        best_key[i] = ~0ull;
     }
 }
 
@@ -569,8 +593,10 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ WaveP
 // A warp whose span does not fit marks its entries OVERFLOW; wf_shade re-intersects those exactly.
 template <int R, int BLOCK>
 struct PairSink {
-    unsigned idx0;                 // queue entry of ray r = idx0 + 32 r
-    unsigned n;                    // end of the entry range being culled
+    unsigned idx0;                 // VIRTUAL index of ray r = idx0 + 32 r; queue entry = entry(idx0 + 32 r)
+    unsigned n;                    // end of the virtual range being culled
+    unsigned n_g, p0;              // virtual index v < n_g is entry v, else entry p0 + (v - n_g) (n_g = ~0: identity)
+    __device__ __forceinline__ unsigned entry(unsigned v) const { return v < n_g ? v : p0 + (v - n_g); }
     unsigned long long live;       // bits 16 r .. 16 r + 15 set if ray r of this lane is a live entry
     uint2* pairs;                  // by value (not a WaveParams*): keeps a caller's modified copy of the params in registers
     unsigned pair_cap;
@@ -602,19 +628,21 @@ struct PairSink {
         it.begin(nz, count);
         int r, k;
         while (it.next(list, r, k)) {
-            const unsigned idx = idx0 + 32u * (unsigned)r;
+            const unsigned v = idx0 + 32u * (unsigned)r;
             if (fits) {
-                pairs[w] = make_uint2(idx, (unsigned)(kbase + k));
+                pairs[w] = make_uint2(entry(v), (unsigned)(kbase + k));
             } else {
                 if (w < pair_cap) pairs[w] = make_uint2(PAIR_NULL, 0u);
-                if (idx < n) best_key[idx] = BEST_KEY_OVERFLOW;
+                if (v < n) best_key[entry(v)] = BEST_KEY_OVERFLOW;   // nothing else writes the word during the cull
             }
             ++w;
         }
     }
 };
 
-// Queue entries [e0, e1) in batches of 32*R, each batch optionally split into `parts` sphere slices.  The
+// Virtual entries [e0, e1) in batches of 32*R, each batch optionally split into `parts` sphere slices.  Virtual index
+// v < n_g is queue entry v (a path in flight: its ray is loaded); v >= n_g is entry p0 + (v - n_g), FRESH: the ray of
+// work item gen0 + (v - n_g) is generated here and its queue record written for the later stages.  The
 // (batch, slice) work items of this range are numbered item0, item0 + 1, ...; warps claim item numbers from the
 // shared counter (preloaded scenes) or take them in a CTA-uniform static order (tiled scenes).  `claimed` is an
 // item number this warp has already claimed (or ~0u); returns the first claimed number beyond the range, so a
@@ -628,8 +656,9 @@ struct Scope {
 };
 __device__ __forceinline__ Scope grid_scope() { return Scope{blockIdx.x, gridDim.x}; }
 template <int R, int BLOCK, bool COMMON>
-__device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope sc_, int cur, unsigned e0, unsigned e1, int parts,
-                                                    unsigned item0, unsigned claimed, int& budget, float4* s_cull, uint32_t* s_list) {
+__device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope sc_, int cur, unsigned e0, unsigned e1, unsigned n_g,
+                                                    unsigned p0, unsigned long long gen0, int parts, unsigned item0, unsigned claimed,
+                                                    int& budget, float4* s_cull, uint32_t* s_list) {
     if (claimed == ITEM_STOP) return ITEM_STOP;
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = BLOCK / 32;
@@ -639,6 +668,8 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope s
     K.cox = P.cam.origin.x; K.coy = P.cam.origin.y; K.coz = P.cam.origin.z;
     PairSink<R, BLOCK> sink;
     sink.n = e1;
+    sink.n_g = n_g;
+    sink.p0 = p0;
     sink.pairs = W.pairs;
     sink.pair_cap = W.pair_cap;
     sink.best_key = W.best_key;
@@ -664,16 +695,21 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope s
         sink.idx0 = e0 + batch * (32 * R) + lane;     // ray r of this lane = entry idx0 + 32 r
         sink.live = 0ull;
         RT_FOR_R {
-            unsigned idx = sink.idx0 + 32 * r;
-            if (idx < e1 && batch < n_batches) {
-                const float4* qc = cur ? W.queue[1] : W.queue[0];   // a select, not a dynamic index (keeps copies of W in registers)
-                float4 a = qc[3 * (size_t)idx], b = qc[3 * (size_t)idx + 1];
+            const unsigned v = sink.idx0 + 32 * r;
+            if (v < e1 && batch < n_batches) {
+                float4* qc = cur ? W.queue[1] : W.queue[0];   // a select, not a dynamic index (keeps copies of W in registers)
+                float4 a, b;
+                if (v >= n_g) {                               // fresh: generate the camera ray of its work item
+                    float4 c;
+                    float4* q = qc + 3 * (size_t)(p0 + (v - n_g));
+                    make_path(P, gen0 + (v - n_g), a, b, c);
+                    if (part == 0) { q[0] = a; q[1] = b; q[2] = c; }
+                } else {
+                    a = qc[3 * (size_t)v];
+                    b = qc[3 * (size_t)v + 1];
+                }
                 K.set_ray(r, a.x, a.y, a.z, b.x, b.y, b.z);
                 sink.live |= 0xffffull << (16 * r);
-                if (part == 0) {
-                    W.best_t[idx] = BEST_T_INIT;
-                    W.best_key[idx] = BEST_KEY_MISS;
-                }
             } else {
                 K.kill(r);
             }
@@ -686,47 +722,52 @@ __device__ __forceinline__ unsigned wf_cull_batches(const WaveParams& W, Scope s
     return ITEM_NONE;
 }
 
-// The shape of the cull work.  The queue holds n_p common-origin entries (camera rays, culled in the cheaper
-// common-origin form against the tile s_cullc) and n_g general ones.  A long queue: batches of R rays per thread
-// for the bulk of both, then — so that the warps do not finish up to a whole 32*R batch apart — one-ray batches
-// for the last stretch (two per warp of the grid), all claimed from the same counter.  A short queue: 1 ray per
-// thread, and below two batches per warp the sphere list is split across warps too (the pairs merge in
-// wf_refine).  R = 1 instantiates only the short form.  s_cullc may be null when n_p is 0 (the tail).
+// The shape of the cull work.  The queue holds n_p fresh entries (camera rays, generated here; when they all share an
+// origin they are culled in the cheaper common-origin form against the tile s_cullc) and n_g paths in flight.  A long
+// queue: batches of R rays per thread for the bulk of both, then — so that the warps do not finish up to a whole 32*R
+// batch apart — one-ray batches for the last stretch (two per warp of the grid), all claimed from the same counter.  A
+// short queue: 1 ray per thread, and below two batches per warp the sphere list is split across warps too (the pairs
+// merge in wf_refine).  R = 1 instantiates only the short form.  s_cullc may be null when n_p is 0 (the tail).
 template <int R, int BLOCK>
-__device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int cur, unsigned n_g, unsigned n_p, float4* s_cull,
-                                             float4* s_cullc, uint32_t* s_list) {
+__device__ __forceinline__ void wf_cull_body(const WaveParams& W, Scope sc_, int cur, unsigned n_g, unsigned n_p, unsigned long long gen_base,
+                                             float4* s_cull, float4* s_cullc, uint32_t* s_list) {
     const RenderParams& P = W.base;
     const unsigned n = n_g + n_p, p0 = (unsigned)W.capacity - n_p;
     if (sc_.bid == 0 && threadIdx.x == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
     const unsigned grid_warps = W.resident_warps > 0 ? (unsigned)W.resident_warps : sc_.nblk * (BLOCK / 32);
     int budget = W.claims_per_warp;
+    // two virtual ranges: C = the fresh entries in the common-origin form (identity mapping over [p0, p0 + n_c)), and
+    // V = everything culled in the general form: the n_g paths in flight, followed — when the camera rays do NOT share an
+    // origin (a real aperture) — by the fresh entries (virtual index >= n_g)
+    const unsigned n_c = P.common_origin ? n_p : 0u, n_v = n - n_c;
+    const unsigned long long genC = gen_base - p0;   // C: virtual index = entry index; item = gen_base + (entry - p0)
     if (R > 1 && !P.preloaded) {
         // tiled scene: CTA-uniform static order; the tile loader builds the common-origin records itself
-        if (n_p) wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, 1, 0u, ITEM_NONE, budget, s_cull, s_list);
-        if (n_g) wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, n_g, 1, 0u, ITEM_NONE, budget, s_cull, s_list);
+        if (n_c) wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + n_c, 0u, 0u, genC + 0u, 1, 0u, ITEM_NONE, budget, s_cull, s_list);
+        if (n_v) wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, n_v, n_g, p0, gen_base, 1, 0u, ITEM_NONE, budget, s_cull, s_list);
     } else if (R > 1 && n >= grid_warps * 64u) {
         const unsigned tail = grid_warps * 64u, per = 32u * R;                       // two one-ray batches per warp
-        const unsigned g_rest0 = min(n_g, tail), p_rest0 = min(n_p, tail - g_rest0);
-        const unsigned g_bulk = (n_g - g_rest0) / per * per, p_bulk = (n_p - p_rest0) / per * per;
+        const unsigned g_rest0 = min(n_v, tail), p_rest0 = min(n_c, tail - g_rest0);
+        const unsigned g_bulk = (n_v - g_rest0) / per * per, p_bulk = (n_c - p_rest0) / per * per;
         unsigned items = 0;
-        unsigned next = wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + p_bulk, 1, items, ITEM_NONE, budget, s_cullc, s_list);
+        unsigned next = wf_cull_batches<R, BLOCK, true>(W, sc_, cur, p0, p0 + p_bulk, 0u, 0u, genC, 1, items, ITEM_NONE, budget, s_cullc, s_list);
         items += p_bulk / per;
-        next = wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, g_bulk, 1, items, next, budget, s_cull, s_list);
+        next = wf_cull_batches<R, BLOCK, false>(W, sc_, cur, 0u, g_bulk, n_g, p0, gen_base, 1, items, next, budget, s_cull, s_list);
         items += g_bulk / per;
-        next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0 + p_bulk, p0 + n_p, 1, items, next, budget, s_cullc, s_list);
-        items += (n_p - p_bulk + 31u) / 32u;
-        wf_cull_batches<1, BLOCK, false>(W, sc_, cur, g_bulk, n_g, 1, items, next, budget, s_cull, s_list);
+        next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0 + p_bulk, p0 + n_c, 0u, 0u, genC, 1, items, next, budget, s_cullc, s_list);
+        items += (n_c - p_bulk + 31u) / 32u;
+        wf_cull_batches<1, BLOCK, false>(W, sc_, cur, g_bulk, n_v, n_g, p0, gen_base, 1, items, next, budget, s_cull, s_list);
     } else {
         const unsigned b1 = (n + 31) / 32;
         int parts = 1;
         if (P.preloaded)
             while (parts < 16 && b1 * (unsigned)parts * 2u <= grid_warps) parts *= 2;
         unsigned next = ITEM_NONE, items = 0;
-        if (n_p) {
-            next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0, p0 + n_p, parts, 0u, ITEM_NONE, budget, P.preloaded ? s_cullc : s_cull, s_list);
-            items = (n_p + 31u) / 32u * (unsigned)parts;
+        if (n_c) {
+            next = wf_cull_batches<1, BLOCK, true>(W, sc_, cur, p0, p0 + n_c, 0u, 0u, genC, parts, 0u, ITEM_NONE, budget, P.preloaded ? s_cullc : s_cull, s_list);
+            items = (n_c + 31u) / 32u * (unsigned)parts;
         }
-        if (n_g) wf_cull_batches<1, BLOCK, false>(W, sc_, cur, 0u, n_g, parts, items, next, budget, s_cull, s_list);
+        if (n_v) wf_cull_batches<1, BLOCK, false>(W, sc_, cur, 0u, n_v, n_g, p0, gen_base, parts, items, next, budget, s_cull, s_list);
     }
 }
 
@@ -738,16 +779,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const __grid_constant__ W
     float4* s_cull = smem_f4;
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     float4* s_cullc = reinterpret_cast<float4*>(s_list + Culler<R, BLOCK>::LIST_WORDS * BLOCK);   // common-origin records
+    if (W.st->mode != MODE_RUN) return;
     const unsigned n_g = W.st->cnt[W.cur][0], n_p = W.st->cnt[W.cur][1];
     if (n_g + n_p == 0) return;
+    const unsigned long long gen_base = W.st->gen_base[W.cur];
     if (P.preloaded) {
         preload_scene(P.sc, s_cull, BLOCK);
-        if (n_p)
+        if (n_p && P.common_origin)
             for (int i = threadIdx.x; i < P.sc.n_cull; i += BLOCK)
                 s_cullc[i] = Culler<R, BLOCK, true>::common_record(s_cull[i], P.cam.origin.x, P.cam.origin.y, P.cam.origin.z);
     }
     __syncthreads();
-    wf_cull_body<R, BLOCK>(W, grid_scope(), W.cur, n_g, n_p, s_cull, s_cullc, s_list);
+    wf_cull_body<R, BLOCK>(W, grid_scope(), W.cur, n_g, n_p, gen_base, s_cull, s_cullc, s_list);
 }
 
 // one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved).
@@ -821,6 +864,7 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, const DevSce
 }
 template <bool GEN>
 __global__ void __launch_bounds__(256) wf_refine(const __grid_constant__ WaveParams W) {
+    if (W.st->mode != MODE_RUN) return;
     TraceScope trace(W.trace);
     wf_refine_body<GEN>(W, &W.base.sc, grid_scope(), W.cur);
 }
@@ -841,6 +885,7 @@ __device__ __forceinline__ void wf_tiebreak_body(const WaveParams& W, Scope sc_)
     }
 }
 __global__ void __launch_bounds__(256) wf_tiebreak(const __grid_constant__ WaveParams W) {
+    if (W.st->mode != MODE_RUN) return;
     TraceScope trace(W.trace);
     wf_tiebreak_body(W, grid_scope());
 }
@@ -872,19 +917,13 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, const Dev
     const unsigned lane = threadIdx.x & 31u;
     const float4* qc = cur ? W.queue[1] : W.queue[0];
     float4* qn = cur ? W.queue[0] : W.queue[1];
-    if (sc_.bid == 0 && threadIdx.x == 0) {
-        W.st->npairs = 0;   // refine / tie-break are done with it
-        W.st->exhausted = (*(volatile unsigned long long*)P.work_counter >= P.total_work) ? 1u : 0u;
-    }
-    // once the (sample, pixel) counter is known to have run out, finished lanes stop asking it (a returning atomic
-    // per tile); the flag only ever goes 0 -> 1, so racing with the writer above is harmless
-    const bool no_work = *(volatile unsigned*)&W.st->exhausted != 0u;
-    unsigned n_samples = 0, n_direct = 0;
+    if (sc_.bid == 0 && threadIdx.x == 0) W.st->npairs = 0;   // refine / tie-break are done with it
+    unsigned n_direct = 0;
     const unsigned stride = sc_.nblk * blockDim.x;
     for (unsigned idx0 = sc_.bid * blockDim.x + threadIdx.x - lane; idx0 < n; idx0 += stride) {   // warp-uniform
         const bool have = idx0 + lane < n;
         const unsigned idx = wf_entry(idx0 + lane, n_g, n_p, (unsigned)W.capacity);
-        bool cont = false, fresh = false;
+        bool cont = false;
         float4 a, b, c;
         if (have) {
             a = qc[3 * (size_t)idx]; b = qc[3 * (size_t)idx + 1]; c = qc[3 * (size_t)idx + 2];
@@ -896,6 +935,10 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, const Dev
             const uint32_t bounce = (uint32_t)(P.max_depth - depth + 1);
             int k = (int)(unsigned)key;
             double td = __longlong_as_double((long long)W.best_t[idx]);
+            // this thread is the last reader of the entry's closest-hit words: it leaves them reset for the next
+            // iteration's entry at this index (the cull and the refine only ever lower them; nothing else initialises them)
+            W.best_key[idx] = BEST_KEY_MISS;
+            W.best_t[idx] = BEST_T_INIT;
             if (key == BEST_KEY_OVERFLOW) {                 // overflow mark: exact brute force for this entry
                 exact_closest_hit<GEN>(scp, a.x, a.y, a.z, b.x, b.y, b.z, a.w, P.key, pix, smp, bounce, &td, &k);
                 key = k < 0 ? BEST_KEY_MISS : 1ull;
@@ -943,47 +986,58 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, const Dev
                 }
             }
         }
-        // a finished path frees its lane for the next (sample, pixel)
-        unsigned long long w;
-        if (!no_work && take_work(P, have && !cont, lane, w)) {
-            make_path(P, w, a, b, c);
-            fresh = P.common_origin != 0;       // a camera ray from the common origin: the other region of the queue
-            cont = !fresh;
-            n_samples++;
-        }
-        // one 64-bit atomic per warp claims the general slots (low word) and the common-origin slots (high word)
-        const unsigned mc = __ballot_sync(0xffffffffu, cont), mf = __ballot_sync(0xffffffffu, fresh);
-        if (mc | mf) {
-            unsigned long long base = 0ull;
-            if (lane == 0)
-                base = atomicAdd(reinterpret_cast<unsigned long long*>(&W.st->cnt[cur ^ 1][0]),
-                                 ((unsigned long long)__popc(mf) << 32) | (unsigned long long)__popc(mc));
+        // compaction: the surviving paths go to [0, n) of the other queue — ballot + prefix popc + ONE atomic per warp.
+        // (Finished paths are not replaced here: the launch's last CTA hands out the next iteration's fresh work.)
+        const unsigned mc = __ballot_sync(0xffffffffu, cont);
+        if (mc) {
+            unsigned base = 0u;
+            if (lane == 0) base = atomicAdd(&W.st->cnt[cur ^ 1][0], (unsigned)__popc(mc));
             base = __shfl_sync(0xffffffffu, base, 0);
-            const unsigned lt = (1u << lane) - 1u;
             if (cont) {
-                float4* q = qn + 3 * (size_t)((unsigned)base + __popc(mc & lt));
-                q[0] = a; q[1] = b; q[2] = c;
-            } else if (fresh) {
-                float4* q = qn + 3 * (size_t)((unsigned)W.capacity - 1u - ((unsigned)(base >> 32) + __popc(mf & lt)));
+                float4* q = qn + 3 * (size_t)(base + __popc(mc & ((1u << lane) - 1u)));
                 q[0] = a; q[1] = b; q[2] = c;
             }
         }
     }
     if (n_direct) atomicAdd(&s_ctr[DC_DIRECT], n_direct);
-    return n_samples;
+    return 0u;
 }
 
 template <bool GEN>
 __global__ void __launch_bounds__(256, GEN ? 1 : 0) wf_shade(const __grid_constant__ WaveParams W) {
+    if (W.st->mode != MODE_RUN) return;        // only this kernel's LAST CTA (below) or the tail ever change the mode
     TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     __shared__ unsigned s_ctr[DC_COUNT];
     if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned n_samples = wf_shade_body<GEN>(W, &W.base.sc, grid_scope(), W.cur, s_ctr);
-    atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
+    wf_shade_body<GEN>(W, &W.base.sc, grid_scope(), W.cur, s_ctr);
     __syncthreads();
     if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+    // The last CTA to finish hands out the next iteration's fresh work: the free slots of the other queue, as many as the
+    // shared (sample, pixel) counter still has — one returning atomic per LAUNCH (it used to be one per warp and tile).
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&W.st->done, 1u) == gridDim.x - 1) {
+            __threadfence();
+            W.st->done = 0;
+            const unsigned n_cont = *(volatile unsigned*)&W.st->cnt[W.cur ^ 1][0];
+            const unsigned want = (unsigned)W.capacity - n_cont;
+            unsigned n_fresh = 0;
+            unsigned long long base = 0ull;
+            if (!W.st->exhausted && want) {
+                base = atomicAdd(P.work_counter, (unsigned long long)want);
+                if (base < P.total_work) n_fresh = (unsigned)min((unsigned long long)want, P.total_work - base);
+                if (base + want >= P.total_work) W.st->exhausted = 1u;
+            }
+            W.st->cnt[W.cur ^ 1][1] = n_fresh;
+            W.st->gen_base[W.cur ^ 1] = base;
+            if (n_fresh) atomicAdd(&P.counters[DC_SAMPLES], (unsigned long long)n_fresh);
+            if (n_cont + n_fresh == 0) W.st->mode = MODE_DONE;   // kernels already queued behind this one return at once
+            __threadfence();
+            publish_status(W, n_cont + n_fresh, n_fresh, W.st->exhausted, W.st->mode, W.iter);
+        }
+    }
 }
 
 // Tail of a render: the work counter is exhausted and the queue is short (up to 50 more bounces of a shrinking
@@ -995,63 +1049,79 @@ __global__ void __launch_bounds__(256, GEN ? 1 : 0) wf_shade(const __grid_consta
 constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 1.5)
 template <int BLOCK, bool GEN>
 __global__ void __launch_bounds__(BLOCK, GEN ? 1 : 2) wf_tail(const __grid_constant__ WaveParams W) {
-    TraceScope trace(W.trace);
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
     float4* s_cull = smem_f4;
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_f4 + P.cull_cap);
     __shared__ unsigned s_ctr[DC_COUNT];
     __shared__ WaveState s_st;
+    if (W.st->mode == MODE_DONE) return;             // the iterations queued ahead of this launch already drained the lane
+    TraceScope trace(W.trace);
     int cur = W.cur;
-    const unsigned n_all = W.st->cnt[cur][0];        // the host launches the tail only when the common-origin region is empty
+    const unsigned n_all = W.st->cnt[cur][0];        // the host launches it only once the fresh region stays empty
     const unsigned K = ((n_all + gridDim.x - 1) / gridDim.x + 31u) / 32u * 32u;      // slice capacity
     const unsigned first = blockIdx.x * K;
-    if (first >= n_all) return;                                                       // CTA-uniform
-    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+    if (first < n_all) {                                                              // CTA-uniform
+        if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+        if (threadIdx.x == 0) {
+            s_st.cnt[cur][0] = min(K, n_all - first);
+            s_st.cnt[cur ^ 1][0] = 0;
+            s_st.cnt[0][1] = s_st.cnt[1][1] = 0;
+            s_st.gen_base[0] = s_st.gen_base[1] = 0ull;
+            s_st.batch = 0;
+            s_st.npairs = 0;
+            s_st.exhausted = 1;
+            s_st.done = 0;
+            s_st.mode = MODE_RUN;
+        }
+        // this CTA's view of the lane's buffers
+        const unsigned warps = BLOCK / 32;
+        WaveParams L = W;
+        L.queue[0] = W.queue[0] + 3 * (size_t)first;
+        L.queue[1] = W.queue[1] + 3 * (size_t)first;
+        L.best_t = W.best_t + first;
+        L.best_key = W.best_key + first;
+        L.pairs = W.pairs + (size_t)first * kPairsPerEntry;
+        // the slice's share of the pair buffer ends where the allocation ends (the last slice may be cut short)
+        L.pair_cap = min(K, (unsigned)W.capacity - first) * kPairsPerEntry;
+        const size_t cand_slice = (size_t)wf_cand_region(L, warps) * warps;
+        L.cands = W.cands + (size_t)blockIdx.x * cand_slice;
+        L.cand_t = W.cand_t + (size_t)blockIdx.x * cand_slice;
+        L.cand_count = W.cand_count + blockIdx.x * warps;
+        L.st = &s_st;
+        L.status = nullptr;
+        L.capacity = (int)K;
+        L.claims_per_warp = 0;
+        L.resident_warps = 0;
+        if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
+        const Scope solo{0u, 1u};
+        for (;;) {
+            __syncthreads();
+            const unsigned n = *(volatile unsigned*)&s_st.cnt[cur][0];
+            if (n == 0) break;
+            wf_cull_body<1, BLOCK>(L, solo, cur, n, 0u, 0ull, s_cull, nullptr, s_list);
+            __syncthreads();
+            wf_refine_body<GEN>(L, &W.base.sc, solo, cur);
+            __syncthreads();
+            wf_tiebreak_body(L, solo);
+            __syncthreads();
+            wf_shade_body<GEN>(L, &W.base.sc, solo, cur, s_ctr);
+            cur ^= 1;
+        }
+        __syncthreads();
+        if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+    }
+    // the last CTA to finish marks the lane drained: every kernel queued behind this one returns at once
     if (threadIdx.x == 0) {
-        s_st.cnt[cur][0] = min(K, n_all - first);
-        s_st.cnt[cur ^ 1][0] = 0;
-        s_st.cnt[0][1] = s_st.cnt[1][1] = 0;
-        s_st.batch = 0;
-        s_st.npairs = 0;
-        s_st.exhausted = 1;
+        __threadfence();
+        if (atomicAdd(&W.st->done, 1u) == gridDim.x - 1) {
+            W.st->done = 0;
+            W.st->cnt[0][0] = W.st->cnt[0][1] = W.st->cnt[1][0] = W.st->cnt[1][1] = 0;
+            W.st->mode = MODE_DONE;
+            __threadfence();
+            publish_status(W, 0u, 0u, 1u, MODE_DONE, W.iter);
+        }
     }
-    // this CTA's view of the lane's buffers
-    const unsigned warps = BLOCK / 32;
-    WaveParams L = W;
-    L.queue[0] = W.queue[0] + 3 * (size_t)first;
-    L.queue[1] = W.queue[1] + 3 * (size_t)first;
-    L.best_t = W.best_t + first;
-    L.best_key = W.best_key + first;
-    L.pairs = W.pairs + (size_t)first * kPairsPerEntry;
-    L.pair_cap = K * kPairsPerEntry;
-    const size_t cand_slice = (size_t)wf_cand_region(L, warps) * warps;
-    L.cands = W.cands + (size_t)blockIdx.x * cand_slice;
-    L.cand_t = W.cand_t + (size_t)blockIdx.x * cand_slice;
-    L.cand_count = W.cand_count + blockIdx.x * warps;
-    L.st = &s_st;
-    L.capacity = (int)K;
-    L.claims_per_warp = 0;
-    L.resident_warps = 0;
-    if (P.preloaded) preload_scene(P.sc, s_cull, BLOCK);
-    const Scope solo{0u, 1u};
-    unsigned n_samples = 0;
-    for (;;) {
-        __syncthreads();
-        const unsigned n = *(volatile unsigned*)&s_st.cnt[cur][0];
-        if (n == 0) break;
-        wf_cull_body<1, BLOCK>(L, solo, cur, n, 0u, s_cull, nullptr, s_list);
-        __syncthreads();
-        wf_refine_body<GEN>(L, &W.base.sc, solo, cur);
-        __syncthreads();
-        wf_tiebreak_body(L, solo);
-        __syncthreads();
-        n_samples += wf_shade_body<GEN>(L, &W.base.sc, solo, cur, s_ctr);
-        cur ^= 1;
-    }
-    atomicAdd(&s_ctr[DC_SAMPLES], n_samples);
-    __syncthreads();
-    if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
 }
 
 
