@@ -98,7 +98,7 @@ struct Options {
     int common_origin = 1;            // RT_COMMON_ORIGIN
     int reduce = 0;                   // multi-device rt_render: 0 = NVLink peer loads inside the resolve kernel, 1 = ncclReduce
     int rows = 0;                     // multi-device partition: 0 = sample slices, 1 = interleaved rows
-    int wave_depth = 3;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
+    int wave_depth = 2;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
 };
 
 struct rt_ctx {
