@@ -5,12 +5,17 @@ A "step" is one full pass of the hot path over the workload: every pixel of the 
 spheres scene (make-random-scene n=11 moving=true, scene seed 1, ~486 spheres), 10 samples per
 pixel, depth 50 (BASELINE.json configs[1]).  `value` = samples/s with the scene resident in HBM
 (kernels + reduce + resolve timed with CUDA events on the launching stream); `e2e` = the same
-metric through the C-ABI calls a front end makes (rt_set_scene + rt_set_camera + render + image
-back on the host), host<->device copies inside the timed region.
+metric through the C-ABI calls a front end makes (rt_set_scene + rt_set_camera + rt_render with
+HOST buffers), host<->device copies inside the timed region.
 
 N > 1 (torchrun, one rank per GPU): every rank renders its own 10-spp sample slice of the same
 frame (weak scaling: global spp = 10 N), the float sums are combined with one NCCL reduce over
-NVLink and rank 0 resolves; time = max over ranks.
+NVLink and rank 0 resolves; time = max over ranks.  `e2e` at N > 1 is what the drop-in's caller —
+ONE process, core.clj:99-108 — would get: rank 0 alone drives an N-device context
+(rt_create(ids, N) + rt_render with host buffers; sample slices on every device, cross-device
+reduce inside the library) while the other ranks idle.  The `strong_c3` block adds BASELINE
+config 3 (3840x2160, 1024 spp) through that same in-library path: total work fixed, split over
+the N devices by sample slices and by interleaved rows, reduce time reported separately.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, double precision C++ with
 OpenMP on all host threads) — the Clojure original cannot run here (no JVM in the image).
@@ -32,6 +37,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FLOP_PER_TEST = 17.0            # oc (3) + oc.d (5) + oc.oc - r^2 (6) + b'^2 - a c' (3)
+FLOP_COMMON_ORIGIN_TEST = 10.0  # what the common-origin form EXECUTES per test (5 FFMA): the rest is hoisted per sphere
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.45: SMs x lanes x 2 flop x max SM clock
 
 WORKLOADS = {
@@ -46,7 +52,12 @@ WORKLOADS = {
     "c5-1k": (1920, 1080, 64, 50, "sweep:1000", 5),
     "c5-10k": (1920, 1080, 64, 50, "sweep:10000", 5),
     "c5-100k": (1920, 1080, 64, 50, "sweep:100000", 5),
+    # beyond spheres, for the record
+    "cornell": (600, 600, 64, 50, "cornell", 2),
+    "final": (600, 600, 64, 50, "final", 2),
 }
+SCENE_DESC = {"random": "make-random-scene n=11 moving=true", "stress": "make-random-scene n=11, 10/45/45 % Lambert/metal/glass",
+              "cornell": "make-cornell-box classic", "final": "make-final (book 2), synthetic earth map"}
 
 
 def build_scene(name, nx, ny, seed):
@@ -59,6 +70,10 @@ def build_scene(name, nx, ny, seed):
         sc = rt.scene.make_material_stress_scene(nx, ny, 11, rng)
     elif name.startswith("sweep:"):
         sc = rt.scene.make_scale_sweep_scene(nx, ny, int(name.split(":")[1]), rng)
+    elif name == "cornell":
+        sc = rt.scene.make_cornell_box(nx, ny, True, rng)
+    elif name == "final":
+        sc = rt.scene.make_final(nx, ny, rng)
     else:
         raise ValueError(name)
     flat = rt.native.marshal_world(sc["world"])
@@ -66,15 +81,19 @@ def build_scene(name, nx, ny, seed):
     return flat, cam_type, cam
 
 
+def workload_string(name, flat):
+    """ONE description of the workload, used verbatim by both arms (the driver compares them)."""
+    nx, ny, spp, depth, scene_name, scene_seed = WORKLOADS[name]
+    desc = SCENE_DESC.get(scene_name, "5 hero objects + static r=0.2 spheres on a grid, scene.clj:369-375 placement rule")
+    return (f"{name}: {nx}x{ny}, {spp} spp, depth {depth}, {flat.n_spheres} primitives ({desc}, scene seed {scene_seed}), "
+            f"brute force over every primitive")
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
-
-
-def scene_bytes(flat):
-    return flat.nbytes() + 24 * 4
 
 
 class ClockSampler:
@@ -132,7 +151,8 @@ class ClockSampler:
 
 def run_reference(args, world, rank):
     """The reference's own CPU implementation of the path — here its C++ restatement (oracle/), all host
-    threads; each step = a bounded sample of the workload (2 of the 10 spp of every pixel)."""
+    threads; each step = one full pass over the workload when that stays bounded (C2: ~3 s per step on 16
+    threads), else a bounded sample of its spp, stated in `cpu_baseline.sample`."""
     if rank != 0:
         return 0
     import oracle
@@ -140,25 +160,26 @@ def run_reference(args, world, rank):
     nx, ny, spp, depth, scene_name, scene_seed = WORKLOADS[args.workload]
     flat, cam_type, cam = build_scene(scene_name, nx, ny, scene_seed)
     S = oracle.Scene(flat)
-    step_spp = max(1, min(spp, 2))
     cores = host_cores()            # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
+    # bounded: at most ~6 s of CPU work per step at ~0.25 G tests/s per core
+    budget = 6.0 * 0.25e9 * cores / (nx * ny * 2.6 * flat.n_spheres)
+    step_spp = int(max(1, min(spp, budget)))
     for w in range(args.warmup):
         S.render_accumulate(cam_type, cam, nx, ny, 0, 1, depth, seed=w, n_threads=cores)
     t0 = time.perf_counter()
     samples = tests = 0
     for k in range(args.steps):
-        _, c = S.render_accumulate(cam_type, cam, nx, ny, k * step_spp, step_spp, depth, seed=1, n_threads=cores)
+        _, c = S.render_accumulate(cam_type, cam, nx, ny, (k * step_spp) % max(1, spp), step_spp, depth, seed=1 + k, n_threads=cores)
         samples += c["samples"]
         tests += c["sphere_tests"]
     dt = time.perf_counter() - t0
     v = samples / dt
-    sample = f"{nx}x{ny}, {step_spp} of {spp} spp per step, depth {depth}, brute force over {flat.n_spheres} spheres"
+    sample = f"{nx}x{ny}, {step_spp} of {spp} spp per step, depth {depth}, brute force over {flat.n_spheres} primitives, double precision"
     line = {
         "impl": "reference", "metric": "samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: random-spheres scene {nx}x{ny}, {spp} spp, depth {depth}, "
-                               f"{flat.n_spheres} spheres (make-random-scene n=11 moving=true, scene seed {scene_seed})"},
+        "config": {"workload": workload_string(args.workload, flat)},
         "tests_per_sec": tests / dt,
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "C++ double-precision restatement of raytrace-clj (oracle/); the Clojure original "
@@ -167,6 +188,36 @@ def run_reference(args, world, rank):
     }
     print(json.dumps(line))
     return 0
+
+
+def in_library_run(rt, device_ids, flat, cam_type, cam, nx, ny, spp, depth, variant, steps, warmup, reduce_mode, rows, seed0=600):
+    """ONE process driving len(device_ids) GPUs through the C ABI with host buffers — what the JVM caller would do
+    (core.clj:99-108): rt_set_scene + rt_set_camera + rt_render per step, wall clock.  Returns a record."""
+    out_img = np.empty((ny, nx, 3), np.uint8)
+    with rt.native.Renderer(device_ids) as r:
+        r.set_option("reduce", reduce_mode)
+        r.set_option("rows", rows)
+
+        def one(seed, n_spp):
+            r.set_scene(flat)
+            r.set_camera(cam_type, cam)
+            r.render(nx, ny, n_spp, depth, seed=seed, variant=variant, linear=False, rgb8=True, out_rgb8=out_img)
+
+        for w in range(warmup):
+            one(500 + w, spp)
+        if warmup == 0:
+            one(499, max(1, len(device_ids)))       # allocations and module load only: one sample per device
+        r.reset_counters()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            one(seed0 + k, spp)
+        dt = time.perf_counter() - t0
+        c = r.counters()
+    return {"value": nx * ny * spp * steps / dt, "unit": "samples/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
+            "devices": len(device_ids), "partition": "interleaved rows" if rows else "sample slices",
+            "reduce": "ncclReduce (single process, ncclCommInitAll)" if reduce_mode else "NVLink peer loads fused into the resolve kernel",
+            "reduce_ms_per_step": c["reduce_ns"] * 1e-6 / steps, "device_ms_last_step": c["kernel_ns"] * 1e-6,
+            "tests_per_sec": c["sphere_tests"] / dt, "samples_check": c["samples"] == nx * ny * spp * steps}
 
 
 def main():
@@ -180,6 +231,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU renders the workload's spp (global spp = spp x N); strong: the spp are divided")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong-c3", action="store_true", help="skip the BASELINE config 3 strong-scaling block")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -202,9 +254,11 @@ def main():
     rtbuild.build_library()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # host-side barriers that keep the GPUs free (the in-library legs)
 
     nx, ny, spp, depth, scene_name, scene_seed = WORKLOADS[args.workload]
     if args.scaling == "strong":
@@ -270,110 +324,131 @@ def main():
     ctr = r.counters()
     launches = ctr["kernel_launches"]
     t = torch.tensor([my_ms, my_kernel_ms], device=dev, dtype=torch.float64)
-    cnt = torch.tensor([ctr["samples"], ctr["rays"], ctr["sphere_tests"], ctr["candidates"]], device=dev, dtype=torch.float64)
+    cnt = torch.tensor([ctr["samples"], ctr["rays"], ctr["sphere_tests"], ctr["candidates"], ctr["direct_tests"]], device=dev,
+                       dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     total_ms, kernel_ms = float(t[0]), float(t[1])
-    samples, rays, tests, cands = (float(x) for x in cnt)
+    samples, rays, tests, cands, direct = (float(x) for x in cnt)
     value = samples / (total_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ------------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 10)
-    out_img = np.empty((ny, nx, 3), np.uint8)
-    host_rgb = torch.empty(ny, nx, 3, dtype=torch.uint8, pin_memory=True)
+    e2e_rec = None
+    strong = None
+    if world == 1:
+        e2e_rec = in_library_run(rt, [local_rank], flat, cam_type, cam, nx, ny, spp, depth, args.variant, e2e_steps, 1, 0, 0)
+    else:
+        # the drop-in's caller is ONE process: rank 0 drives all N devices through rt_create(ids, N) + rt_render with
+        # host buffers while the other ranks sit on a HOST barrier (their GPUs stay free); both reduce flavours
+        r.close()
+        r = None
+        del d_sum, d_rgb, flush
+        torch.cuda.empty_cache()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            ids = list(range(world))
+            e2e_rec = in_library_run(rt, ids, flat, cam_type, cam, nx, ny, spp * world, depth, args.variant, e2e_steps, 2, 0, 0)
+            e2e_rec["nccl"] = in_library_run(rt, ids, flat, cam_type, cam, nx, ny, spp * world, depth, args.variant, e2e_steps, 2, 1, 0)
+        dist.barrier(group=cpu_group)
 
-    def e2e_step(seed):
-        r.set_scene(flat)                           # H2D: the marshalled SoA scene
-        r.set_camera(cam_type, cam)
-        if world == 1:
-            r.render(nx, ny, spp, depth, seed=seed, variant=args.variant, linear=False, rgb8=True, out_rgb8=out_img)
-        else:
-            d_sum.zero_()
-            r.render_accumulate_device(nx, ny, rank * spp, spp, d_sum.data_ptr(), max_depth=depth, seed=seed,
-                                       variant=args.variant, stream=stream.cuda_stream, sync=False)
-            dist.reduce(d_sum, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                r.resolve_device(nx, ny, total_spp, d_sum.data_ptr(), d_rgb.data_ptr(), stream=stream.cuda_stream, sync=False)
-                host_rgb.copy_(d_rgb, non_blocking=True)
-            torch.cuda.synchronize(dev)
-
-    e2e_step(500)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(600 + k)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = (nx * ny * spp * world * e2e_steps) / float(te[0])
+    # ---- BASELINE config 3, strong scaling: 3840x2160, 1024 spp split over the N devices of ONE context -----------
+    if not args.no_strong_c3 and args.workload == "c2":
+        if world > 1:
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            cnx, cny, cspp, cdepth, cscene, cseed = WORKLOADS["c3"]
+            cflat, ccam_type, ccam = build_scene(cscene, cnx, cny, cseed)
+            ids = list(range(world))
+            strong = {"workload": workload_string("c3", cflat), "n_gpus": world, "scaling": "strong",
+                      "path": "in-library: one process, rt_create(ids, N) + rt_set_scene + rt_set_camera + rt_render with host buffers, "
+                              "1 frame per leg, wall clock"}
+            legs = [("sample_slices", 0, 0)] + ([("sample_slices_nccl", 1, 0), ("interleaved_rows", 0, 1)] if world > 1 else [])
+            for name, red, rows in legs:
+                strong[name] = in_library_run(rt, ids, cflat, ccam_type, ccam, cnx, cny, cspp, cdepth, args.variant, 1, 0, red, rows)
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     # ---- stage shares: one extra (untimed) step with per-stage CUDA events (rank 0, wavefront only) ------
     stage = None
     if rank == 0 and args.variant == 1:
-        r.reset_counters()
-        r.set_profile(True)
-        d_sum.zero_()
-        r.render_accumulate_device(nx, ny, rank * spp, spp, d_sum.data_ptr(), max_depth=depth, seed=1,
-                                   variant=args.variant, stream=stream.cuda_stream, sync=True)
-        r.set_profile(False)
-        pc = r.counters()
+        with rt.native.Renderer([local_rank]) as rp:
+            rp.set_scene(flat)
+            rp.set_camera(cam_type, cam)
+            ps = torch.zeros(ny, nx, 3, device=dev, dtype=torch.float32)
+            rp.render_accumulate_device(nx, ny, 0, spp, ps.data_ptr(), max_depth=depth, seed=1, variant=args.variant, sync=True)   # warm
+            rp.reset_counters()
+            rp.set_profile(True)
+            ps.zero_()
+            rp.render_accumulate_device(nx, ny, 0, spp, ps.data_ptr(), max_depth=depth, seed=1, variant=args.variant, sync=True)
+            pc = rp.counters()
         stage = {k: pc[k + "_ns"] * 1e-6 for k in ("cull", "refine", "tiebreak", "shade")}
         stage["tests"] = pc["sphere_tests"]
-    barrier()
 
-    scene_desc = {"random": "make-random-scene n=11 moving=true", "stress": "make-random-scene n=11, 10/45/45 % Lambert/metal/glass"}.get(
-        scene_name, "5 hero objects + static r=0.2 spheres on a grid, scene.clj:369-375 placement rule")
     if rank == 0:
-        achieved_tflops = FLOP_PER_TEST * (tests / world) / (kernel_ms * 1e-3) / 1e12   # per GPU, whole render step
+        step_s = total_ms / args.steps * 1e-3
+        tests_gpu = tests / world / args.steps                  # per GPU per step
+        achieved_tflops = FLOP_PER_TEST * tests_gpu / step_s / 1e12            # per GPU, whole render step incl. reduce + resolve
+        # what the cull EXECUTES: the camera rays (one per sample when they share an origin) run the 10-flop common-origin form
+        n_prims = flat.n_spheres
+        cam_tests = (samples / world / args.steps) * n_prims if (cam[21] == 0.0 or cam_type == 0) else 0.0
+        executed_tflops = (FLOP_COMMON_ORIGIN_TEST * cam_tests + FLOP_PER_TEST * (tests_gpu - cam_tests)) / step_s / 1e12
         peak_measured = max(fp32_peak)
         line = {
             "metric": "samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: random-spheres scene {nx}x{ny}, {spp} spp per GPU, depth {depth}, "
-                            f"{flat.n_spheres} spheres ({scene_desc}, scene seed {scene_seed})",
+                "workload": workload_string(args.workload, flat),
                 "variant": "megakernel" if args.variant == 0 else "wavefront",
-                "parallelism": f"sample-slice x{world}" if world > 1 else "single GPU",
+                "parallelism": (f"sample slices x{world}: every GPU renders {spp} spp of the frame, one NCCL reduce"
+                                if world > 1 else "single GPU"),
                 "l2": "flushed between timed iterations (256 MiB fill); the scene itself is staged in shared memory",
-                "precision": "FP32 cull over all spheres, FP64 refine of survivors, FP32 shading",
+                "precision": "FP32 cull over all primitives, FP64 refine of survivors, FP32 shading",
             },
             "tests_per_sec": tests / (total_ms * 1e-3),
             "rays_per_sample": rays / samples,
             "cull_survivors_per_ray": cands / rays,
+            "direct_tests_per_ray": direct / rays,
             "kernel_ms_per_step": kernel_ms / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tflops, "peak": peak_measured, "unit": "TFLOP/s",
                 "frac": achieved_tflops / peak_measured if peak_measured else None,
+                "frac_executed_flop": executed_tflops / peak_measured if peak_measured else None,
                 "peak_source": "measured on this box: FFMA-chain microbenchmark (rt_measure_fp32_peak), max of scalar "
                                "FFMA and packed FFMA2",
                 "peak_ffma_tflops": fp32_peak[0], "peak_ffma2_tflops": fp32_peak[1],
                 "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
                 "flop_per_test": FLOP_PER_TEST,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the largest wf_cull launch of a C2 frame (a lane's 4.8 M
-                # camera rays), from the committed `ncu --set full` capture (profiles/r01_ncu_wf_cull_common_summary.txt)
-                "traffic": 343.5e6 if args.workload == "c2" and args.variant == 1 else None,
-                "traffic_note": "bytes per wf_cull launch (ncu): 72 B per ray (ray record in, pairs and closest-hit words out); "
-                                "the kernel is FP32-issue bound, not HBM bound (0.6 TB/s)",
-                "note": "non-tensor FP32 pipe; HBM is not the bound (scene in shared memory). `achieved` divides the "
-                        "17-flop tests by the time of the WHOLE render step (cull + refine + tie-break + shade kernels)",
+                "traffic": None,
+                "traffic_note": "not measured inside this run; the committed `ncu --set full` captures under profiles/ hold the "
+                                "dram__bytes of a wf_cull launch (ray record in, pairs out: the kernel is FP32-issue bound, not HBM bound)",
+                "note": "non-tensor FP32 pipe; HBM is not the bound (scene in shared memory). `achieved` = 17 algorithmic flop x "
+                        "(rays x primitives) / ms_per_step (the whole step: cull + refine + tie-break + shade + reduce + resolve); "
+                        "`frac_executed_flop` counts the camera rays' tests at the 10 flop their common-origin form executes",
                 "dominant_kernel": None if not stage else {
                     "name": "wf_cull", "ms_per_step": stage["cull"],
                     "achieved": FLOP_PER_TEST * stage["tests"] / (stage["cull"] * 1e-3) / 1e12,
                     "frac": FLOP_PER_TEST * stage["tests"] / (stage["cull"] * 1e-3) / 1e12 / peak_measured,
                     "share_of_step": stage["cull"] / max(1e-9, sum(stage[k] for k in ("cull", "refine", "tiebreak", "shade"))),
                     "other_stages_ms": {k: stage[k] for k in ("refine", "tiebreak", "shade")},
+                    "note": "one lane, stages serialised with CUDA events (rt_set_profile): shares, not the overlapped step",
                 },
             },
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": scene_bytes(flat),
-                    "d2h_bytes_per_step": nx * ny * 3, "steps": e2e_steps},
+            "e2e": {"value": e2e_rec["value"], "unit": "samples/s", "h2d_bytes_per_step": flat.nbytes() + 24 * 4,
+                    "d2h_bytes_per_step": nx * ny * 3, "steps": e2e_steps, "ms_per_step": e2e_rec["ms_per_step"],
+                    "path": ("rt_set_scene + rt_set_camera + rt_render, host buffers" if world == 1 else
+                             f"ONE process, rt_create over {world} devices + rt_set_scene + rt_set_camera + rt_render, host buffers; "
+                             f"{e2e_rec['partition']}, {e2e_rec['reduce']}"),
+                    "reduce_ms_per_step": e2e_rec["reduce_ms_per_step"],
+                    **({"nccl_reduce": e2e_rec["nccl"]} if "nccl" in e2e_rec else {})},
             "device": info,
         }
+        if strong:
+            line["strong_c3"] = strong
         if world == 1 and not args.no_cpu_baseline:
             import oracle
 
@@ -392,9 +467,20 @@ def main():
                 "sample": f"{nx}x{ny}, {cpu_spp} of {spp} spp, depth {depth}, brute force, double precision",
                 "note": "C++ restatement of raytrace-clj (oracle/), OpenMP; the Clojure original cannot run here (no JVM)",
             }
+            # the reference itself does NOT brute-force: every scene is wrapped in make-bvh (hitable.clj:108-123).  The same
+            # restatement traversing its own reference-style BVH states the reference's real algorithmic complexity.
+            S.build_bvh(0.0, 1.0, seed=1)
+            t0 = time.perf_counter()
+            _, cb = S.render_accumulate(cam_type, cam, nx, ny, 0, cpu_spp, depth, seed=1, n_threads=cores, use_bvh=True)
+            dtb = time.perf_counter() - t0
+            line["cpu_baseline"]["bvh"] = {"value": cb["samples"] / dtb, "unit": "samples/s", "seconds": dtb,
+                                           "leaf_tests_per_ray": cb["sphere_tests"] / cb["rays"], "aabb_tests_per_ray": cb["aabb_tests"] / cb["rays"],
+                                           "note": "same restatement through bvh-node.hit? / AABB.hit? (hitable.clj:36-48, 97-106)"}
         print(json.dumps(line))
-    r.close()
+    if r is not None:
+        r.close()
     if world > 1:
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
     return 0
 

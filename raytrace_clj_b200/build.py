@@ -36,7 +36,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     cmd = [_nvcc()] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
-    cmd += ["-o", OUT] + [os.path.join(CSRC, f) for f in SOURCES]
+    cmd += ["-o", OUT] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "csrc", "build.log")
     with open(log, "w") as f:

@@ -6,7 +6,9 @@
 #include "../../include/raytrace_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math_constants.h>
+#include <nccl.h>   // types only: the library itself is dlopen'ed when a multi-device context asks for the NCCL reduce
 
 #include <algorithm>
 #include <cmath>
@@ -78,6 +80,22 @@ struct DeviceBuffers {
     char name[64] = {0};
     float last_ms = 0.f;
     bool timed = false;
+    // pinned staging for the results of rt_render (root device): D2H at link speed, then one host memcpy into the caller's buffer
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;   // around the cross-device reduce (RT_CTR_REDUCE_NS)
+};
+
+// NCCL, loaded on demand (single process, one communicator per device: ncclCommInitAll)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::vector<ncclComm_t> comms;
 };
 
 }  // namespace
@@ -125,7 +143,9 @@ struct rt_ctx {
     std::mutex err_mu;
     bool profile = false;
     double stage_ms[4] = {0, 0, 0, 0};   // cull, refine, tie-break, shade (profile mode)
+    double reduce_ms = 0.0;              // cross-device reduce of the multi-device renders since the last reset
     std::vector<bool> peer_ok;
+    NcclApi nccl;
 };
 
 namespace {
@@ -667,6 +687,46 @@ int ensure_window(rt_ctx* ctx, double lo, double hi) {
     return RT_OK;
 }
 
+int ensure_stage(rt_ctx* ctx, DeviceBuffers& d, size_t bytes) {
+    if (d.h_stage_bytes >= bytes) return RT_OK;
+    if (d.h_stage) cudaFreeHost(d.h_stage);
+    d.h_stage = nullptr;
+    d.h_stage_bytes = 0;
+    RT_CUDA(ctx, cudaHostAlloc(&d.h_stage, bytes, cudaHostAllocDefault));
+    d.h_stage_bytes = bytes;
+    return RT_OK;
+}
+
+// dlopen libnccl.so.2 (the system library, or the one a host process such as PyTorch already loaded) and build one
+// communicator per device of the context.  Failing to do so is an error: the caller asked for the NCCL reduce.
+int ensure_nccl(rt_ctx* ctx) {
+    NcclApi& N = ctx->nccl;
+    if (!N.comms.empty()) return RT_OK;
+    if (!N.handle) {
+        N.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!N.handle) return fail(ctx, RT_ERR_NCCL, std::string("dlopen(libnccl.so.2): ") + dlerror());
+        auto sym = [&](const char* name) { return dlsym(N.handle, name); };
+        N.CommInitAll = (decltype(N.CommInitAll))sym("ncclCommInitAll");
+        N.CommDestroy = (decltype(N.CommDestroy))sym("ncclCommDestroy");
+        N.Reduce = (decltype(N.Reduce))sym("ncclReduce");
+        N.GroupStart = (decltype(N.GroupStart))sym("ncclGroupStart");
+        N.GroupEnd = (decltype(N.GroupEnd))sym("ncclGroupEnd");
+        N.GetErrorString = (decltype(N.GetErrorString))sym("ncclGetErrorString");
+        if (!N.CommInitAll || !N.CommDestroy || !N.Reduce || !N.GroupStart || !N.GroupEnd || !N.GetErrorString)
+            return fail(ctx, RT_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+    }
+    std::vector<int> ids;
+    for (auto& d : ctx->devs) ids.push_back(d.dev);
+    N.comms.assign(ids.size(), nullptr);
+    ncclResult_t r = N.CommInitAll(N.comms.data(), (int)ids.size(), ids.data());
+    if (r != ncclSuccess) {
+        N.comms.clear();
+        return fail(ctx, RT_ERR_NCCL, std::string("ncclCommInitAll: ") + N.GetErrorString(r));
+    }
+    cudaSetDevice(ctx->devs[0].dev);
+    return RT_OK;
+}
+
 int check_ready(rt_ctx* ctx) {
     if (!ctx) return RT_ERR_ARG;
     if (!ctx->has_scene) return fail(ctx, RT_ERR_STATE, "rt_set_scene has not been called");
@@ -715,6 +775,7 @@ int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
             (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev0)) != cudaSuccess || (e = cudaEventCreate(&d.ev1)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.ev_r0)) != cudaSuccess || (e = cudaEventCreate(&d.ev_r1)) != cudaSuccess ||
             (e = cudaMalloc(&d.d_counters, (DC_COUNT + 1) * sizeof(unsigned long long))) != cudaSuccess ||
             (e = cudaMemset(d.d_counters, 0, (DC_COUNT + 1) * sizeof(unsigned long long))) != cudaSuccess) {
             g_create_error = std::string("device init: ") + cudaGetErrorString(e);
@@ -750,6 +811,9 @@ int rt_create(rt_ctx** out, const int* device_ids, int n_devices) {
 
 void rt_destroy(rt_ctx* ctx) {
     if (!ctx) return;
+    for (auto c : ctx->nccl.comms)
+        if (c && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(c);
+    ctx->nccl.comms.clear();
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -764,6 +828,9 @@ void rt_destroy(rt_ctx* ctx) {
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.ev_done) cudaEventDestroy(d.ev_done);
+        if (d.ev_r0) cudaEventDestroy(d.ev_r0);
+        if (d.ev_r1) cudaEventDestroy(d.ev_r1);
+        if (d.h_stage) cudaFreeHost(d.h_stage);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
@@ -1268,8 +1335,12 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
     if ((long long)nx * ny > 0x7fffffffLL / 3) return fail(ctx, RT_ERR_ARG, "image too large");
     const size_t px = (size_t)nx * ny;
     const int G = (int)ctx->devs.size();
-    // sample slices: device g renders samples [g*S/G, (g+1)*S/G) of every pixel; one host thread per device
-    // (the wavefront variant polls its queue count from the host, so devices must not be driven serially)
+    const bool by_rows = G > 1 && ctx->opt.rows != 0;
+    const bool use_nccl = G > 1 && ctx->opt.reduce != 0;
+    if (use_nccl && (rc = ensure_nccl(ctx))) return rc;
+    // Partition over the devices of the context (core.clj:100-108's chunk pool): sample slices — device g
+    // renders samples [g*S/G, (g+1)*S/G) of every pixel — or interleaved rows — device g renders rows j = g (mod G) with
+    // all S samples.  One host thread per device (each feeds its own wavefront loop).
     auto device_work = [&](int g) -> int {
         DeviceBuffers& d = ctx->devs[g];
         RT_CUDA(ctx, cudaSetDevice(d.dev));
@@ -1278,7 +1349,9 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
         int s0 = (int)((long long)nsamples * g / G), s1 = (int)((long long)nsamples * (g + 1) / G);
         RT_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
         RT_CUDA(ctx, cudaMemsetAsync(d.d_sum, 0, px * 3 * sizeof(float), d.stream));
-        if ((r = launch_render(ctx, d, nx, ny, s0, s1 - s0, 0, 1, max_depth, seed, variant, d.d_sum, d.stream))) return r;
+        if (by_rows) r = launch_render(ctx, d, nx, ny, 0, nsamples, g, G, max_depth, seed, variant, d.d_sum, d.stream);
+        else r = launch_render(ctx, d, nx, ny, s0, s1 - s0, 0, 1, max_depth, seed, variant, d.d_sum, d.stream);
+        if (r) return r;
         RT_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
         RT_CUDA(ctx, cudaEventRecord(d.ev_done, d.stream));
         d.timed = true;
@@ -1300,7 +1373,9 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
             return bad;
         }
     }
-    // combine on the root device: the resolve kernel reads the peers' sums over NVLink
+    // combine on the root device.  Default: the resolve kernel reads the peers' float sums over NVLink peer mappings (the
+    // reduce fused into core.clj:52-57's gamma / quantise pass).  Option "reduce" = 1: one ncclReduce(sum, float32,
+    // nx*ny*3, root 0) over the per-device communicators, then the plain resolve.
     DeviceBuffers& root = ctx->devs[0];
     RT_CUDA(ctx, cudaSetDevice(root.dev));
     ResolveParams P{};
@@ -1308,31 +1383,63 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
     P.rgb8 = out_rgb8 ? root.d_rgb8 : nullptr;
     P.mean = out_linear_rgb ? root.d_mean : nullptr;
     P.sum_out = nullptr;
-    for (int g = 1; g < G; ++g) {
-        DeviceBuffers& d = ctx->devs[g];
-        RT_CUDA(ctx, cudaStreamWaitEvent(root.stream, d.ev_done, 0));
-        if (ctx->peer_ok[g]) {
-            P.peers[P.n_peers++] = d.d_sum;
-        } else {   // no peer mapping: stage through a copy, then add
-            if ((rc = ensure_scratch(ctx, root, (size_t)(G - 1) * px * 3 * sizeof(float)))) return rc;
-            float* stage = (float*)root.scratch + (size_t)(g - 1) * px * 3;
-            RT_CUDA(ctx, cudaMemcpyPeerAsync(stage, root.dev, d.d_sum, d.dev, px * 3 * sizeof(float), root.stream));
-            P.peers[P.n_peers++] = stage;
+    const int total = nx * ny * 3;
+    if (use_nccl) {
+        NcclApi& N = ctx->nccl;
+        for (int g = 1; g < G; ++g) RT_CUDA(ctx, cudaStreamWaitEvent(root.stream, ctx->devs[g].ev_done, 0));   // time the reduce alone
+        RT_CUDA(ctx, cudaEventRecord(root.ev_r0, root.stream));
+        ncclResult_t nr = N.GroupStart();
+        for (int g = 0; g < G && nr == ncclSuccess; ++g)
+            nr = N.Reduce(ctx->devs[g].d_sum, ctx->devs[g].d_sum, (size_t)total, ncclFloat, ncclSum, 0, N.comms[(size_t)g], ctx->devs[g].stream);
+        const ncclResult_t ge = N.GroupEnd();
+        if (nr == ncclSuccess) nr = ge;
+        if (nr != ncclSuccess) {
+            for (auto& dv : ctx->devs) { cudaSetDevice(dv.dev); cudaDeviceSynchronize(); }
+            cudaSetDevice(root.dev);
+            return fail(ctx, RT_ERR_NCCL, std::string("ncclReduce: ") + N.GetErrorString(nr));
         }
+        RT_CUDA(ctx, cudaSetDevice(root.dev));
+        RT_CUDA(ctx, cudaEventRecord(root.ev_r1, root.stream));
+        resolve_kernel<<<(total + 255) / 256, 256, 0, root.stream>>>(P);
+    } else {
+        for (int g = 1; g < G; ++g) {
+            DeviceBuffers& d = ctx->devs[g];
+            RT_CUDA(ctx, cudaStreamWaitEvent(root.stream, d.ev_done, 0));
+            if (ctx->peer_ok[g]) {
+                P.peers[P.n_peers++] = d.d_sum;
+            } else {   // no peer mapping: stage through a copy, then add
+                if ((rc = ensure_scratch(ctx, root, (size_t)(G - 1) * px * 3 * sizeof(float)))) return rc;
+                float* stage = (float*)root.scratch + (size_t)(g - 1) * px * 3;
+                RT_CUDA(ctx, cudaMemcpyPeerAsync(stage, root.dev, d.d_sum, d.dev, px * 3 * sizeof(float), root.stream));
+                P.peers[P.n_peers++] = stage;
+            }
+        }
+        RT_CUDA(ctx, cudaEventRecord(root.ev_r0, root.stream));
+        resolve_kernel<<<(total + 255) / 256, 256, 0, root.stream>>>(P);   // reduce + resolve in one pass
+        RT_CUDA(ctx, cudaEventRecord(root.ev_r1, root.stream));
     }
-    int total = nx * ny * 3;
-    resolve_kernel<<<(total + 255) / 256, 256, 0, root.stream>>>(P);
     RT_CUDA(ctx, cudaGetLastError());
     ctx->n_launches += 1;
-    if (out_linear_rgb)
-        RT_CUDA(ctx, cudaMemcpyAsync(out_linear_rgb, root.d_mean, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
-    if (out_rgb8) RT_CUDA(ctx, cudaMemcpyAsync(out_rgb8, root.d_rgb8, px * 3, cudaMemcpyDeviceToHost, root.stream));
+    // results: D2H into pinned staging at link speed, then one host memcpy into the caller's (pageable) buffer
+    const size_t b_lin = out_linear_rgb ? align_up(px * 3 * sizeof(float), 256) : 0, b_rgb = out_rgb8 ? px * 3 : 0;
+    if (b_lin + b_rgb) {
+        if ((rc = ensure_stage(ctx, root, b_lin + b_rgb))) return rc;
+        if (out_linear_rgb) RT_CUDA(ctx, cudaMemcpyAsync(root.h_stage, root.d_mean, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
+        if (out_rgb8) RT_CUDA(ctx, cudaMemcpyAsync((char*)root.h_stage + b_lin, root.d_rgb8, px * 3, cudaMemcpyDeviceToHost, root.stream));
+    }
     RT_CUDA(ctx, cudaStreamSynchronize(root.stream));
+    if (out_linear_rgb) memcpy(out_linear_rgb, root.h_stage, px * 3 * sizeof(float));
+    if (out_rgb8) memcpy(out_rgb8, (char*)root.h_stage + b_lin, px * 3);
     for (int g = 1; g < G; ++g) {
         RT_CUDA(ctx, cudaSetDevice(ctx->devs[g].dev));
         RT_CUDA(ctx, cudaStreamSynchronize(ctx->devs[g].stream));
     }
     cudaSetDevice(root.dev);
+    if (G > 1) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, root.ev_r0, root.ev_r1) == cudaSuccess) ctx->reduce_ms += ms;
+        cudaGetLastError();
+    }
     return RT_OK;
 }
 
@@ -1658,6 +1765,7 @@ int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]) {
     out[RT_CTR_REFINE_NS] = (uint64_t)(ctx->stage_ms[1] * 1e6);
     out[RT_CTR_TIEBREAK_NS] = (uint64_t)(ctx->stage_ms[2] * 1e6);
     out[RT_CTR_SHADE_NS] = (uint64_t)(ctx->stage_ms[3] * 1e6);
+    out[RT_CTR_REDUCE_NS] = (uint64_t)(ctx->reduce_ms * 1e6);
     return RT_OK;
 }
 
@@ -1672,6 +1780,7 @@ int rt_reset_counters(rt_ctx* ctx) {
     cudaSetDevice(ctx->devs[0].dev);
     ctx->n_launches = 0;
     for (double& x : ctx->stage_ms) x = 0.0;
+    ctx->reduce_ms = 0.0;
     return RT_OK;
 }
 

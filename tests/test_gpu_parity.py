@@ -530,21 +530,29 @@ def test_error_paths(scene_c2):
 
 
 def test_multi_device_in_library_matches_single(scene_c2):
-    """rt_create with two devices (the single-process path a JVM caller uses): sample slices on each device,
-    per-device float sums combined on device 0 over NVLink peer access inside the resolve kernel."""
+    """rt_create over ALL visible devices (the single-process path a JVM caller uses, core.clj:99-108): sample slices or
+    interleaved rows on each device, per-device float sums combined on device 0 — by NVLink peer loads inside the
+    resolve kernel, or by one ncclReduce (libnccl.so.2 loaded on demand) — equal the single-device render."""
     import torch
 
-    if torch.cuda.device_count() < 2:
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
         pytest.skip("needs 2 GPUs")
     flat, cam_type, cam, _ = scene_c2
-    nx, ny, ns = 160, 96, 8
-    with rt.native.Renderer([0]) as r1, rt.native.Renderer([0, 1]) as r2:
-        for r in (r1, r2):
-            r.set_scene(flat)
-            r.set_camera(cam_type, cam)
+    nx, ny, ns = 160, 96, 16
+    with rt.native.Renderer([0]) as r1:
+        r1.set_scene(flat)
+        r1.set_camera(cam_type, cam)
         a, img_a = r1.render(nx, ny, ns, 50, seed=11)
-        b, img_b = r2.render(nx, ny, ns, 50, seed=11)
-        c2 = r2.counters()
-    assert np.allclose(a, b, rtol=1e-4, atol=1e-4)          # same paths; float summation order differs
-    assert (img_a != img_b).mean() < 1e-3
-    assert c2["samples"] == nx * ny * ns
+    for reduce_mode in (0, 1):
+        for rows in (0, 1):
+            with rt.native.Renderer(list(range(n_dev))) as r2:
+                r2.set_option("reduce", reduce_mode)
+                r2.set_option("rows", rows)
+                r2.set_scene(flat)
+                r2.set_camera(cam_type, cam)
+                b, img_b = r2.render(nx, ny, ns, 50, seed=11)
+                c2 = r2.counters()
+            assert np.allclose(a, b, rtol=1e-4, atol=1e-4), (reduce_mode, rows)   # same paths; float summation order differs
+            assert (img_a != img_b).mean() < 1e-3
+            assert c2["samples"] == nx * ny * ns and c2["reduce_ns"] > 0
