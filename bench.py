@@ -230,6 +230,7 @@ def main():
     ap.add_argument("--variant", type=int, default=int(os.environ.get("RT_VARIANT", "1")), help="1 wavefront (default), 0 megakernel")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU renders the workload's spp (global spp = spp x N); strong: the spp are divided")
+    ap.add_argument("--accel", default="brute", choices=["brute", "bvh"], help="closest-hit search: brute force (the roofline path) or the GPU BVH")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong-c3", action="store_true", help="skip the BASELINE config 3 strong-scaling block")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
@@ -269,6 +270,8 @@ def main():
     r = rt.native.Renderer([local_rank])
     r.set_scene(flat)
     r.set_camera(cam_type, cam)
+    if args.accel == "bvh":
+        r.set_accel(rt.native.RT_ACCEL_BVH)
     info = r.device_info()
 
     d_sum = torch.zeros(ny, nx, 3, device=dev, dtype=torch.float32)
@@ -372,7 +375,7 @@ def main():
 
     # ---- stage shares: one extra (untimed) step with per-stage CUDA events (rank 0, wavefront only) ------
     stage = None
-    if rank == 0 and args.variant == 1:
+    if rank == 0 and args.variant == 1 and args.accel == "brute":
         with rt.native.Renderer([local_rank]) as rp:
             rp.set_scene(flat)
             rp.set_camera(cam_type, cam)
@@ -402,6 +405,7 @@ def main():
             "config": {
                 "workload": workload_string(args.workload, flat),
                 "variant": "megakernel" if args.variant == 0 else "wavefront",
+                "accel": "GPU BVH (RT_ACCEL_BVH): tests_per_sec counts the exact leaf tests actually made" if args.accel == "bvh" else "brute force",
                 "parallelism": (f"sample slices x{world}: every GPU renders {spp} spp of the frame, one NCCL reduce"
                                 if world > 1 else "single GPU"),
                 "l2": "flushed between timed iterations (256 MiB fill); the scene itself is staged in shared memory",

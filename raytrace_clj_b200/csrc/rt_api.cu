@@ -80,6 +80,9 @@ struct DeviceBuffers {
     char name[64] = {0};
     float last_ms = 0.f;
     bool timed = false;
+    // RT_ACCEL_BVH: the flattened tree (4 float4 per node), rebuilt with the scene / the movers' time window
+    float4* bvh_nodes = nullptr;
+    size_t bvh_cap = 0;
     // pinned staging for the results of rt_render (root device): D2H at link speed, then one host memcpy into the caller's buffer
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -131,6 +134,7 @@ struct rt_ctx {
     int cull_cap = 0, preloaded = 0;
     int generic = 0;              // some leaf is not a plain sphere (rt_set_scene_ex)
     int accel = RT_ACCEL_BRUTE_FORCE;
+    bool bvh_dirty = true;        // the tree must be (re)built before the next BVH render
     // time window [win_lo, win_hi] the movers' bounding spheres cover; grown (and the cull records rebuilt)
     // when a camera shutter interval or a traced ray's time falls outside
     double win_lo = 0.0, win_hi = 0.0;
@@ -350,7 +354,9 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     RT_CUDA(ctx, cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
     RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_bps, k_tail, 256, tail_smem));
     const int tail_grid = d.sm_count * (opt.tail_ctas_per_sm > 0 ? opt.tail_ctas_per_sm : (n_lanes > 1 ? 1 : std::max(1, std::min(tail_bps, 2))));
-    const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile;
+    const bool bvh = ctx->accel == RT_ACCEL_BVH;   // closest hit through the tree: one wf_bvh launch instead of cull + refine + tie-break
+    void (*k_bvh)(const WaveParams) = gen ? wf_bvh<true> : wf_bvh<false>;
+    const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile && !bvh;
 
     const int light_block = std::max(64, std::min(256, opt.light_block / 32 * 32));   // <= a cull CTA in every resource
     const int light_grid = d.sm_count * 8 * 256 / light_block;
@@ -360,7 +366,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     // on a high-priority stream, take the freed slots at once instead of waiting for the whole persistent cull to end.
     // 0 = persistent cull warps, one stream per lane.
     const int claims_env = std::max(0, opt.cull_claims);
-    const int claims = (ctx->profile || !ctx->preloaded || n_lanes < 2) ? 0 : claims_env;
+    const int claims = (ctx->profile || !ctx->preloaded || n_lanes < 2 || bvh) ? 0 : claims_env;
     const int cull_warps = cull_block / 32, resident_warps = cull_grid * cull_warps;
     unsigned n_bound[kMaxLanes];   // upper bound of each lane's queue length (sizes the short-CTA grids)
     WaveParams W[kMaxLanes];
@@ -463,7 +469,15 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     for (auto& x : e) { RT_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
                 if (ctx->profile) cudaEventRecord(e[0], st[l]);
                 W[l].iter = (unsigned)(enq[l] + 1);
-                if (claims) {
+                if (bvh) {
+                    W[l].trace = trace_slot("bvh", l, iter_no[l]);
+                    k_bvh<<<light_grid, 128, 0, st[l]>>>(W[l]);
+                    if (ctx->profile) { cudaEventRecord(e[1], st[l]); cudaEventRecord(e[2], st[l]); cudaEventRecord(e[3], st[l]); }
+                    W[l].trace = trace_slot("shade", l, iter_no[l]);
+                    k_shade<<<light_grid, light_block, 0, st[l]>>>(W[l]);
+                    if (ctx->profile) cudaEventRecord(e[4], st[l]);
+                    ctx->n_launches -= 2;   // two launches this iteration, not four
+                } else if (claims) {
                     // every work item of the launch must find a warp: items <= n / (32 R) + 2 resident_warps + 8 (wf_cull_body)
                     const unsigned items = n_bound[l] / (32u * kR) + 2u * (unsigned)resident_warps + 8u;
                     const unsigned ctas = (items + (unsigned)(cull_warps * claims) - 1u) / (unsigned)(cull_warps * claims);
@@ -675,6 +689,7 @@ int ensure_window(rt_ctx* ctx, double lo, double hi) {
     bool any_moving = false;
     for (unsigned f : ctx->h_flags) any_moving |= (f & RT_SPHERE_MOVING) != 0;
     if (!any_moving) return RT_OK;
+    ctx->bvh_dirty = true;   // the movers' boxes cover the window too
     std::vector<float> cull((size_t)(ctx->n_cull + ctx->n_spheres - ctx->n_list) * 4);
     build_cull_records(ctx, ctx->win_lo, ctx->win_hi, cull.data());
     if (cull.empty()) return RT_OK;
@@ -684,6 +699,99 @@ int ensure_window(rt_ctx* ctx, double lo, double hi) {
         RT_CUDA(ctx, cudaMemcpy((void*)d.sc.cull_a, cull.data(), cull.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     cudaSetDevice(ctx->devs[0].dev);
+    return RT_OK;
+}
+
+// RT_ACCEL_BVH: build the tree over the listed leaves on the host — the reference's make-bvh shape (hitable.clj:108-123:
+// sort along one axis, the left half takes ceil(n/2), a lone leaf is stored as both children) with the axis chosen as
+// the longest extent of the centroids instead of at random — and upload it.  Leaf boxes = the boxes of the leaves' world-
+// space bounding spheres over the movers' time window, widened so the FP32 slab test can only over-report.
+struct BuildLeaf {
+    float lo[3], hi[3];
+    float c[3];
+    int k;
+};
+int bvh_build_node(std::vector<BuildLeaf>& L, int begin, int end, std::vector<float>& nodes, float lo[3], float hi[3]) {
+    if (end - begin == 1) {
+        for (int a = 0; a < 3; ++a) { lo[a] = L[(size_t)begin].lo[a]; hi[a] = L[(size_t)begin].hi[a]; }
+        return ~L[(size_t)begin].k;
+    }
+    float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = begin; i < end; ++i)
+        for (int a = 0; a < 3; ++a) { cmin[a] = std::min(cmin[a], L[(size_t)i].c[a]); cmax[a] = std::max(cmax[a], L[(size_t)i].c[a]); }
+    int axis = 0;
+    for (int a = 1; a < 3; ++a) if (cmax[a] - cmin[a] > cmax[axis] - cmin[axis]) axis = a;
+    const int mid = begin + (end - begin + 1) / 2;
+    std::nth_element(L.begin() + begin, L.begin() + mid, L.begin() + end,
+                     [axis](const BuildLeaf& x, const BuildLeaf& y) { return x.c[axis] < y.c[axis]; });
+    const size_t me = nodes.size() / 16;
+    nodes.resize(nodes.size() + 16, 0.f);
+    float llo[3], lhi[3], rlo[3], rhi[3];
+    const int left = bvh_build_node(L, begin, mid, nodes, llo, lhi);
+    const int right = bvh_build_node(L, mid, end, nodes, rlo, rhi);
+    float* N = nodes.data() + 16 * me;
+    N[0] = llo[0]; N[1] = llo[1]; N[2] = llo[2]; N[3] = lhi[0]; N[4] = lhi[1]; N[5] = lhi[2];
+    N[6] = rlo[0]; N[7] = rlo[1]; N[8] = rlo[2]; N[9] = rhi[0]; N[10] = rhi[1]; N[11] = rhi[2];
+    memcpy(&N[12], &left, 4);
+    memcpy(&N[13], &right, 4);
+    for (int a = 0; a < 3; ++a) { lo[a] = std::min(llo[a], rlo[a]); hi[a] = std::max(lhi[a], rhi[a]); }
+    return (int)me;
+}
+int ensure_bvh(rt_ctx* ctx) {
+    if (!ctx->bvh_dirty) return RT_OK;
+    const int n = ctx->n_list;
+    std::vector<BuildLeaf> L((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        BuildLeaf& b = L[(size_t)k];
+        b.k = k;
+        const bool moving = (ctx->h_flags[(size_t)k] & RT_SPHERE_MOVING) != 0;
+        const double r = std::fabs(ctx->h_bs_r[(size_t)k]);
+        for (int a = 0; a < 3; ++a) {
+            double pa = ctx->h_bs_c0[3 * (size_t)k + a], pb = pa;
+            if (moving) {
+                const double p0 = ctx->h_bs_c0[3 * (size_t)k + a], p1 = ctx->h_bs_c1[3 * (size_t)k + a];
+                const double t0 = ctx->h_t0t1[2 * k], t1 = ctx->h_t0t1[2 * k + 1];
+                const double fa = (ctx->win_lo - t0) / (t1 - t0), fb = (ctx->win_hi - t0) / (t1 - t0);
+                pa = p0 * (1.0 - fa) + p1 * fa;
+                pb = p0 * (1.0 - fb) + p1 * fb;
+            }
+            const double lo = std::min(pa, pb) - r, hi = std::max(pa, pb) + r;
+            const double m = 1e-6 * (std::fabs(lo) + std::fabs(hi) + r) + 1e-30;   // covers the float rounding of the box and its share of the slab test
+            b.lo[a] = nextafterf((float)(lo - m), -INFINITY);
+            b.hi[a] = nextafterf((float)(hi + m), INFINITY);
+            b.c[a] = (float)(0.5 * (lo + hi));
+        }
+    }
+    std::vector<float> nodes;
+    nodes.reserve(16 * (size_t)std::max(1, n));
+    float lo[3], hi[3];
+    if (n == 1) {   // a lone leaf is both children of the root (hitable.clj:113-114)
+        nodes.assign(16, 0.f);
+        for (int a = 0; a < 3; ++a) { nodes[(size_t)a] = nodes[6 + (size_t)a] = L[0].lo[a]; nodes[3 + (size_t)a] = nodes[9 + (size_t)a] = L[0].hi[a]; }
+        const int leaf = ~0;
+        memcpy(&nodes[12], &leaf, 4);
+        memcpy(&nodes[13], &leaf, 4);
+    } else {
+        const int root = bvh_build_node(L, 0, n, nodes, lo, hi);
+        if (root != 0) return fail(ctx, RT_ERR_STATE, "BVH build: the root is not node 0");
+    }
+    for (auto& d : ctx->devs) {
+        RT_CUDA(ctx, cudaSetDevice(d.dev));
+        RT_CUDA(ctx, cudaDeviceSynchronize());
+        const size_t bytes = nodes.size() * sizeof(float);
+        if (d.bvh_cap < bytes) {
+            if (d.bvh_nodes) cudaFree(d.bvh_nodes);
+            d.bvh_nodes = nullptr;
+            d.bvh_cap = 0;
+            RT_CUDA(ctx, cudaMalloc(&d.bvh_nodes, bytes));
+            d.bvh_cap = bytes;
+        }
+        RT_CUDA(ctx, cudaMemcpy(d.bvh_nodes, nodes.data(), bytes, cudaMemcpyHostToDevice));
+        d.sc.bvh = d.bvh_nodes;
+        d.sc.bvh_nodes = (int)(nodes.size() / 16);
+    }
+    cudaSetDevice(ctx->devs[0].dev);
+    ctx->bvh_dirty = false;
     return RT_OK;
 }
 
@@ -735,9 +843,10 @@ int check_ready(rt_ctx* ctx) {
 
 int check_camera_times(rt_ctx* ctx) {
     if (!ctx->has_cam) return fail(ctx, RT_ERR_STATE, "rt_set_camera has not been called");
-    if (ctx->cam.type == CAM_THIN_LENS)
-        return ensure_window(ctx, std::min(ctx->cam.t0, ctx->cam.t1), std::max(ctx->cam.t0, ctx->cam.t1));
-    return ensure_window(ctx, 0.0, 0.0);
+    int rc = ctx->cam.type == CAM_THIN_LENS ? ensure_window(ctx, std::min(ctx->cam.t0, ctx->cam.t1), std::max(ctx->cam.t0, ctx->cam.t1))
+                                            : ensure_window(ctx, 0.0, 0.0);
+    if (rc) return rc;
+    return ctx->accel == RT_ACCEL_BVH ? ensure_bvh(ctx) : RT_OK;
 }
 
 }  // namespace
@@ -831,6 +940,7 @@ void rt_destroy(rt_ctx* ctx) {
         if (d.ev_r0) cudaEventDestroy(d.ev_r0);
         if (d.ev_r1) cudaEventDestroy(d.ev_r1);
         if (d.h_stage) cudaFreeHost(d.h_stage);
+        if (d.bvh_nodes) cudaFree(d.bvh_nodes);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
@@ -1231,6 +1341,7 @@ int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* s, const rt_scene_ext* x) 
     ctx->win_lo = win_lo;
     ctx->win_hi = win_hi;
     ctx->has_scene = true;
+    ctx->bvh_dirty = true;
     return RT_OK;
 }
 
@@ -1241,6 +1352,7 @@ int rt_set_accel(rt_ctx* ctx, int accel) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (accel != RT_ACCEL_BRUTE_FORCE && accel != RT_ACCEL_BVH) return fail(ctx, RT_ERR_ARG, "unknown accelerator");
     ctx->accel = accel;
+    if (accel == RT_ACCEL_BVH && ctx->has_scene) return ensure_bvh(ctx);
     return RT_OK;
 }
 
@@ -1547,6 +1659,20 @@ int rt_trace_primary(rt_ctx* ctx, int n, const float* origins, const float* dirs
     RT_CUDA(ctx, cudaMemcpyAsync(d_o, origins, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
     RT_CUDA(ctx, cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
     if (times) RT_CUDA(ctx, cudaMemcpyAsync(d_tm, times, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
+    if (ctx->accel == RT_ACCEL_BVH) {
+        if ((rc = ensure_bvh(ctx))) return rc;
+        TraceParamsB B{};
+        B.sc = d.sc; B.n = n; B.origins = d_o; B.dirs = d_d; B.times = times ? d_tm : nullptr;
+        B.tmin = tmin; B.tmax = tmax; B.out_t = d_t; B.out_id = d_id;
+        B.stats = nullptr;
+        if (ctx->generic) trace_bvh_kernel<true><<<(n + 127) / 128, 128, 0, d.stream>>>(B);
+        else trace_bvh_kernel<false><<<(n + 127) / 128, 128, 0, d.stream>>>(B);
+        RT_CUDA(ctx, cudaGetLastError());
+        RT_CUDA(ctx, cudaMemcpyAsync(out_t, d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, d.stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(out_id, d_id, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
+        RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        return RT_OK;
+    }
     TraceParams P{};
     P.sc = d.sc; P.n = n; P.origins = d_o; P.dirs = d_d; P.times = times ? d_tm : nullptr;
     P.tmin = tmin; P.tmax = tmax; P.out_t = d_t; P.out_id = d_id; P.cull_cap = ctx->cull_cap; P.preloaded = ctx->preloaded;
@@ -1760,6 +1886,8 @@ int rt_get_counters(rt_ctx* ctx, uint64_t out[RT_CTR_COUNT]) {
     out[RT_CTR_KERNEL_NS] = (uint64_t)((double)max_ms * 1e6);
     out[RT_CTR_CANDIDATES] = total[DC_CANDIDATES];
     out[RT_CTR_DIRECT_TESTS] = total[DC_DIRECT];
+    out[RT_CTR_BVH_NODE_TESTS] = total[DC_BVH_NODES];
+    if (ctx->accel == RT_ACCEL_BVH) out[RT_CTR_SPHERE_TESTS] = total[DC_CANDIDATES] + total[DC_DIRECT];   // exact tests actually made
     out[RT_CTR_KERNEL_LAUNCHES] = ctx->n_launches.load();
     out[RT_CTR_CULL_NS] = (uint64_t)(ctx->stage_ms[0] * 1e6);
     out[RT_CTR_REFINE_NS] = (uint64_t)(ctx->stage_ms[1] * 1e6);

@@ -40,7 +40,7 @@ constexpr float CULL_EPS = 7.62939453125e-6f;  // 2^-17
 enum TermReason { TERM_NONE = 0, TERM_LIGHT = 1, TERM_ABSORB = 2, TERM_DEPTH = 3, TERM_MISS = 4 };
 
 // device counter slots (subset of RT_CTR_* that the kernels write)
-enum { DC_RAYS = 0, DC_SAMPLES, DC_TERM_LIGHT, DC_TERM_ABSORB, DC_TERM_DEPTH, DC_TERM_MISS, DC_CANDIDATES, DC_DIRECT, DC_COUNT = 8 };
+enum { DC_RAYS = 0, DC_SAMPLES, DC_TERM_LIGHT, DC_TERM_ABSORB, DC_TERM_DEPTH, DC_TERM_MISS, DC_CANDIDATES, DC_DIRECT, DC_BVH_NODES, DC_COUNT = 10 };
 
 // Scene in HBM, every per-sphere array in "cull order": first the n_list spheres the FP32 cull runs over,
 // then the n - n_list "direct" spheres that bypass it (enclosing spheres such as a sky dome or a ground
@@ -87,6 +87,11 @@ struct DevScene {
     const int2* image_wh;     // [images]
     const long long* image_off;
     const unsigned char* image_rgb;
+    // ---- RT_ACCEL_BVH: flattened BVH over the listed leaves [0, n_list) (the role of hitable.clj:97-123) ----
+    const float4* bvh;        // [4 per node]: left child's box lo.xyz / hi.xyz, right child's box lo / hi packed as
+                              //   (llo.x llo.y llo.z lhi.x) (lhi.y lhi.z rlo.x rlo.y) (rlo.z rhi.x rhi.y rhi.z) (left, right, -, -);
+                              //   a child index < 0 is the leaf ~index (cull order); node 0 is the root
+    int bvh_nodes;
 };
 
 struct DevCamera {

@@ -1040,6 +1040,158 @@ __global__ void __launch_bounds__(256, GEN ? 1 : 0) wf_shade(const __grid_consta
     }
 }
 
+struct TraceParamsB {
+    DevScene sc;
+    int n;
+    const float* origins;
+    const float* dirs;
+    const float* times;   // may be null
+    double tmin, tmax;
+    double* out_t;
+    int* out_id;
+    unsigned long long* stats;   // may be null: += leaf tests, box tests
+};
+
+// ------------------------------------------------------------------------------------------
+// RT_ACCEL_BVH: the reference's own accelerator (AABB.hit? hitable.clj:36-48, bvh-node.hit? :97-106, make-bvh :108-123) as
+// a flattened tree walked with a short stack.  The boxes are only a CULL, like the FP32 sphere cull of the brute-force
+// path: conservative FP32 slab tests (boxes widened at build, NaN-safe min / max, the far bound relaxed by a few ulps),
+// and every leaf that survives goes through the same exact FP64 test with the same tie rule — so the closest hit is
+// the brute-force one, bit for bit (the reference's tree answers exact ties by tree position and misses a leaf whose
+// slab test divides 0 by 0; neither can be observed outside coincident geometry).
+// ------------------------------------------------------------------------------------------
+struct BvhHit {
+    double t;
+    int k;
+    unsigned tie;
+    unsigned n_leaf, n_node;
+};
+template <bool GEN>
+__device__ __forceinline__ BvhHit bvh_closest(const DevScene* sc, float ox, float oy, float oz, float dx, float dy, float dz, float time,
+                                              double tmin, double tmax, bool has_ctx, uint2 key, uint32_t pixel, uint32_t sample,
+                                              uint32_t bounce) {
+    BvhHit H{CUDART_INF, -1, 0xffffffffu, 0u, 0u};
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+    // the rounding of (box - origin) is relative to the larger operand: the boxes carry their own share (widened at
+    // build), the ray's share widens every box here
+    const float e = 2.4e-7f * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz));
+    const float tlo = (float)tmin * (1.0f - 1e-6f);
+    float thi = tmax >= (double)FLT_MAX ? FLT_MAX : __double2float_ru(tmax);
+    int stack[48];
+    int sp = 0, node = 0;
+    for (;;) {
+        if (node >= 0) {
+            const float4 A = __ldg(&sc->bvh[4 * node]), B = __ldg(&sc->bvh[4 * node + 1]), C = __ldg(&sc->bvh[4 * node + 2]);
+            const int4 D = __ldg(reinterpret_cast<const int4*>(&sc->bvh[4 * node + 3]));
+            H.n_node += 2;
+            // slab test of both children; fminf / fmaxf drop a NaN (0 * inf) operand, which keeps the test conservative
+            float a0 = ((A.x - e) - ox) * ix, a1 = ((A.w + e) - ox) * ix, b0 = ((A.y - e) - oy) * iy, b1 = ((B.x + e) - oy) * iy,
+                  c0 = ((A.z - e) - oz) * iz, c1 = ((B.y + e) - oz) * iz;
+            float ln = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tlo));
+            float lf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), thi));
+            a0 = ((B.z - e) - ox) * ix; a1 = ((C.y + e) - ox) * ix; b0 = ((B.w - e) - oy) * iy; b1 = ((C.z + e) - oy) * iy;
+            c0 = ((C.x - e) - oz) * iz; c1 = ((C.w + e) - oz) * iz;
+            float rn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tlo));
+            float rf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), thi));
+            const bool hl = ln <= lf * 1.0000005f + 1e-30f, hr = rn <= rf * 1.0000005f + 1e-30f;
+            if (hl && hr) {                      // nearer child first, the other on the stack
+                const bool left_first = ln <= rn;
+                stack[sp++] = left_first ? D.y : D.x;
+                node = left_first ? D.x : D.y;
+                continue;
+            }
+            if (hl) { node = D.x; continue; }
+            if (hr) { node = D.y; continue; }
+        } else {
+            const int k = ~node;
+            H.n_leaf++;
+            const double t = refine_leaf<GEN>(sc, k, ox, oy, oz, dx, dy, dz, time, tmin, tmax, has_ctx, key, pixel, sample, bounce);
+            if (t < CUDART_INF) {
+                const unsigned tie = __ldg(&sc->tie_hi[k]);
+                if (t < H.t || (t == H.t && tie < H.tie)) {
+                    H.t = t; H.k = k; H.tie = tie;
+                    thi = fminf(thi, __double2float_ru(t));   // boxes entirely beyond the hit are skipped; equal t still passes (ties)
+                }
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return H;
+}
+
+// one wavefront iteration's closest-hit search through the BVH: replaces wf_cull + wf_refine + wf_tiebreak.  One thread
+// per entry: load (or, for a fresh entry, generate) the ray, walk the tree, leave (t, key) in the closest-hit words for
+// wf_shade.  The direct spheres stay with wf_shade as in the brute-force path.
+template <bool GEN>
+__global__ void __launch_bounds__(128, GEN ? 1 : 0) wf_bvh(const __grid_constant__ WaveParams W) {
+    if (W.st->mode != MODE_RUN) return;
+    TraceScope trace(W.trace);
+    const RenderParams& P = W.base;
+    __shared__ unsigned s_ctr[DC_COUNT];
+    if (threadIdx.x < DC_COUNT) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    const int cur = W.cur;
+    const unsigned n_g = W.st->cnt[cur][0], n_p = W.st->cnt[cur][1], n = n_g + n_p, p0 = (unsigned)W.capacity - n_p;
+    const unsigned long long gen_base = W.st->gen_base[cur];
+    float4* qc = cur ? W.queue[1] : W.queue[0];
+    unsigned n_leaf = 0, n_node = 0;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        float4 a, b, c;
+        unsigned idx;
+        if (v >= n_g) {
+            idx = p0 + (v - n_g);
+            make_path(P, gen_base + (v - n_g), a, b, c);
+            float4* q = qc + 3 * (size_t)idx;
+            q[0] = a; q[1] = b; q[2] = c;
+        } else {
+            idx = v;
+            a = qc[3 * (size_t)idx]; b = qc[3 * (size_t)idx + 1]; c = qc[3 * (size_t)idx + 2];
+        }
+        const uint32_t sd = __float_as_uint(c.w);
+        const BvhHit H = bvh_closest<GEN>(&W.base.sc, a.x, a.y, a.z, b.x, b.y, b.z, a.w, 0.001, (double)FLT_MAX, true, P.key,
+                                          rng_pixel(P, __float_as_uint(b.w)), sd >> 8, (uint32_t)(P.max_depth - (int)(sd & 255u) + 1));
+        n_leaf += H.n_leaf; n_node += H.n_node;
+        if (H.k >= 0) {
+            W.best_t[idx] = (unsigned long long)__double_as_longlong(H.t);
+            W.best_key[idx] = ((unsigned long long)H.tie << 32) | (unsigned)H.k;
+        }
+    }
+    atomicAdd(&s_ctr[DC_CANDIDATES], n_leaf);
+    atomicAdd(&s_ctr[DC_BVH_NODES], n_node);
+    __syncthreads();
+    if (threadIdx.x < DC_COUNT && s_ctr[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // the housekeeping wf_cull / wf_refine do in the brute-force path
+        atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
+        W.st->batch = 0;
+        W.st->npairs = 0;
+        W.st->cnt[cur ^ 1][0] = 0;
+        W.st->cnt[cur ^ 1][1] = 0;
+    }
+}
+
+// rt_trace_primary through the BVH (one thread per ray; the direct spheres are tested exactly, after the tree)
+template <bool GEN>
+__global__ void __launch_bounds__(128) trace_bvh_kernel(const __grid_constant__ TraceParamsB P) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.n) return;
+    const float ox = P.origins[3 * idx], oy = P.origins[3 * idx + 1], oz = P.origins[3 * idx + 2];
+    const float dx = P.dirs[3 * idx], dy = P.dirs[3 * idx + 1], dz = P.dirs[3 * idx + 2];
+    const float tm = P.times ? P.times[idx] : 0.f;
+    BvhHit H = bvh_closest<GEN>(&P.sc, ox, oy, oz, dx, dy, dz, tm, P.tmin, P.tmax, false, make_uint2(0u, 0u), 0u, 0u, 0u);
+    for (int k = P.sc.n_list; k < P.sc.n; ++k) {
+        const double t = refine_leaf<GEN>(&P.sc, k, ox, oy, oz, dx, dy, dz, tm, P.tmin, P.tmax, false, make_uint2(0u, 0u), 0u, 0u, 0u);
+        const unsigned tie = __ldg(&P.sc.tie_hi[k]);
+        if (t < H.t || (t < CUDART_INF && t == H.t && tie < H.tie)) { H.t = t; H.k = k; H.tie = tie; }
+    }
+    P.out_t[idx] = H.t;
+    P.out_id[idx] = H.k >= 0 ? __ldg(&P.sc.orig_id[H.k]) : -1;
+    if (P.stats) {
+        atomicAdd(&P.stats[0], (unsigned long long)H.n_leaf);
+        atomicAdd(&P.stats[1], (unsigned long long)H.n_node);
+    }
+}
+
 // Tail of a render: the work counter is exhausted and the queue is short (up to 50 more bounces of a shrinking
 // handful of paths).  ONE launch finishes the lane: the queue is cut into one slice per CTA, and every CTA runs
 // the wavefront stages on its own slice by itself — its queue counters live in shared memory, the stages are

@@ -451,3 +451,59 @@ def test_medium_hits_on_device(renderer):
     _assert_hits(t_gpu, id_gpu, t_ref, id_ref, exact=False)        # log() may differ in the last ulp: 1e-5 relative, not bit-exact
     h = id_ref >= 0
     assert (t_gpu[h] == t_ref[h]).mean() > 0.9
+
+
+# ---- f-3: the GPU BVH accelerator -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["random", "sweep6000", "cornell", "final"])
+def test_bvh_accel_equals_brute_force(renderer, name):
+    """RT_ACCEL_BVH (flattened tree, conservative FP32 slab tests, the same FP64 leaf tests and tie keys) returns the
+    brute-force closest hit bit for bit — ids and t on camera / secondary / grazing rays, and whole paths: per-path
+    radiance, bounce count and termination of rt_trace_paths are IDENTICAL under both accelerators."""
+    rng = random.Random(2)
+    nx, ny = 320, 200
+    sc = {"random": lambda: rt.scene.make_random_scene(nx, ny, 11, True, rng),
+          "sweep6000": lambda: rt.scene.make_scale_sweep_scene(nx, ny, 6000, rng),
+          "cornell": lambda: rt.scene.make_cornell_box(nx, ny, True, rng),
+          "final": lambda: rt.scene.make_final(nx, ny, rng, nb=10, ns=300)}[name]()
+    flat, cam_type, cam, S = _load(renderer, sc)
+    g = np.random.default_rng(9)
+    n = 120_000
+    camd = np.asarray(cam, np.float64)
+    o = np.tile(camd[0:3], (n, 1)).astype(np.float32)
+    d = (camd[3:6] + g.random((n, 1)) * camd[6:9] + g.random((n, 1)) * camd[9:12] - camd[0:3]).astype(np.float32)
+    tm = g.random(n).astype(np.float32)
+    try:
+        renderer.set_accel(rt.native.RT_ACCEL_BRUTE_FORCE)
+        t0, id0 = renderer.trace_primary(o, d, tm)
+        renderer.set_accel(rt.native.RT_ACCEL_BVH)
+        t1, id1 = renderer.trace_primary(o, d, tm)
+        assert np.array_equal(id0, id1) and np.array_equal(t0, t1)
+        t_ref, id_ref = S.hit(o, d, tm)
+        exact = name != "final"                               # a medium's log() may differ in the last ulp from the CPU's
+        _assert_hits(t1, id1, t_ref, id_ref, exact=exact)
+        h = id0 >= 0
+        p = (o[h].astype(np.float64) + t0[h][:, None] * d[h].astype(np.float64)).astype(np.float32)
+        nd = g.normal(size=p.shape).astype(np.float32)
+        a = renderer.trace_primary(p, nd, tm[h])
+        renderer.set_accel(rt.native.RT_ACCEL_BRUTE_FORCE)
+        b = renderer.trace_primary(p, nd, tm[h])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        # whole paths, both accelerators, the production wavefront
+        m = 150_000
+        pix = g.integers(0, nx * ny, m).astype(np.int32)
+        smp = g.integers(0, 64, m).astype(np.int32)
+        brute = renderer.trace_paths(nx, ny, pix, smp, 50, seed=3)
+        renderer.reset_counters()
+        renderer.set_accel(rt.native.RT_ACCEL_BVH)
+        tree = renderer.trace_paths(nx, ny, pix, smp, 50, seed=3)
+        c = renderer.counters()
+        assert np.array_equal(brute[1], tree[1]) and np.array_equal(brute[2], tree[2]) and np.array_equal(brute[0], tree[0])
+        assert c["bvh_node_tests"] > 0 and c["rays"] == int(tree[1].sum())
+        if name in ("random", "sweep6000"):                   # O(log N): far fewer exact tests than rays x N
+            assert c["sphere_tests"] < 0.05 * c["rays"] * flat.n_spheres
+        lin, _ = renderer.render(nx, ny, 8, 50, seed=5)
+        renderer.set_accel(rt.native.RT_ACCEL_BRUTE_FORCE)
+        lin0, _ = renderer.render(nx, ny, 8, 50, seed=5)
+        assert np.allclose(lin, lin0, rtol=1e-5, atol=1e-6)    # same paths; only the order of the float atomics differs
+    finally:
+        renderer.set_accel(rt.native.RT_ACCEL_BRUTE_FORCE)
