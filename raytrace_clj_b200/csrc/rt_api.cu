@@ -119,6 +119,7 @@ struct Options {
     int common_origin = 1;            // RT_COMMON_ORIGIN
     int reduce = 0;                   // multi-device rt_render: 0 = NVLink peer loads inside the resolve kernel, 1 = ncclReduce
     int rows = 0;                     // multi-device partition: 0 = sample slices, 1 = interleaved rows
+    int mega_regcap = 0;              // 1: the register-capped megakernel (128 registers, 2 CTAs / SM) instead of the uncapped one
     int wave_depth = 2;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
 };
 
@@ -617,7 +618,10 @@ int launch_params(rt_ctx* ctx, DeviceBuffers& d, RenderParams& P, int variant, c
     unsigned long long want = (P.total_work + (unsigned long long)kBlock * kR - 1) / ((unsigned long long)kBlock * kR);
     int bps = 0;
     if (variant == RT_VARIANT_MEGAKERNEL) {
-        void (*kern)(const RenderParams) = ctx->generic ? mega_kernel<kR, kBlock, kMinBlocks, true> : mega_kernel<kR, kBlock, kMinBlocks, false>;
+        // option "mega_regcap" = 1: the 128-register build of round 1 (2 CTAs / SM, spills) kept as an A/B for the
+        // reproducibility check (tests/test_gpu_parity.py::test_render_is_reproducible runs both)
+        void (*kern)(const RenderParams) = ctx->generic ? mega_kernel<kR, kBlock, kMinBlocks, true>
+                                           : (ctx->opt.mega_regcap ? mega_kernel<kR, kBlock, 2, false> : mega_kernel<kR, kBlock, kMinBlocks, false>);
         int rc = configure_kernel(ctx, kern, smem, &bps);
         if (rc) return rc;
         int grid = (int)std::min<unsigned long long>((unsigned long long)d.sm_count * bps, want);
@@ -1376,6 +1380,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "reduce") o.reduce = (int)value;
     else if (k == "rows") o.rows = (int)value;
     else if (k == "wave_depth") o.wave_depth = (int)value;
+    else if (k == "mega_regcap") o.mega_regcap = (int)value;
     else return fail(ctx, RT_ERR_ARG, "unknown option: " + k);
     return RT_OK;
 }

@@ -1283,6 +1283,34 @@ __global__ void __launch_bounds__(BLOCK, GEN ? 1 : 2) wf_tail(const __grid_const
 // ballot + prefix popc) so the intersect loop runs with full lanes until the work runs out.
 // Warps run asynchronously through generate / intersect / refine / shade code.
 // ------------------------------------------------------------------------------------------
+// One shared body for the shading of every path slot of the megakernel.  Inlined once per slot (RT_FOR_R) the R copies
+// were contracted / scheduled differently, so a path's last bits depended on WHICH slot the dynamic work counter gave
+// it — the run-to-run "one path in ~600 k takes a different number of bounces" of the register-capped build of round 1
+// (no race: every per-path value lives in registers, everything shared is read-only or atomic).  A single out-of-line
+// copy makes the result a function of (pixel, sample) alone.  By value in, one struct out (no caller registers forced
+// into local memory).
+struct MegaShade {
+    float4 o_t;      // scattered origin, ray time
+    float4 d_c;      // scattered direction, continue flag (1 / 0)
+    float4 att_r;    // attenuation, termination reason
+    float4 em;       // emitted
+};
+template <bool GEN>
+__device__ __noinline__ MegaShade mega_shade_one(const DevScene* scp, int k, float t, float ox, float oy, float oz, float dx, float dy,
+                                                 float dz, float time, int allow_scatter, uint2 key, uint32_t pix, uint32_t smp,
+                                                 uint32_t bounce) {
+    float3 o = f3(ox, oy, oz), d = f3(dx, dy, dz), att, em;
+    int reason = TERM_NONE;
+    ScatterRng rng{key, pix, smp, bounce, nullptr, nullptr};
+    const bool cont = shade_hit<GEN>(*scp, scp, k, t, o, d, time, allow_scatter != 0, rng, att, em, reason);
+    MegaShade m;
+    m.o_t = make_float4(o.x, o.y, o.z, time);
+    m.d_c = make_float4(d.x, d.y, d.z, cont ? 1.f : 0.f);
+    m.att_r = make_float4(att.x, att.y, att.z, (float)reason);
+    m.em = make_float4(em.x, em.y, em.z, 0.f);
+    return m;
+}
+
 template <int R, int BLOCK, int MINB, bool GEN>
 __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ float4 smem_f4[];
@@ -1381,12 +1409,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) mega_kernel(const __grid_constant
                     atomicAdd(&s_ctr[DC_TERM_MISS], 1u);
                     if (P.path_pixel) path_log_end(P, slot[r], (int)I.bounce[r], TERM_MISS);
                 } else {
-                    float3 o = f3(I.ox[r], I.oy[r], I.oz[r]), d = f3(I.dx[r], I.dy[r], I.dz[r]);
-                    float3 att, em;
-                    int reason = TERM_NONE;
-                    ScatterRng rng{P.key, pix[r], smp[r], I.bounce[r], nullptr, nullptr};
-                    bool cont = shade_hit<GEN>(P.sc, &P.sc, I.best_k[r], (float)I.best_t[r], o, d, I.tm[r], depth[r] > 0, rng, att, em,
-                                          reason);
+                    const MegaShade ms = mega_shade_one<GEN>(&P.sc, I.best_k[r], (float)I.best_t[r], I.ox[r], I.oy[r], I.oz[r], I.dx[r], I.dy[r],
+                                                             I.dz[r], I.tm[r], depth[r] > 0 ? 1 : 0, P.key, pix[r], smp[r], I.bounce[r]);
+                    const float3 o = f3(ms.o_t.x, ms.o_t.y, ms.o_t.z), d = f3(ms.d_c.x, ms.d_c.y, ms.d_c.z);
+                    const float3 att = f3(ms.att_r.x, ms.att_r.y, ms.att_r.z), em = f3(ms.em.x, ms.em.y, ms.em.z);
+                    const bool cont = ms.d_c.w != 0.f;
+                    const int reason = (int)ms.att_r.w;
+                    I.tm[r] = ms.o_t.w;
                     if (em.x != 0.f || em.y != 0.f || em.z != 0.f) {   // accum += atten * emitted (core.clj:32-34,37-39)
                         float* dst = P.sum + (size_t)slot[r] * 3;
                         atomicAdd(dst + 0, ar[r] * em.x);

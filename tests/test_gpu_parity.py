@@ -458,6 +458,32 @@ def test_render_is_reproducible(renderer, scene_c2, variant):
     assert c["samples"] == 480 * 320 * 4 == c["term_light"] + c["term_absorb"] + c["term_depth"] + c["term_miss"]
 
 
+def test_capped_megakernel_is_reproducible(scene_c2):
+    """Round 1's register-capped megakernel rendered one path in ~600 k differently from run to run.  Cause: the shading
+    code was inlined once per path slot, the copies rounded differently, and the slot a (pixel, sample) lands in depends
+    on the dynamic work counter — not a race.  With ONE out-of-line shading body (mega_shade_one) the capped build is
+    as reproducible as the others: identical counters over 12 runs, and equal to the uncapped build and the wavefront."""
+    flat, _, _, _ = scene_c2
+    sc = rt.scene.make_random_scene(480, 320, 11, True, random.Random(1))
+    cam_type, cam = rt.native.marshal_camera(sc["camera"])
+    keys = ("rays", "samples", "term_light", "term_absorb", "term_depth", "term_miss")
+    seen = {}
+    with rt.native.Renderer([0]) as r:
+        r.set_scene(flat)
+        r.set_camera(cam_type, cam)
+        for cap, variant, runs in ((1, 0, 12), (0, 0, 3), (0, 1, 3)):
+            r.set_option("mega_regcap", cap)
+            for _ in range(runs):
+                r.reset_counters()
+                r.render(480, 320, 4, 50, seed=99, variant=variant, linear=False, rgb8=False)
+                c = r.counters()
+                seen.setdefault((cap, variant), set()).add(tuple(c[k] for k in keys))
+    assert all(len(v) == 1 for v in seen.values()), seen             # every build reproduces itself run after run
+    assert seen[(1, 0)] == seen[(0, 0)]                                # capped == uncapped: the same shading body
+    mega, wave = next(iter(seen[(0, 0)])), next(iter(seen[(0, 1)]))    # the wavefront inlines its own copy: FP32 threshold flips only
+    assert abs(mega[0] - wave[0]) <= 1e-5 * wave[0] and mega[1] == wave[1]
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_resolve_bit_exact_and_sharding(renderer, scene_c2, variant):
     """rt_render_accumulate_device + rt_resolve_device on caller-owned device buffers (the per-GPU leg of the

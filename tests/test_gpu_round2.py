@@ -497,6 +497,18 @@ def test_bvh_accel_equals_brute_force(renderer, name):
         renderer.set_accel(rt.native.RT_ACCEL_BVH)
         tree = renderer.trace_paths(nx, ny, pix, smp, 50, seed=3)
         c = renderer.counters()
+        brute2 = None
+        if not (np.array_equal(brute[1], tree[1]) and np.array_equal(brute[0], tree[0])):      # diagnostics before failing
+            renderer.set_accel(rt.native.RT_ACCEL_BRUTE_FORCE)
+            brute2 = renderer.trace_paths(nx, ny, pix, smp, 50, seed=3, log_bounces=6)
+            renderer.set_accel(rt.native.RT_ACCEL_BVH)
+            tree2 = renderer.trace_paths(nx, ny, pix, smp, 50, seed=3, log_bounces=6)
+            bad = np.nonzero((brute[1] != tree[1]) | np.any(brute[0] != tree[0], axis=1))[0]
+            print(f"[bvh] {name}: {len(bad)} of {m} paths differ; brute self-consistent: {np.array_equal(brute[0], brute2[0])}; "
+                  f"tree self-consistent: {np.array_equal(tree[0], tree2[0])}")
+            for q in bad[:6]:
+                print("   path", q, "nrays", brute[1][q], tree[1][q], "brute hits", brute2[3]["hit_id"][q], brute2[3]["t"][q],
+                      "tree hits", tree2[3]["hit_id"][q], tree2[3]["t"][q], "times", brute2[3]["time"][q])
         assert np.array_equal(brute[1], tree[1]) and np.array_equal(brute[2], tree[2]) and np.array_equal(brute[0], tree[0])
         assert c["bvh_node_tests"] > 0 and c["rays"] == int(tree[1].sum())
         if name in ("random", "sweep6000"):                   # O(log N): far fewer exact tests than rays x N

@@ -154,12 +154,25 @@ def test_bench_reference_arm_contract():
 
 
 def test_no_kernel_spills_registers():
-    """ptxas -v of the in-tree build: no kernel spills.  (A register-capped megakernel that spilled 288 bytes was the one
-    build whose renders were not reproducible run to run; spills are also pure overhead in issue-bound kernels.)"""
+    """ptxas -v of the in-tree build: no kernel spills (spills are pure overhead in issue-bound kernels).  The one
+    exception is deliberate: the register-capped megakernel (launch bound 2 CTAs / SM), kept only as the A/B build
+    of the reproducibility check (option "mega_regcap")."""
+    import subprocess
+
     from raytrace_clj_b200 import build as rtbuild
 
     rtbuild.build_library()
     log = open(os.path.join(os.path.dirname(rtbuild.OUT), "csrc", "build.log")).read()
-    spills = re.findall(r"(\d+) bytes spill stores, (\d+) bytes spill loads", log)
-    assert len(spills) >= 15                      # every kernel reported
-    assert all(a == "0" and b == "0" for a, b in spills), [s for s in spills if s != ("0", "0")]
+    kernels = {}
+    cur = None
+    for line in log.splitlines():
+        m = re.search(r"Compiling entry function '([^']+)'", line)
+        if m:
+            cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        m = re.search(r"(\d+) bytes spill stores, (\d+) bytes spill loads", line)
+        if m and cur:
+            kernels[cur] = (int(m.group(1)), int(m.group(2)))
+            cur = None
+    assert len(kernels) >= 20                      # every kernel reported
+    spilling = {k: v for k, v in kernels.items() if v != (0, 0)}
+    assert all("mega_kernel<4, 256, 2, false>" in k for k in spilling), spilling
