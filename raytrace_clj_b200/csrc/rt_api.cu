@@ -1112,6 +1112,19 @@ int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* s, const rt_scene_ext* x) 
     {
         std::vector<char> direct((size_t)n, 0);
         double direct_centroid[3] = {0, 0, 0};
+        // Isotropic.scatter hands the hit's t to the scattered ray as its TIME (shader.clj:135, kept as written), so in a
+        // scene with media a ray's time can leave every shutter window — and a MovingSphere is then met at an extrapolated
+        // position no window-bound cull record covers.  There the movers bypass the cull / the tree and are tested exactly.
+        bool any_iso = false;
+        for (int m = 0; m < nm_; ++m) any_iso |= s->mat_type[m] == RT_MAT_ISOTROPIC;
+        if (any_iso)
+            for (int i = 0; i < n; ++i)
+                if (ptype(i) == RT_PRIM_SPHERE && s->sphere_flags && (s->sphere_flags[i] & RT_SPHERE_MOVING) && s->center1 && s->t0t1) {
+                    if (n_direct == 8) return fail(ctx, RT_ERR_UNSUPPORTED, "more than 8 moving spheres in a scene with Isotropic media");
+                    direct[(size_t)i] = 1;
+                    ++n_direct;
+                }
+        if (n_direct == n) { direct[0] = 0; --n_direct; }   // the cull list must not be empty
         if (n > 16 && ctx->opt.direct_spheres && !generic) {
             std::vector<double> radii((size_t)n);
             for (int i = 0; i < n; ++i) radii[(size_t)i] = std::fabs((double)s->center0_r[4 * i + 3]);

@@ -947,8 +947,8 @@ __device__ __forceinline__ unsigned wf_shade_body(const WaveParams& W, const Dev
                 // ray) are tested here, exactly, from the registers that hold the ray anyway; same merge rule
                 for (int kd = P.sc.n_list; kd < P.sc.n; ++kd) {
                     ++n_direct;
-                    const double t = refine_candidate(P.sc.ex_c0r, P.sc.ex_c1, P.sc.ex_t0t1, P.sc.flags, kd, a.x, a.y, a.z, b.x,
-                                                      b.y, b.z, a.w, 0.001, (double)FLT_MAX);   // core.clj:25 t-range
+                    const double t = refine_leaf<GEN>(scp, kd, a.x, a.y, a.z, b.x, b.y, b.z, a.w, 0.001, (double)FLT_MAX, true, P.key, pix,
+                                                      smp, bounce);   // core.clj:25 t-range
                     const unsigned long long kk = (((unsigned long long)__ldg(&P.sc.tie_hi[kd])) << 32) | (unsigned)kd;
                     if (t < td || (t < CUDART_INF && t == td && kk < key)) {
                         td = t;
