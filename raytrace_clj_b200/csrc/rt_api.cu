@@ -119,6 +119,7 @@ struct Options {
     int common_origin = 1;            // RT_COMMON_ORIGIN
     int reduce = 0;                   // multi-device rt_render: 0 = NVLink peer loads inside the resolve kernel, 1 = ncclReduce
     int rows = 0;                     // multi-device partition: 0 = sample slices, 1 = interleaved rows
+    int tail_rays = 1;                // RT_TAIL_RAYS: rays per thread of the tail kernel's cull while its slices are long (1 | 4)
     int mega_regcap = 0;              // 1: the register-capped megakernel (128 registers, 2 CTAs / SM) instead of the uncapped one
     int wave_depth = 2;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
 };
@@ -301,6 +302,7 @@ Options options_from_env() {
     o.reduce = env_int("RT_REDUCE", o.reduce);
     o.rows = env_int("RT_ROWS", o.rows);
     o.wave_depth = env_int("RT_WAVE_DEPTH", o.wave_depth);
+    o.tail_rays = env_int("RT_TAIL_RAYS", o.tail_rays);
     return o;
 }
 
@@ -345,11 +347,12 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     // tail kernel: one CTA per SM per lane (two lanes' tails run side by side)
     bool done[kMaxLanes] = {};
     const unsigned tail_entries = (unsigned)std::max<long long>(0, opt.tail_entries);
-    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + Culler<1, 256>::LIST_BYTES;
+    const bool tail4 = opt.tail_rays == 4;
+    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + (tail4 ? Culler<4, 256>::LIST_BYTES : Culler<1, 256>::LIST_BYTES);
     int tail_bps = 0;
     // GEN = false instantiations hold none of the generic-leaf / extended-texture code (registers, I-cache)
     const bool gen = ctx->generic != 0;
-    void (*k_tail)(const WaveParams) = gen ? wf_tail<256, true> : wf_tail<256, false>;
+    void (*k_tail)(const WaveParams) = gen ? wf_tail<256, true, 1> : (tail4 ? wf_tail<256, false, 4> : wf_tail<256, false, 1>);
     void (*k_refine)(const WaveParams) = gen ? wf_refine<true> : wf_refine<false>;
     void (*k_shade)(const WaveParams) = gen ? wf_shade<true> : wf_shade<false>;
     RT_CUDA(ctx, cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
@@ -1394,6 +1397,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "rows") o.rows = (int)value;
     else if (k == "wave_depth") o.wave_depth = (int)value;
     else if (k == "mega_regcap") o.mega_regcap = (int)value;
+    else if (k == "tail_rays") o.tail_rays = (int)value;
     else return fail(ctx, RT_ERR_ARG, "unknown option: " + k);
     return RT_OK;
 }

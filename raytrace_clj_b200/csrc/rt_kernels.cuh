@@ -1199,7 +1199,10 @@ __global__ void __launch_bounds__(128) trace_bvh_kernel(const __grid_constant__ 
 // iteration) or grid.sync() (the cooperative form of this kernel: ~20 us per iteration, 0.75 ms per render).
 // The slices are the CTA's ranges of the lane's own buffers, so a slice's population can only shrink in place.
 constexpr int kPairsPerEntry = 8;       // pair buffer = 8 (ray, sphere) pairs per queue entry (measured mean: 1.5)
-template <int BLOCK, bool GEN>
+// TR: rays per thread of the tail's cull while a slice is still long (the first bounces after the hand-over, when a
+// slice holds thousands of paths): TR = 4 runs them like wf_cull does (4 independent chains per thread), the short-queue
+// forms (1 ray per thread, sphere list split across warps) take over as the slice shrinks.
+template <int BLOCK, bool GEN, int TR>
 __global__ void __launch_bounds__(BLOCK, GEN ? 1 : 2) wf_tail(const __grid_constant__ WaveParams W) {
     const RenderParams& P = W.base;
     extern __shared__ float4 smem_f4[];
@@ -1251,7 +1254,7 @@ __global__ void __launch_bounds__(BLOCK, GEN ? 1 : 2) wf_tail(const __grid_const
             __syncthreads();
             const unsigned n = *(volatile unsigned*)&s_st.cnt[cur][0];
             if (n == 0) break;
-            wf_cull_body<1, BLOCK>(L, solo, cur, n, 0u, 0ull, s_cull, nullptr, s_list);
+            wf_cull_body<TR, BLOCK>(L, solo, cur, n, 0u, 0ull, s_cull, nullptr, s_list);
             __syncthreads();
             wf_refine_body<GEN>(L, &W.base.sc, solo, cur);
             __syncthreads();
