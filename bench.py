@@ -206,7 +206,9 @@ def in_library_run(rt, device_ids, flat, cam_type, cam, nx, ny, spp, depth, vari
         for w in range(warmup):
             one(500 + w, spp)
         if warmup == 0:
-            one(499, max(1, len(device_ids)))       # allocations and module load only: one sample per device
+            # allocations and module load only — but with enough samples per device (4) that the wavefront queues
+            # get their full size here, not inside the timed frame
+            one(499, min(spp, 4 * max(1, len(device_ids))))
         r.reset_counters()
         t0 = time.perf_counter()
         for k in range(steps):
