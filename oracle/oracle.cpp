@@ -372,6 +372,18 @@ struct HitCtx {            // what ConstantMedium.hit? needs beyond the ray (its
 };
 
 bool prim_hit(const Scene& sc, int id, const Ray& r, double t_min, double t_max, HitRec& h, HitCtx* hc);
+// the common leaf — a sphere without wrappers — inline (the brute-force loop of the benchmark scenes: this is the
+// CPU baseline bench.py times, so it must not pay for the generality of prim_hit); everything else out of line
+inline bool leaf_hit(const Scene& sc, int id, const Ray& r, double t_min, double t_max, HitRec& h, HitCtx* hc) {
+    const Prim& s = sc.prims[id];
+    if (s.type == PRIM_SPHERE && s.xform < 0) {
+        if (!sphere_hit(s, r, t_min, t_max, h)) return false;
+        h.mat = s.mat;
+        h.id = id;
+        return true;
+    }
+    return prim_hit(sc, id, r, t_min, t_max, h, hc);
+}
 
 // hitable.clj:15-26  Hitlist.hit? over primitives [first, first + count): reduce with shrinking t-max.  A sphere
 // replaces the running hit only when strictly closer (t < t-max); a rect / triangle also at t == t-max.
@@ -380,7 +392,7 @@ inline bool list_hit(const Scene& sc, int first, int count, const Ray& r, double
     double closest = t_max;
     HitRec h;
     for (int i = first; i < first + count; ++i) {
-        if (prim_hit(sc, i, r, t_min, closest, h, hc)) {
+        if (leaf_hit(sc, i, r, t_min, closest, h, hc)) {
             any = true;
             closest = h.t;
             out = h;
@@ -589,9 +601,9 @@ bool bvh_hit(const Scene& sc, int node, const Ray& r, double t_min, double t_max
     if (!aabb_hit(n.box, r, t_min, t_max)) return false;
     HitRec hl, hr;
     bool bl, br;
-    if (n.left < 0) { if (st) st->leaf_tests++; bl = prim_hit(sc, ~n.left, r, t_min, t_max, hl, hc); }
+    if (n.left < 0) { if (st) st->leaf_tests++; bl = leaf_hit(sc, ~n.left, r, t_min, t_max, hl, hc); }
     else bl = bvh_hit(sc, n.left, r, t_min, t_max, hl, hc, st);
-    if (n.right < 0) { if (st) st->leaf_tests++; br = prim_hit(sc, ~n.right, r, t_min, t_max, hr, hc); }
+    if (n.right < 0) { if (st) st->leaf_tests++; br = leaf_hit(sc, ~n.right, r, t_min, t_max, hr, hc); }
     else br = bvh_hit(sc, n.right, r, t_min, t_max, hr, hc, st);
     if (bl && br) { out = (hl.t < hr.t) ? hl : hr; return true; }
     if (bl) { out = hl; return true; }
@@ -606,13 +618,21 @@ inline bool world_hit(const Scene& sc, const Ray& r, double t_min, double t_max,
                       bool use_bvh = false, BvhStats* st = nullptr) {
     if (use_bvh && sc.bvh_root >= 0) return bvh_hit(sc, sc.bvh_root, r, t_min, t_max, out, hc, st);
     if (sc.tie_rule == TIE_BVH) {
+        // every leaf of a bvh-node tree sees the root's t-max and an equal t on the right replaces the left one.  Same
+        // answer with a shrinking bound (only closer-or-EQUAL leaves build a hit record): a strict-range leaf (sphere,
+        // t < t-max) is offered the next double above the running t, an inclusive one (t <= t-max) the running t itself.
         bool any = false;
+        double closest = t_max;
         HitRec h;
-        for (int i = 0; i < sc.n_world; ++i)
-            if (prim_hit(sc, i, r, t_min, t_max, h, hc) && (!any || !(out.t < h.t))) {
+        for (int i = 0; i < sc.n_world; ++i) {
+            const bool strict = sc.prims[i].type == PRIM_SPHERE;
+            const double lim = (any && strict) ? std::nextafter(closest, INFINITY) : closest;
+            if (leaf_hit(sc, i, r, t_min, lim, h, hc)) {
                 any = true;
+                closest = h.t;
                 out = h;
             }
+        }
         return any;
     }
     return list_hit(sc, 0, sc.n_world, r, t_min, t_max, out, hc);

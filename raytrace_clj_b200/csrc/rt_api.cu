@@ -87,6 +87,7 @@ struct DeviceBuffers {
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
     cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;   // around the cross-device reduce (RT_CTR_REDUCE_NS)
+    cudaEvent_t ev_chunk[4] = {};                   // D2H of the results in chunks: the host memcpy of chunk k overlaps the copy of chunk k + 1
 };
 
 // NCCL, loaded on demand (single process, one communicator per device: ncclCommInitAll)
@@ -946,6 +947,7 @@ void rt_destroy(rt_ctx* ctx) {
         if (d.ev_done) cudaEventDestroy(d.ev_done);
         if (d.ev_r0) cudaEventDestroy(d.ev_r0);
         if (d.ev_r1) cudaEventDestroy(d.ev_r1);
+        for (auto& e : d.ev_chunk) if (e) cudaEventDestroy(e);
         if (d.h_stage) cudaFreeHost(d.h_stage);
         if (d.bvh_nodes) cudaFree(d.bvh_nodes);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -1558,12 +1560,28 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
     const size_t b_lin = out_linear_rgb ? align_up(px * 3 * sizeof(float), 256) : 0, b_rgb = out_rgb8 ? px * 3 : 0;
     if (b_lin + b_rgb) {
         if ((rc = ensure_stage(ctx, root, b_lin + b_rgb))) return rc;
-        if (out_linear_rgb) RT_CUDA(ctx, cudaMemcpyAsync(root.h_stage, root.d_mean, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
-        if (out_rgb8) RT_CUDA(ctx, cudaMemcpyAsync((char*)root.h_stage + b_lin, root.d_rgb8, px * 3, cudaMemcpyDeviceToHost, root.stream));
+        constexpr int NCH = 4;
+        for (auto& e : root.ev_chunk)
+            if (!e) RT_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        struct Part { char* dst; const char* src; char* stage; size_t bytes; };
+        const Part parts[2] = {{(char*)out_linear_rgb, (const char*)root.d_mean, (char*)root.h_stage, out_linear_rgb ? px * 3 * sizeof(float) : 0},
+                               {(char*)out_rgb8, (const char*)root.d_rgb8, (char*)root.h_stage + b_lin, b_rgb}};
+        for (const Part& pt : parts) {
+            if (!pt.bytes) continue;
+            const size_t step = align_up((pt.bytes + NCH - 1) / NCH, 4096);
+            for (int c = 0; c < NCH; ++c) {
+                const size_t off = std::min(pt.bytes, (size_t)c * step), len = std::min(pt.bytes - off, step);
+                if (len) RT_CUDA(ctx, cudaMemcpyAsync(pt.stage + off, pt.src + off, len, cudaMemcpyDeviceToHost, root.stream));
+                RT_CUDA(ctx, cudaEventRecord(root.ev_chunk[c], root.stream));
+            }
+            for (int c = 0; c < NCH; ++c) {
+                const size_t off = std::min(pt.bytes, (size_t)c * step), len = std::min(pt.bytes - off, step);
+                RT_CUDA(ctx, cudaEventSynchronize(root.ev_chunk[c]));
+                if (len) memcpy(pt.dst + off, pt.stage + off, len);
+            }
+        }
     }
     RT_CUDA(ctx, cudaStreamSynchronize(root.stream));
-    if (out_linear_rgb) memcpy(out_linear_rgb, root.h_stage, px * 3 * sizeof(float));
-    if (out_rgb8) memcpy(out_rgb8, (char*)root.h_stage + b_lin, px * 3);
     for (int g = 1; g < G; ++g) {
         RT_CUDA(ctx, cudaSetDevice(ctx->devs[g].dev));
         RT_CUDA(ctx, cudaStreamSynchronize(ctx->devs[g].stream));

@@ -164,9 +164,10 @@ def test_bvh_mode_equals_brute_force(builder):
     t1, id1 = S.hit(p[ok], nd[ok], tm[ok])
     t2, id2 = S.hit(p[ok], nd[ok], tm[ok], use_bvh=True)
     assert np.array_equal(id1, id2) and np.array_equal(t1, t2)
-    # and whole renders agree sample for sample (same RNG stream, same hits)
-    a, ca = S.render_accumulate(cam_type, cam, 40, 30, 0, 4, 50, seed=3)
-    b, cb = S.render_accumulate(cam_type, cam, 40, 30, 0, 4, 50, seed=3, use_bvh=True)
+    # and whole renders agree sample for sample.  Counter-keyed draws (replay mode): with the sequential stream a
+    # ConstantMedium's `rand` inside hit? (hitable.clj:529) is consumed in TRAVERSAL order, which differs by construction
+    a, ca = S.render_accumulate(cam_type, cam, 40, 30, 0, 4, 50, seed=3, replay=True)
+    b, cb = S.render_accumulate(cam_type, cam, 40, 30, 0, 4, 50, seed=3, replay=True, use_bvh=True)
     assert np.array_equal(a, b) and ca["rays"] == cb["rays"] and cb["aabb_tests"] > 0
 
 
