@@ -120,6 +120,7 @@ struct Options {
     int common_origin = 1;            // RT_COMMON_ORIGIN
     int reduce = 0;                   // multi-device rt_render: 0 = NVLink peer loads inside the resolve kernel, 1 = ncclReduce
     int rows = 0;                     // multi-device partition: 0 = sample slices, 1 = interleaved rows
+    int tail_block = 256;             // RT_TAIL_BLOCK: CTA size of the tail kernel (32 | 64 | 128 | 256)
     int tail_rays = 1;                // RT_TAIL_RAYS: rays per thread of the tail kernel's cull while its slices are long (1 | 4)
     int mega_regcap = 0;              // 1: the register-capped megakernel (128 registers, 2 CTAs / SM) instead of the uncapped one
     int wave_depth = 2;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
@@ -304,6 +305,7 @@ Options options_from_env() {
     o.rows = env_int("RT_ROWS", o.rows);
     o.wave_depth = env_int("RT_WAVE_DEPTH", o.wave_depth);
     o.tail_rays = env_int("RT_TAIL_RAYS", o.tail_rays);
+    o.tail_block = env_int("RT_TAIL_BLOCK", o.tail_block);
     return o;
 }
 
@@ -348,17 +350,26 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     // tail kernel: one CTA per SM per lane (two lanes' tails run side by side)
     bool done[kMaxLanes] = {};
     const unsigned tail_entries = (unsigned)std::max<long long>(0, opt.tail_entries);
+    const bool gen = ctx->generic != 0;   // GEN = false instantiations hold none of the generic-leaf / extended-texture code
     const bool tail4 = opt.tail_rays == 4;
-    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) + (tail4 ? Culler<4, 256>::LIST_BYTES : Culler<1, 256>::LIST_BYTES);
+    // CTA size of the tail kernel: every CTA finishes its own slice, __syncthreads() between the stages.  Smaller CTAs =
+    // more, shorter slices and cheaper barriers (32: one warp per CTA, the barrier is warp-local and the stages of
+    // different warps overlap on the SM)
+    const int tail_block = (gen || tail4) ? 256 : (opt.tail_block == 32 || opt.tail_block == 64 || opt.tail_block == 128 ? opt.tail_block : 256);
+    const size_t tail_smem = (size_t)ctx->cull_cap * sizeof(float4) +
+                             (tail4 ? Culler<4, 256>::LIST_BYTES : (size_t)Culler<1, 256>::LIST_WORDS * tail_block * sizeof(uint32_t));
     int tail_bps = 0;
-    // GEN = false instantiations hold none of the generic-leaf / extended-texture code (registers, I-cache)
-    const bool gen = ctx->generic != 0;
     void (*k_tail)(const WaveParams) = gen ? wf_tail<256, true, 1> : (tail4 ? wf_tail<256, false, 4> : wf_tail<256, false, 1>);
+    if (tail_block == 128) k_tail = wf_tail<128, false, 1>;
+    if (tail_block == 64) k_tail = wf_tail<64, false, 1>;
+    if (tail_block == 32) k_tail = wf_tail<32, false, 1>;
     void (*k_refine)(const WaveParams) = gen ? wf_refine<true> : wf_refine<false>;
     void (*k_shade)(const WaveParams) = gen ? wf_shade<true> : wf_shade<false>;
     RT_CUDA(ctx, cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_bps, k_tail, 256, tail_smem));
-    const int tail_grid = d.sm_count * (opt.tail_ctas_per_sm > 0 ? opt.tail_ctas_per_sm : (n_lanes > 1 ? 1 : std::max(1, std::min(tail_bps, 2))));
+    RT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_bps, k_tail, tail_block, tail_smem));
+    // automatic: the same number of tail THREADS per SM whatever the CTA size (256 per lane with two lanes, 512 with one)
+    const int tail_auto = (n_lanes > 1 ? 1 : std::max(1, std::min((int)(tail_bps * tail_block / 256), 2))) * (256 / tail_block);
+    const int tail_grid = d.sm_count * (opt.tail_ctas_per_sm > 0 ? opt.tail_ctas_per_sm : tail_auto);
     const bool bvh = ctx->accel == RT_ACCEL_BVH;   // closest hit through the tree: one wf_bvh launch instead of cull + refine + tie-break
     void (*k_bvh)(const WaveParams) = gen ? wf_bvh<true> : wf_bvh<false>;
     const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile && !bvh;
@@ -539,7 +550,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 // (they shrink the population further; the tail takes whatever is left), finishes this lane
                 W[l].iter = (unsigned)(enq[l] + 1);
                 W[l].trace = trace_slot("tail", l, iter_no[l]);
-                k_tail<<<tail_grid, 256, tail_smem, st[l]>>>(W[l]);
+                k_tail<<<tail_grid, tail_block, tail_smem, st[l]>>>(W[l]);
                 RT_CUDA(ctx, cudaGetLastError());
                 ctx->n_launches += 1;
                 tailed[l] = true;
@@ -1400,6 +1411,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "wave_depth") o.wave_depth = (int)value;
     else if (k == "mega_regcap") o.mega_regcap = (int)value;
     else if (k == "tail_rays") o.tail_rays = (int)value;
+    else if (k == "tail_block") o.tail_block = (int)value;
     else return fail(ctx, RT_ERR_ARG, "unknown option: " + k);
     return RT_OK;
 }
