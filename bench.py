@@ -190,13 +190,15 @@ def run_reference(args, world, rank):
     return 0
 
 
-def in_library_run(rt, device_ids, flat, cam_type, cam, nx, ny, spp, depth, variant, steps, warmup, reduce_mode, rows, seed0=600):
+def in_library_run(rt, device_ids, flat, cam_type, cam, nx, ny, spp, depth, variant, steps, warmup, reduce_mode, rows, seed0=600, accel=0):
     """ONE process driving len(device_ids) GPUs through the C ABI with host buffers — what the JVM caller would do
     (core.clj:99-108): rt_set_scene + rt_set_camera + rt_render per step, wall clock.  Returns a record."""
     out_img = np.empty((ny, nx, 3), np.uint8)
     with rt.native.Renderer(device_ids) as r:
         r.set_option("reduce", reduce_mode)
         r.set_option("rows", rows)
+        if accel:
+            r.set_accel(accel)        # per context; every rt_set_scene below rebuilds the tree (inside the timed region)
 
         def one(seed, n_spp):
             r.set_scene(flat)
@@ -272,8 +274,9 @@ def main():
     r = rt.native.Renderer([local_rank])
     r.set_scene(flat)
     r.set_camera(cam_type, cam)
-    if args.accel == "bvh":
-        r.set_accel(rt.native.RT_ACCEL_BVH)
+    accel_id = rt.native.RT_ACCEL_BVH if args.accel == "bvh" else 0
+    if accel_id:
+        r.set_accel(accel_id)
     info = r.device_info()
 
     d_sum = torch.zeros(ny, nx, 3, device=dev, dtype=torch.float32)
@@ -343,7 +346,7 @@ def main():
     e2e_rec = None
     strong = None
     if world == 1:
-        e2e_rec = in_library_run(rt, [local_rank], flat, cam_type, cam, nx, ny, spp, depth, args.variant, e2e_steps, 1, 0, 0)
+        e2e_rec = in_library_run(rt, [local_rank], flat, cam_type, cam, nx, ny, spp, depth, args.variant, e2e_steps, 1, 0, 0, accel=accel_id)
     else:
         # the drop-in's caller is ONE process: rank 0 drives all N devices through rt_create(ids, N) + rt_render with
         # host buffers while the other ranks sit on a HOST barrier (their GPUs stay free); both reduce flavours
@@ -354,8 +357,8 @@ def main():
         dist.barrier(group=cpu_group)
         if rank == 0:
             ids = list(range(world))
-            e2e_rec = in_library_run(rt, ids, flat, cam_type, cam, nx, ny, spp * world, depth, args.variant, e2e_steps, 2, 0, 0)
-            e2e_rec["nccl"] = in_library_run(rt, ids, flat, cam_type, cam, nx, ny, spp * world, depth, args.variant, e2e_steps, 2, 1, 0)
+            e2e_rec = in_library_run(rt, ids, flat, cam_type, cam, nx, ny, spp * world, depth, args.variant, e2e_steps, 2, 0, 0, accel=accel_id)
+            e2e_rec["nccl"] = in_library_run(rt, ids, flat, cam_type, cam, nx, ny, spp * world, depth, args.variant, e2e_steps, 2, 1, 0, accel=accel_id)
         dist.barrier(group=cpu_group)
 
     # ---- BASELINE config 3, strong scaling: 3840x2160, 1024 spp split over the N devices of ONE context -----------
