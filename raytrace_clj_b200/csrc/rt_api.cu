@@ -124,6 +124,8 @@ struct Options {
     int tail_rays = 1;                // RT_TAIL_RAYS: rays per thread of the tail kernel's cull while its slices are long (1 | 4)
     int mega_regcap = 0;              // 1: the register-capped megakernel (128 registers, 2 CTAs / SM) instead of the uncapped one
     int wave_depth = 2;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
+    int cull_tc = 0;                  // RT_CULL_TC: 1 = the cull runs on the tensor cores (wf_cull_tc) when the list fits (<= 1024 leaves)
+    int tc_tiles_per_cta = 0;         // RT_TC_TILES_PER_CTA: ray tiles a wf_cull_tc CTA takes before it retires (0 = one CTA per SM, persistent)
 };
 
 struct rt_ctx {
@@ -136,6 +138,9 @@ struct rt_ctx {
     int n_total = 0;              // + boundary primitives of media
     int n_list = 0, n_cull = 0;   // spheres in the cull list / cull records (padded)
     int cull_cap = 0, preloaded = 0;
+    int tc_tiles = 0;             // sphere tiles of the tensor-core cull (0: the list is too long for it: FP32 cull only)
+    std::vector<std::vector<float>> tc_scratch_rows;   // build_cull_records: the leaves' feature rows before they are placed
+    std::vector<int> tc_row_k;    // feature row -> cull index (-1 = padding): a fixed shuffle, so every 64-row block sees the same mix
     int generic = 0;              // some leaf is not a plain sphere (rt_set_scene_ex)
     int accel = RT_ACCEL_BRUTE_FORCE;
     bool bvh_dirty = true;        // the tree must be (re)built before the next BVH render
@@ -306,6 +311,8 @@ Options options_from_env() {
     o.wave_depth = env_int("RT_WAVE_DEPTH", o.wave_depth);
     o.tail_rays = env_int("RT_TAIL_RAYS", o.tail_rays);
     o.tail_block = env_int("RT_TAIL_BLOCK", o.tail_block);
+    o.cull_tc = env_int("RT_CULL_TC", o.cull_tc);
+    o.tc_tiles_per_cta = env_int("RT_TC_TILES_PER_CTA", o.tc_tiles_per_cta);
     return o;
 }
 
@@ -373,6 +380,12 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     const bool bvh = ctx->accel == RT_ACCEL_BVH;   // closest hit through the tree: one wf_bvh launch instead of cull + refine + tie-break
     void (*k_bvh)(const WaveParams) = gen ? wf_bvh<true> : wf_bvh<false>;
     const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile && !bvh;
+    // tensor-core cull (rt_cull_tc.cuh): one 544-thread CTA per SM, the whole sphere-feature list resident in shared memory
+    const bool use_tc = opt.cull_tc != 0 && ctx->tc_tiles > 0 && !bvh;
+    const int tc_slots = tc::slots_for(ctx->tc_tiles, 227 * 1024);
+    const size_t tc_smem = tc::smem_bytes(ctx->tc_tiles, tc_slots);
+    if (use_tc) RT_CUDA(ctx, cudaFuncSetAttribute(wf_cull_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    const int tc_per_cta = std::max(0, opt.tc_tiles_per_cta);
 
     const int light_block = std::max(64, std::min(256, opt.light_block / 32 * 32));   // <= a cull CTA in every resource
     const int light_grid = d.sm_count * 8 * 256 / light_block;
@@ -494,11 +507,20 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     if (ctx->profile) cudaEventRecord(e[4], st[l]);
                     ctx->n_launches -= 2;   // two launches this iteration, not four
                 } else if (claims) {
+                    W[l].trace = trace_slot("cull", l, iter_no[l]);
+                    if (use_tc) {
+                        const unsigned tiles = (n_bound[l] + tc::TILE_M - 1) / tc::TILE_M;
+                        WaveParams Wt = W[l];
+                        Wt.claims_per_warp = tc_per_cta;
+                        Wt.tc_slots = tc_slots;
+                        const unsigned ctas = tc_per_cta ? (tiles + (unsigned)tc_per_cta - 1u) / (unsigned)tc_per_cta : (unsigned)d.sm_count;
+                        wf_cull_tc<<<std::max(1u, ctas), tc::THREADS, tc_smem, st[l]>>>(Wt);
+                    } else {
                     // every work item of the launch must find a warp: items <= n / (32 R) + 2 resident_warps + 8 (wf_cull_body)
                     const unsigned items = n_bound[l] / (32u * kR) + 2u * (unsigned)resident_warps + 8u;
                     const unsigned ctas = (items + (unsigned)(cull_warps * claims) - 1u) / (unsigned)(cull_warps * claims);
-                    W[l].trace = trace_slot("cull", l, iter_no[l]);
                     cull<<<ctas, cull_block, smem, st[l]>>>(W[l]);
+                    }
                     RT_CUDA(ctx, cudaEventRecord(L.ev_culled, st[l]));
                     RT_CUDA(ctx, cudaStreamWaitEvent(L.stage_stream, L.ev_culled, 0));
                     W[l].trace = trace_slot("refine", l, iter_no[l]);
@@ -511,7 +533,14 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     RT_CUDA(ctx, cudaStreamWaitEvent(st[l], L.ev_shaded, 0));
                 } else {
                     W[l].trace = trace_slot("cull", l, iter_no[l]);
-                    cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
+                    if (use_tc) {
+                        WaveParams Wt = W[l];
+                        Wt.claims_per_warp = 0;
+                        Wt.tc_slots = tc_slots;
+                        wf_cull_tc<<<d.sm_count, tc::THREADS, tc_smem, st[l]>>>(Wt);
+                    } else {
+                        cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
+                    }
                     if (ctx->profile) cudaEventRecord(e[1], st[l]);
                     W[l].trace = trace_slot("refine", l, iter_no[l]);
                     k_refine<<<light_grid, light_block, 0, st[l]>>>(W[l]);
@@ -657,7 +686,10 @@ int launch_params(rt_ctx* ctx, DeviceBuffers& d, RenderParams& P, int variant, c
 // (48 u c.c + 8 u r^2, u = 2^-24; the bound is 32.6 u c.c + 4.1 u r^2), so the cull only ever over-reports.
 // Records [n_list, n_cull) are padding: W = -inf, the key is -inf for every ray.  The direct spheres' records
 // follow the padding (used as a pre-test where those spheres are resolved).
-void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* cull_all) {
+// tc_out (or null): the tensor-core cull's TF32 feature rows of the listed leaves (rt_cull_tc.cuh: sphere_slots), tc_tiles
+// tiles of 256 rows in the canonical UMMA layout — same bounding spheres, with that kernel's own rounding budget in W
+// (96 u c.c + 24 u R2 on top of the geometric inflation).
+void build_cull_records(rt_ctx* ctx, double win_lo, double win_hi, float* cull_all, float* tc_out) {
     const double eps = std::ldexp(1.0, -20), u = std::ldexp(1.0, -24);
     for (int i = 0; i < ctx->n_spheres; ++i) {
         // listed spheres at [0, n_list); the direct spheres' records follow the padding, at n_cull + (i - n_list)
@@ -692,10 +724,27 @@ void build_cull_records(const rt_ctx* ctx, double win_lo, double win_hi, float* 
         double re = rb + e;
         double r2i = re * re * (1.0 + eps) + 48.0 * u * cc + 8.0 * u * re * re;
         cull_a[4 * i + 3] = round_up_f32(r2i - cc);
+        if (tc_out && i < ctx->n_list) {
+            const double c[3] = {-(double)cull_a[4 * i], -(double)cull_a[4 * i + 1], -(double)cull_a[4 * i + 2]};   // the centre AS STORED
+            const double Wtc = re * re * (1.0 + eps) + 96.0 * u * cc + 24.0 * u * re * re - cc;
+            float row[tc::KTOT];
+            tc::sphere_slots(c, Wtc, row);
+            ctx->tc_scratch_rows[(size_t)i].assign(row, row + tc::KTOT);
+        }
     }
     for (int k = ctx->n_list; k < ctx->n_cull; ++k) {
         cull_all[4 * k] = cull_all[4 * k + 1] = cull_all[4 * k + 2] = 0.f;
         cull_all[4 * k + 3] = -INFINITY;
+    }
+    if (tc_out) {
+        float pad[tc::KTOT];
+        tc::padding_slots(pad);
+        for (int p = 0; p < ctx->tc_tiles * tc::TILE_N; ++p) {
+            const int k = ctx->tc_row_k[(size_t)p];
+            const float* row = k >= 0 ? ctx->tc_scratch_rows[(size_t)k].data() : pad;
+            float* tile = tc_out + (size_t)(p / tc::TILE_N) * (tc::B_TILE_BYTES / 4);
+            for (int q = 0; q < tc::KTOT; ++q) tile[tc::canon_off(tc::TILE_N, p % tc::TILE_N, q) / 4] = row[q];
+        }
     }
 }
 
@@ -710,12 +759,14 @@ int ensure_window(rt_ctx* ctx, double lo, double hi) {
     if (!any_moving) return RT_OK;
     ctx->bvh_dirty = true;   // the movers' boxes cover the window too
     std::vector<float> cull((size_t)(ctx->n_cull + ctx->n_spheres - ctx->n_list) * 4);
-    build_cull_records(ctx, ctx->win_lo, ctx->win_hi, cull.data());
+    std::vector<float> tcr((size_t)ctx->tc_tiles * (tc::B_TILE_BYTES / 4));
+    build_cull_records(ctx, ctx->win_lo, ctx->win_hi, cull.data(), tcr.empty() ? nullptr : tcr.data());
     if (cull.empty()) return RT_OK;
     for (auto& d : ctx->devs) {
         RT_CUDA(ctx, cudaSetDevice(d.dev));
         RT_CUDA(ctx, cudaDeviceSynchronize());   // a render enqueued with sync = 0 on a caller's stream may still read the records
         RT_CUDA(ctx, cudaMemcpy((void*)d.sc.cull_a, cull.data(), cull.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (!tcr.empty()) RT_CUDA(ctx, cudaMemcpy((void*)d.sc.cull_tc, tcr.data(), tcr.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     cudaSetDevice(ctx->devs[0].dev);
     return RT_OK;
@@ -1248,6 +1299,21 @@ int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* s, const rt_scene_ext* x) 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + std::max<size_t>(bytes, 16), 256); return o; };
     size_t o_cull_a = take((size_t)(n_cull + n_direct) * 16);
+    const int tc_tiles = (n_list + tc::TILE_N - 1) / tc::TILE_N <= tc::MAX_TILES ? (n_list + tc::TILE_N - 1) / tc::TILE_N : 0;
+    ctx->tc_tiles = tc_tiles;
+    size_t o_cull_tc = take((size_t)tc_tiles * tc::B_TILE_BYTES), o_tc_row = take((size_t)tc_tiles * tc::TILE_N * 4);
+    {   // rows: the listed leaves dealt out over the 32-row words largest first (a leaf's share of the candidates grows with its
+        // radius), so that every epilogue warp's columns see the same mix; the padding rows are spread the same way
+        ctx->tc_row_k.assign((size_t)tc_tiles * tc::TILE_N, -1);
+        ctx->tc_scratch_rows.assign((size_t)(tc_tiles ? n_list : 0), std::vector<float>());
+        if (tc_tiles) {
+            std::vector<int> order((size_t)n_list);
+            for (int k = 0; k < n_list; ++k) order[(size_t)k] = k;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->h_bs_r[(size_t)a] > ctx->h_bs_r[(size_t)b]; });
+            const int words = tc_tiles * tc::TILE_N / 32;
+            for (int i = 0; i < n_list; ++i) ctx->tc_row_k[(size_t)(i % words) * 32 + (size_t)(i / words)] = order[(size_t)i];
+        }
+    }
     size_t o_c0r = take((size_t)n_total * 16), o_c1 = take((size_t)n_total * 16), o_t0t1 = take((size_t)n_total * 8);
     size_t o_orig = take((size_t)n * 4), o_cull_of = take((size_t)n * 4), o_flags = take((size_t)n_total * 4), o_mat = take((size_t)n_total * 4);
     size_t o_mtype = take((size_t)nm_ * 4), o_mparam = take((size_t)nm_ * 4), o_mtex = take((size_t)nm_ * 4);
@@ -1262,7 +1328,8 @@ int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* s, const rt_scene_ext* x) 
     for (int i = 0; i < n_img; ++i) img_bytes = std::max(img_bytes, (size_t)x->image_offset[i] + (size_t)x->image_wh[2 * i] * x->image_wh[2 * i + 1] * 3);
     size_t o_iwh = take((size_t)n_img * 8), o_ioff = take((size_t)n_img * 8), o_irgb = take(img_bytes);
     std::vector<unsigned char> blob(off, 0);
-    build_cull_records(ctx, win_lo, win_hi, (float*)(blob.data() + o_cull_a));
+    build_cull_records(ctx, win_lo, win_hi, (float*)(blob.data() + o_cull_a), tc_tiles ? (float*)(blob.data() + o_cull_tc) : nullptr);
+    if (tc_tiles) memcpy(blob.data() + o_tc_row, ctx->tc_row_k.data(), ctx->tc_row_k.size() * 4);
     memcpy(blob.data() + o_c0r, ctx->h_c0r.data(), (size_t)n_total * 16);
     memcpy(blob.data() + o_c1, ctx->h_c1.data(), (size_t)n_total * 16);
     memcpy(blob.data() + o_t0t1, ctx->h_t0t1.data(), (size_t)n_total * 8);
@@ -1351,6 +1418,9 @@ int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* s, const rt_scene_ext* x) 
         sc.n_list = n_list;
         sc.n_cull = n_cull;
         sc.cull_a = (const float4*)(b + o_cull_a);
+        sc.cull_tc = (const float*)(b + o_cull_tc);
+        sc.tc_row_k = (const int*)(b + o_tc_row);
+        sc.tc_tiles = tc_tiles;
         sc.ex_c0r = (const float4*)(b + o_c0r); sc.ex_c1 = (const float4*)(b + o_c1); sc.ex_t0t1 = (const float2*)(b + o_t0t1);
         sc.orig_id = (const int*)(b + o_orig); sc.cull_of_orig = (const int*)(b + o_cull_of);
         sc.flags = (const unsigned*)(b + o_flags); sc.mat_id = (const int*)(b + o_mat);
@@ -1412,6 +1482,8 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "mega_regcap") o.mega_regcap = (int)value;
     else if (k == "tail_rays") o.tail_rays = (int)value;
     else if (k == "tail_block") o.tail_block = (int)value;
+    else if (k == "cull_tc") o.cull_tc = (int)value;
+    else if (k == "tc_tiles_per_cta") o.tc_tiles_per_cta = (int)value;
     else return fail(ctx, RT_ERR_ARG, "unknown option: " + k);
     return RT_OK;
 }
@@ -1772,7 +1844,47 @@ int rt_cull_check(rt_ctx* ctx, int n, const float* origins, const float* dirs, c
     RT_CUDA(ctx, cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
     if (times) RT_CUDA(ctx, cudaMemcpyAsync(d_tm, times, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
     RT_CUDA(ctx, cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), d.stream));
-    cull_check_kernel<<<(n + 127) / 128, 128, 0, d.stream>>>(d.sc, n, d_o, d_d, times ? d_tm : nullptr, tmin, tmax, d_out);
+    if (ctx->opt.cull_tc && ctx->tc_tiles > 0) {
+        // option cull_tc: check the tensor-core cull by running the PRODUCTION kernel over a queue of these rays
+        const size_t cap = align_up((size_t)n, 128);
+        if ((rc = ensure_lane(ctx, d, 0, cap))) return rc;
+        DeviceBuffers::WaveLane& L = d.lanes[0];
+        L.best_clean = false;
+        const int words = (ctx->n_cull + 31) / 32;
+        unsigned* d_mask = nullptr;
+        RT_CUDA(ctx, cudaMalloc(&d_mask, (size_t)n * words * sizeof(unsigned)));
+        RT_CUDA(ctx, cudaMemsetAsync(d_mask, 0, (size_t)n * words * sizeof(unsigned), d.stream));
+        WaveParams W{};
+        W.base.sc = d.sc;
+        W.base.cam = ctx->cam;
+        W.base.counters = d.d_counters;
+        W.base.work_counter = d.d_counters + DC_COUNT;
+        W.base.max_depth = 1;
+        W.queue[0] = L.queue;
+        W.queue[1] = L.queue + 3 * L.entries;
+        W.best_t = L.best;
+        W.best_key = L.best + L.entries;
+        W.pairs = L.pairs;
+        W.cands = L.cands;
+        W.cand_t = L.cand_t;
+        W.cand_count = L.cand_count;
+        W.st = L.state;
+        W.capacity = (int)L.entries;
+        W.pair_cap = (unsigned)std::min<size_t>(L.entries * kPairsPerEntry, 0xfffffff0u);
+        wf_fill_best<<<d.sm_count * 4, 256, 0, d.stream>>>(L.best, L.best + L.entries, L.entries);
+        tc_check_fill<<<(n + 127) / 128, 128, 0, d.stream>>>(W, n, d_o, d_d, times ? d_tm : nullptr);
+        W.tc_slots = tc::slots_for(ctx->tc_tiles, 227 * 1024);
+        const size_t tc_smem = tc::smem_bytes(ctx->tc_tiles, W.tc_slots);
+        RT_CUDA(ctx, cudaFuncSetAttribute(wf_cull_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+        wf_cull_tc<<<d.sm_count, tc::THREADS, tc_smem, d.stream>>>(W);
+        tc_check_mark<<<d.sm_count * 4, 256, 0, d.stream>>>(W, d_mask, words);
+        tc_check_compare<<<(n + 127) / 128, 128, 0, d.stream>>>(W, n, tmin, tmax, d_mask, words, d_out);
+        cudaError_t e = cudaStreamSynchronize(d.stream);
+        cudaFree(d_mask);
+        if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("tensor-core cull check: ") + cudaGetErrorString(e));
+    } else {
+        cull_check_kernel<<<(n + 127) / 128, 128, 0, d.stream>>>(d.sc, n, d_o, d_d, times ? d_tm : nullptr, tmin, tmax, d_out);
+    }
     RT_CUDA(ctx, cudaGetLastError());
     unsigned long long h[3];
     RT_CUDA(ctx, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, d.stream));

@@ -92,6 +92,11 @@ struct DevScene {
                               //   (llo.x llo.y llo.z lhi.x) (lhi.y lhi.z rlo.x rlo.y) (rlo.z rhi.x rhi.y rhi.z) (left, right, -, -);
                               //   a child index < 0 is the leaf ~index (cull order); node 0 is the root
     int bvh_nodes;
+    // tensor-core cull (rt_cull_tc.cuh): TF32 feature rows of the listed leaves, tc_tiles tiles of 256 rows x 32 K-slots in
+    // the canonical K-major UMMA layout (padding rows never survive); 0 tiles = not built
+    const float* cull_tc;
+    const int* tc_row_k;          // [tc_tiles * 256] cull index of the leaf in feature row p (a fixed shuffle of the list), -1 = padding
+    int tc_tiles;
 };
 
 struct DevCamera {

@@ -494,6 +494,7 @@ struct WaveParams {
     volatile LaneStatus* status;   // the lane's status record in mapped host memory (null inside wf_tail's per-CTA views)
     unsigned iter;                 // 1-based number of this iteration within the render (LaneStatus::seq after its wf_shade)
     TraceRec* trace;               // this launch's timeline record, or null
+    int tc_slots;                  // wf_cull_tc: ray-tile buffers in shared memory (2 .. 4)
 };
 __device__ __forceinline__ void publish_status(const WaveParams& W, unsigned n_next, unsigned n_fresh, unsigned exhausted, unsigned mode,
                                                unsigned seq) {
@@ -792,6 +793,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) wf_cull(const __grid_constant__ W
     __syncthreads();
     wf_cull_body<R, BLOCK>(W, grid_scope(), W.cur, n_g, n_p, gen_base, s_cull, s_cullc, s_list);
 }
+
+#include "rt_cull_tc.cuh"   // wf_cull_tc: the same cull on the tensor cores (tcgen05 / TMEM)
 
 // one thread per pair: FP64 refine + 64-bit atomicMin on the bit pattern of t (> 0, so the order is preserved).
 // The atomic's result is NOT consumed (fire-and-forget RED; a returning ATOM made this kernel 3x slower):
