@@ -124,7 +124,8 @@ struct Options {
     int tail_rays = 1;                // RT_TAIL_RAYS: rays per thread of the tail kernel's cull while its slices are long (1 | 4)
     int mega_regcap = 0;              // 1: the register-capped megakernel (128 registers, 2 CTAs / SM) instead of the uncapped one
     int wave_depth = 2;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
-    int cull_tc = 0;                  // RT_CULL_TC: 1 = the cull runs on the tensor cores (wf_cull_tc) when the list fits (<= 1024 leaves)
+    int cull_tc = 1;                  // RT_CULL_TC: 0 = FP32 cull (wf_cull) always; 1 = the cull runs on the tensor cores (wf_cull_tc) when the list fits (<= 1024 leaves);
+                                      //   2 = except a lane's first, all-camera-ray iteration when those rays share an origin
     int tc_tiles_per_cta = 0;         // RT_TC_TILES_PER_CTA: ray tiles a wf_cull_tc CTA takes before it retires (0 = one CTA per SM, persistent)
 };
 
@@ -498,6 +499,10 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     for (auto& x : e) { RT_CUDA(ctx, cudaEventCreate(&x)); evs.push_back(x); }
                 if (ctx->profile) cudaEventRecord(e[0], st[l]);
                 W[l].iter = (unsigned)(enq[l] + 1);
+                // cull_tc = 2: a lane's first iteration (only fresh camera rays) stays on the FP32 cull's common-origin form when they
+                // share an origin.  Faster for that launch alone (1.18 vs 1.4 ms for 9.6 M rays), slower for the frame (5.93 vs 5.72 ms
+                // on C2: the short-CTA FP32 cull and the other lane's tensor-core cull get in each other's way)
+                const bool tc_now = use_tc && !(enq[l] == 0 && P.common_origin && opt.cull_tc == 2);
                 if (bvh) {
                     W[l].trace = trace_slot("bvh", l, iter_no[l]);
                     k_bvh<<<light_grid, 128, 0, st[l]>>>(W[l]);
@@ -508,7 +513,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     ctx->n_launches -= 2;   // two launches this iteration, not four
                 } else if (claims) {
                     W[l].trace = trace_slot("cull", l, iter_no[l]);
-                    if (use_tc) {
+                    if (tc_now) {
                         const unsigned tiles = (n_bound[l] + tc::TILE_M - 1) / tc::TILE_M;
                         WaveParams Wt = W[l];
                         Wt.claims_per_warp = tc_per_cta;
@@ -533,7 +538,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     RT_CUDA(ctx, cudaStreamWaitEvent(st[l], L.ev_shaded, 0));
                 } else {
                     W[l].trace = trace_slot("cull", l, iter_no[l]);
-                    if (use_tc) {
+                    if (tc_now) {
                         WaveParams Wt = W[l];
                         Wt.claims_per_warp = 0;
                         Wt.tc_slots = tc_slots;

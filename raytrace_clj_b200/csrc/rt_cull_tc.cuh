@@ -249,9 +249,11 @@ __device__ __forceinline__ void tc_produce_ray(const WaveParams& W, const tc::Sm
 struct TcEmit {
     unsigned pos, end;                 // warp-uniform: next free slot / end of the current reservation
     unsigned next;                     // lane 0: start of the reservation requested ahead
+    unsigned pads;                     // padding slots written so far (WaveState::pad: wf_refine takes them off the candidate count)
 };
-__device__ __forceinline__ void tc_pad(const WaveParams& W, unsigned from, unsigned to, unsigned lane) {
+__device__ __forceinline__ void tc_pad(const WaveParams& W, TcEmit& E, unsigned from, unsigned to, unsigned lane) {
     for (unsigned i = from + lane; i < to; i += 32) W.pairs[i] = make_uint2(PAIR_NULL, 0u);
+    if (to > from) E.pads += to - from;
 }
 __device__ __forceinline__ void tc_request(const WaveParams& W, TcEmit& E, unsigned lane) {
     unsigned b = 0;
@@ -283,7 +285,7 @@ __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S,
         const unsigned total = __popc(bal);
         if (total == 0) continue;
         if (E.pos + total > E.end) {   // move to the reservation requested ahead (the rest of the old one becomes padding), request another
-            tc_pad(W, E.pos, E.end, lane);
+            tc_pad(W, E, E.pos, E.end, lane);
             const unsigned b = __shfl_sync(0xffffffffu, E.next, 0);
             E.pos = min(b, W.pair_cap);
             E.end = min(b + (unsigned)tc::PAIR_CHUNK, W.pair_cap);
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
         const uint32_t t_lane = ((warp & 3u) * 32u) << 16;
         uint32_t* cand = S.cand + warp * tc::CAND_CAP;
         unsigned* cand_n = S.cand_n + warp;
-        TcEmit E{0u, 0u, 0u};
+        TcEmit E{0u, 0u, 0u, 0u};
         tc_request(W, E, lane);
         unsigned g = 0;
         for (unsigned it = 0; it < n_it; ++it) {
@@ -500,10 +502,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
             __syncwarp();
             TC_ACC(3, t3);
         }
-        tc_pad(W, E.pos, E.end, lane);
+        tc_pad(W, E, E.pos, E.end, lane);
         {                              // the reservation requested ahead and never used
             const unsigned b = __shfl_sync(0xffffffffu, E.next, 0);
-            tc_pad(W, min(b, W.pair_cap), min(b + (unsigned)tc::PAIR_CHUNK, W.pair_cap), lane);
+            tc_pad(W, E, min(b, W.pair_cap), min(b + (unsigned)tc::PAIR_CHUNK, W.pair_cap), lane);
+            if (lane == 0 && E.pads) atomicAdd(&W.st->pad, E.pads);
         }
     }
 #ifdef RT_TC_TIMING

@@ -435,7 +435,7 @@ struct alignas(8) WaveState {
     unsigned done;                 // CTAs of the running wf_shade launch that have finished (the last one takes the ticket)
     unsigned mode;                 // MODE_RUN, or MODE_DONE once the lane has drained (set on the device by the last CTA of
                                    // wf_shade / wf_tail): kernels queued past the end look at it and return at once
-    unsigned pad;
+    unsigned pad;                  // PAIR_NULL padding slots among this iteration's npairs (wf_cull_tc reserves pair slots in chunks)
 };
 enum { MODE_RUN = 0, MODE_DONE = 2 };
 // What the host needs to know about a lane, written by the device straight into pinned, mapped HOST memory by the last
@@ -815,7 +815,8 @@ __device__ __forceinline__ void wf_refine_body(const WaveParams& W, const DevSce
         W.st->batch = 0;               // wf_cull is done with it
         W.st->cnt[cur ^ 1][0] = 0;     // wf_shade appends to both regions of the other queue next
         W.st->cnt[cur ^ 1][1] = 0;
-        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)npairs);   // the direct spheres' exact tests are counted apart (DC_DIRECT)
+        atomicAdd(&P.counters[DC_CANDIDATES], (unsigned long long)(npairs - min(npairs, W.st->pad)));   // real pairs (wf_cull_tc pads its reservations); the direct spheres' exact tests are counted apart (DC_DIRECT)
+        W.st->pad = 0;
     }
     const unsigned total_warps = sc_.nblk * (blockDim.x >> 5);
     const unsigned warp_id = sc_.bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
