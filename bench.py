@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FLOP_PER_TEST = 17.0            # oc (3) + oc.d (5) + oc.oc - r^2 (6) + b'^2 - a c' (3)
+TF32_PEAK_MEASURED_TFLOPS = 2043.3 * 2 * 148 * 1.965e9 / 1e12   # csrc/tcprobe.cu, profiles/r02_tcprobe.txt
 FLOP_COMMON_ORIGIN_TEST = 10.0  # what the common-origin form EXECUTES per test (5 FFMA): the rest is hoisted per sphere
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.45: SMs x lanes x 2 flop x max SM clock
 
@@ -190,6 +191,9 @@ def run_reference(args, world, rank):
     return 0
 
 
+CULL_TC = 1   # set by main() from --cull
+
+
 def in_library_run(rt, device_ids, flat, cam_type, cam, nx, ny, spp, depth, variant, steps, warmup, reduce_mode, rows, seed0=600, accel=0):
     """ONE process driving len(device_ids) GPUs through the C ABI with host buffers — what the JVM caller would do
     (core.clj:99-108): rt_set_scene + rt_set_camera + rt_render per step, wall clock.  Returns a record."""
@@ -197,6 +201,7 @@ def in_library_run(rt, device_ids, flat, cam_type, cam, nx, ny, spp, depth, vari
     with rt.native.Renderer(device_ids) as r:
         r.set_option("reduce", reduce_mode)
         r.set_option("rows", rows)
+        r.set_option("cull_tc", CULL_TC)
         if accel:
             r.set_accel(accel)        # per context; every rt_set_scene below rebuilds the tree (inside the timed region)
 
@@ -235,6 +240,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU renders the workload's spp (global spp = spp x N); strong: the spp are divided")
     ap.add_argument("--accel", default="brute", choices=["brute", "bvh"], help="closest-hit search: brute force (the roofline path) or the GPU BVH")
+    ap.add_argument("--cull", default="tc", choices=["tc", "fp32"],
+                    help="brute-force cull: tc = tcgen05 tensor cores where the list fits (the library's default), fp32 = FP32 pipe only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong-c3", action="store_true", help="skip the BASELINE config 3 strong-scaling block")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
@@ -277,6 +284,11 @@ def main():
     accel_id = rt.native.RT_ACCEL_BVH if args.accel == "bvh" else 0
     if accel_id:
         r.set_accel(accel_id)
+    global CULL_TC
+    cull_tc = CULL_TC = 1 if args.cull == "tc" else 0
+    r.set_option("cull_tc", cull_tc)
+    # the tensor-core cull keeps the whole leaf list in shared memory: lists beyond 1024 leaves stay on the FP32 pipe
+    tc_active = bool(cull_tc) and accel_id == 0 and args.variant == 1 and flat.n_spheres <= 1024 + 8
     info = r.device_info()
 
     d_sum = torch.zeros(ny, nx, 3, device=dev, dtype=torch.float32)
@@ -382,6 +394,7 @@ def main():
     stage = None
     if rank == 0 and args.variant == 1 and args.accel == "brute":
         with rt.native.Renderer([local_rank]) as rp:
+            rp.set_option("cull_tc", cull_tc)
             rp.set_scene(flat)
             rp.set_camera(cam_type, cam)
             ps = torch.zeros(ny, nx, 3, device=dev, dtype=torch.float32)
@@ -400,7 +413,7 @@ def main():
         achieved_tflops = FLOP_PER_TEST * tests_gpu / step_s / 1e12            # per GPU, whole render step incl. reduce + resolve
         # what the cull EXECUTES: the camera rays (one per sample when they share an origin) run the 10-flop common-origin form
         n_prims = flat.n_spheres
-        cam_tests = (samples / world / args.steps) * n_prims if (cam[21] == 0.0 or cam_type == 0) else 0.0
+        cam_tests = (samples / world / args.steps) * n_prims if ((cam[21] == 0.0 or cam_type == 0) and not tc_active) else 0.0
         executed_tflops = (FLOP_COMMON_ORIGIN_TEST * cam_tests + FLOP_PER_TEST * (tests_gpu - cam_tests)) / step_s / 1e12
         peak_measured = max(fp32_peak)
         line = {
@@ -414,7 +427,9 @@ def main():
                 "parallelism": (f"sample slices x{world}: every GPU renders {spp} spp of the frame, one NCCL reduce"
                                 if world > 1 else "single GPU"),
                 "l2": "flushed between timed iterations (256 MiB fill); the scene itself is staged in shared memory",
-                "precision": "FP32 cull over all primitives, FP64 refine of survivors, FP32 shading",
+                "cull": ("tcgen05 tensor cores: the line-sphere discriminant of every (ray, primitive) pair as a 3xTF32 GEMM (32 K-slots) into TMEM, "
+                         "sign-bit epilogue, FP32 confirm of the ~0.5 % candidates" if tc_active else "FP32 pipe (17-flop conservative test, 10.4 instructions per pair)"),
+                "precision": "conservative cull over all primitives (never loses an exact hit), FP64 refine of survivors, FP32 shading",
             },
             "tests_per_sec": tests / (total_ms * 1e-3),
             "rays_per_sample": rays / samples,
@@ -432,14 +447,24 @@ def main():
                 "peak_ffma_tflops": fp32_peak[0], "peak_ffma2_tflops": fp32_peak[1],
                 "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tflops / NOMINAL_FP32_TFLOPS,
                 "flop_per_test": FLOP_PER_TEST,
+                "tensor": None if not tc_active else {
+                    "executed_tf32_flop_per_test": 64, "achieved": 64.0 * tests_gpu / step_s / 1e12, "peak": TF32_PEAK_MEASURED_TFLOPS,
+                    "unit": "TFLOP/s", "frac": 64.0 * tests_gpu / step_s / 1e12 / TF32_PEAK_MEASURED_TFLOPS,
+                    "note": "what the tensor pipe executes for the cull: 32 TF32 multiply-adds per pair (hi/lo split of 11 feature products), "
+                            "whole step; peak = tcgen05 kind::tf32 M128 N256 K8 issue rate measured by csrc/tcprobe.cu on this pool's B200 "
+                            "(2043 MAC/clk/SM x 148 SMs x 1.965 GHz; profiles/r02_tcprobe.txt). The kernel's own bound is the epilogue: one "
+                            "ALU-pipe funnel shift (half rate) and 4 bytes of TMEM read per pair, 64 pairs/clk/SM at best",
+                },
                 "traffic": None,
                 "traffic_note": "not measured inside this run; the committed `ncu --set full` captures under profiles/ hold the "
                                 "dram__bytes of a wf_cull launch (ray record in, pairs out: the kernel is FP32-issue bound, not HBM bound)",
-                "note": "non-tensor FP32 pipe; HBM is not the bound (scene in shared memory). `achieved` = 17 algorithmic flop x "
+                "note": "denominator = the non-tensor FP32 pipe (what the 17-flop test costs without tensor cores); with the tensor-core cull "
+                        "the dot products leave that pipe, so `frac` can pass what the FP32 pipe alone could reach (see `tensor`). "
+                        "HBM is not the bound (scene in shared memory). `achieved` = 17 algorithmic flop x "
                         "(rays x primitives) / ms_per_step (the whole step: cull + refine + tie-break + shade + reduce + resolve); "
                         "`frac_executed_flop` counts the camera rays' tests at the 10 flop their common-origin form executes",
                 "dominant_kernel": None if not stage else {
-                    "name": "wf_cull", "ms_per_step": stage["cull"],
+                    "name": "wf_cull_tc" if tc_active else "wf_cull", "ms_per_step": stage["cull"],
                     "achieved": FLOP_PER_TEST * stage["tests"] / (stage["cull"] * 1e-3) / 1e12,
                     "frac": FLOP_PER_TEST * stage["tests"] / (stage["cull"] * 1e-3) / 1e12 / peak_measured,
                     "share_of_step": stage["cull"] / max(1e-9, sum(stage[k] for k in ("cull", "refine", "tiebreak", "shade"))),

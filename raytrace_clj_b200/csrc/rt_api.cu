@@ -439,6 +439,14 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
         return d.d_trace + (d.trace_meta.size() - 1);
     };
     int iter_no[kMaxLanes] = {};
+    // RT_DEBUG_SYNC=1: synchronise after every launch of the iteration loop and name the kernel that failed
+    static const bool debug_sync = getenv("RT_DEBUG_SYNC") && *getenv("RT_DEBUG_SYNC") == '1';
+    auto dbg = [&](const char* what, int lane, int it) -> int {
+        if (!debug_sync) return RT_OK;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string(what) + " (lane " + std::to_string(lane) + ", iteration " + std::to_string(it) + "): " + cudaGetErrorString(e));
+        return RT_OK;
+    };
     // the shared work counter starts past every lane's first fill
     unsigned count0[kMaxLanes];
     unsigned long long total0 = 0;
@@ -513,6 +521,12 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     ctx->n_launches -= 2;   // two launches this iteration, not four
                 } else if (claims) {
                     W[l].trace = trace_slot("cull", l, iter_no[l]);
+                    if (debug_sync) {
+                        WaveState hs{};
+                        cudaMemcpy(&hs, W[l].st, sizeof hs, cudaMemcpyDeviceToHost);
+                        fprintf(stderr, "lane %d iteration %d cur %d: in flight %u fresh %u | other queue %u %u | mode %u exhausted %u npairs %u\n", l, enq[l], W[l].cur,
+                                hs.cnt[W[l].cur][0], hs.cnt[W[l].cur][1], hs.cnt[W[l].cur ^ 1][0], hs.cnt[W[l].cur ^ 1][1], hs.mode, hs.exhausted, hs.npairs);
+                    }
                     if (tc_now) {
                         const unsigned tiles = (n_bound[l] + tc::TILE_M - 1) / tc::TILE_M;
                         WaveParams Wt = W[l];
@@ -526,14 +540,18 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     const unsigned ctas = (items + (unsigned)(cull_warps * claims) - 1u) / (unsigned)(cull_warps * claims);
                     cull<<<ctas, cull_block, smem, st[l]>>>(W[l]);
                     }
+                    if ((rc = dbg(tc_now ? "wf_cull_tc" : "wf_cull", l, enq[l]))) return rc;
                     RT_CUDA(ctx, cudaEventRecord(L.ev_culled, st[l]));
                     RT_CUDA(ctx, cudaStreamWaitEvent(L.stage_stream, L.ev_culled, 0));
                     W[l].trace = trace_slot("refine", l, iter_no[l]);
                     k_refine<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    if ((rc = dbg("wf_refine", l, enq[l]))) return rc;
                     W[l].trace = trace_slot("tiebreak", l, iter_no[l]);
                     wf_tiebreak<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    if ((rc = dbg("wf_tiebreak", l, enq[l]))) return rc;
                     W[l].trace = trace_slot("shade", l, iter_no[l]);
                     k_shade<<<light_grid, light_block, 0, L.stage_stream>>>(W[l]);
+                    if ((rc = dbg("wf_shade", l, enq[l]))) return rc;
                     RT_CUDA(ctx, cudaEventRecord(L.ev_shaded, L.stage_stream));
                     RT_CUDA(ctx, cudaStreamWaitEvent(st[l], L.ev_shaded, 0));
                 } else {
@@ -585,6 +603,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 W[l].iter = (unsigned)(enq[l] + 1);
                 W[l].trace = trace_slot("tail", l, iter_no[l]);
                 k_tail<<<tail_grid, tail_block, tail_smem, st[l]>>>(W[l]);
+                if ((rc = dbg("wf_tail", l, enq[l]))) return rc;
                 RT_CUDA(ctx, cudaGetLastError());
                 ctx->n_launches += 1;
                 tailed[l] = true;
@@ -1877,6 +1896,9 @@ int rt_cull_check(rt_ctx* ctx, int n, const float* origins, const float* dirs, c
         W.capacity = (int)L.entries;
         W.pair_cap = (unsigned)std::min<size_t>(L.entries * kPairsPerEntry, 0xfffffff0u);
         wf_fill_best<<<d.sm_count * 4, 256, 0, d.stream>>>(L.best, L.best + L.entries, L.entries);
+#ifdef RT_TC_CHECK
+        RT_CUDA(ctx, cudaMemsetAsync(L.pairs, 0xDD, (size_t)W.pair_cap * sizeof(uint2), d.stream));
+#endif
         tc_check_fill<<<(n + 127) / 128, 128, 0, d.stream>>>(W, n, d_o, d_d, times ? d_tm : nullptr);
         W.tc_slots = tc::slots_for(ctx->tc_tiles, 227 * 1024);
         const size_t tc_smem = tc::smem_bytes(ctx->tc_tiles, W.tc_slots);

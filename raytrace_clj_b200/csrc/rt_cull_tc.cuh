@@ -135,6 +135,7 @@ inline void sphere_slots(const double c[3], double W, float out[KTOT]) {
 }
 inline void padding_slots(float out[KTOT]) {
     for (int k = 0; k < KTOT; ++k) out[k] = 0.f;
+    out[0] = 1.f;                      // against g0.hi: a DEAD ray stays dead (0 x 0 would be +0 = "candidate")
     out[2] = DEAD;                     // W.hi against the ray's 1
 }
 
@@ -183,6 +184,13 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int tiles, int slots)
 
 }  // namespace tc
 
+// RT_TC_CHECK (compile-time, debugging): index checks before every global access of the kernel
+#ifdef RT_TC_CHECK
+#define TC_CHECK(cond, what, a, b) do { if (!(cond)) { printf("wf_cull_tc check failed: %s (%u, %u) block %u thread %u\n", what, (unsigned)(a), (unsigned)(b), blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define TC_CHECK(cond, what, a, b)
+#endif
+
 // One ray of the tile: features into A[slot] (canonical layout), FP32 cull constants into ray[slot].
 // v = virtual queue index (v < n_g: path in flight, its record is loaded; else fresh: generated here and written).
 __device__ __forceinline__ void tc_produce_ray(const WaveParams& W, const tc::Smem& S, int slot, int rl, bool live, unsigned v, unsigned n_g,
@@ -196,9 +204,12 @@ __device__ __forceinline__ void tc_produce_ray(const WaveParams& W, const tc::Sm
         if (v >= n_g) {
             float4 c;
             float4* q = qc + 3 * (size_t)(p0 + (v - n_g));
+            TC_CHECK(p0 + (v - n_g) < (unsigned)W.capacity, "fresh entry", p0 + (v - n_g), W.capacity);
+            TC_CHECK(gen_base + (v - n_g) < P.total_work, "work item", (unsigned)(gen_base + (v - n_g)), (unsigned)P.total_work);
             make_path(P, gen_base + (v - n_g), a, b, c);
             q[0] = a; q[1] = b; q[2] = c;
         } else {
+            TC_CHECK(v < (unsigned)W.capacity, "entry in flight", v, W.capacity);
             a = qc[3 * (size_t)v];
             b = qc[3 * (size_t)v + 1];
         }
@@ -231,7 +242,8 @@ __device__ __forceinline__ void tc_produce_ray(const WaveParams& W, const tc::Sm
     } else {
 #pragma unroll
         for (int k = 0; k < tc::KTOT; ++k) f[k] = 0.f;
-        f[0] = tc::DEAD;
+        f[0] = tc::DEAD;               // g0.hi against the 1 every row (padding included) carries in slot 0
+        f[2] = 1.f;                    // and a padding row's W.hi = DEAD counts too: dead ray x padding row = -2e30, never +0
         r0 = make_float4(1.f, 0.f, 0.f, 0.f);
         r1 = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);
     }
@@ -252,7 +264,12 @@ struct TcEmit {
     unsigned pads;                     // padding slots written so far (WaveState::pad: wf_refine takes them off the candidate count)
 };
 __device__ __forceinline__ void tc_pad(const WaveParams& W, TcEmit& E, unsigned from, unsigned to, unsigned lane) {
+    TC_CHECK(to <= W.pair_cap, "pad", from, to);
+#ifdef RT_TC_CHECK
+    for (unsigned i = from + lane; i < to; i += 32) W.pairs[i] = make_uint2(PAIR_NULL, (blockIdx.x << 8) | (threadIdx.x >> 5));
+#else
     for (unsigned i = from + lane; i < to; i += 32) W.pairs[i] = make_uint2(PAIR_NULL, 0u);
+#endif
     if (to > from) E.pads += to - from;
 }
 __device__ __forceinline__ void tc_request(const WaveParams& W, TcEmit& E, unsigned lane) {
@@ -271,6 +288,7 @@ __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S,
         if (idx < ncand) {
             const uint32_t c = cand[idx];
             const unsigned rl = c >> 20, row = c & 0xfffffu;
+            TC_CHECK(rl < 128u && row < (unsigned)W.base.sc.tc_tiles * 256u, "candidate", c, ncand);
             const float4 r0 = S.ray((unsigned)slot)[2 * rl], r1 = S.ray((unsigned)slot)[2 * rl + 1];
             const float4 R = S.rec[row];
             const int kk = S.row_k[row];
@@ -280,6 +298,20 @@ __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S,
             emit = (__float_as_uint(key) >> 31) == 0u && kk >= 0;                 // (a padding row never gets here: W = DEAD)
             k = (unsigned)kk;
             entry = wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity);
+#ifdef RT_TC_CHECK
+            if (kk >= 0) {   // the candidate must be a line-sphere intersection of THIS entry's ray and THIS leaf's bounding sphere (with slack)
+                const float4* qc = W.cur ? W.queue[1] : W.queue[0];
+                const float4 qa = qc[3 * (size_t)entry], qb = qc[3 * (size_t)entry + 1];
+                const float4 Rg = W.base.sc.cull_a[kk];
+                const double cx = -(double)Rg.x, cy = -(double)Rg.y, cz = -(double)Rg.z, R2 = (double)Rg.w + cx * cx + cy * cy + cz * cz;
+                const double dn = sqrt((double)qb.x * qb.x + (double)qb.y * qb.y + (double)qb.z * qb.z);
+                const double ux = qb.x / dn, uy = qb.y / dn, uz = qb.z / dn, ox = qa.x - cx, oy = qa.y - cy, oz = qa.z - cz;
+                const double bb = ux * ox + uy * oy + uz * oz, disc = bb * bb - (ox * ox + oy * oy + oz * oz) + R2;
+                if (disc < -1e-3 * (R2 + ox * ox + oy * oy + oz * oz))
+                    printf("bogus candidate: tile %u rl %u row %u k %d entry %u disc %g (R2 %g |oc|2 %g) slot %d idx %u of %u block %u warp %u\n", tile, rl, row, kk, entry, disc, R2,
+                           ox * ox + oy * oy + oz * oz, slot, idx, ncand, blockIdx.x, threadIdx.x >> 5);
+            }
+#endif
         }
         const unsigned bal = __ballot_sync(0xffffffffu, emit);
         const unsigned total = __popc(bal);
@@ -293,6 +325,8 @@ __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S,
         }
         if (emit) {
             const unsigned w = E.pos + __popc(bal & ((1u << lane) - 1u));
+            TC_CHECK(entry < (unsigned)W.capacity && k < (unsigned)W.base.sc.n_list, "pair", entry, k);
+            TC_CHECK(w >= E.end || w < W.pair_cap, "pair slot", w, W.pair_cap);
             if (w < E.end) W.pairs[w] = make_uint2(entry, k);
             else W.best_key[entry] = BEST_KEY_OVERFLOW;       // pair buffer full: wf_shade re-intersects this entry exactly
         }
@@ -434,6 +468,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
                 if (progressed) idle = 0;
                 else if (++idle > 0x20000000u) __trap();        // a protocol error must not hang the device
             }
+            // the last commit's arrival is asynchronous: it must have landed in this CTA's shared memory before the CTA may exit
+            tc::mbar_wait(&S.a_free[(n_it - 1) % slots], ((n_it - 1) / slots) & 1u);
         }
         __syncwarp();
     } else {
@@ -469,14 +505,53 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
                     unsigned w0 = 0u, w1 = 0u;
 #pragma unroll
                     for (int q = 0; q < 32; ++q) { w0 = __funnelshift_l(v0[q], w0, 1); w1 = __funnelshift_l(v1[q], w1, 1); }
-                    m0 = ~w0; m1 = ~w1;                         // candidates: clear sign bits; column q of a word is bit 31 - q
+                    const bool live_ray = tile * tc::TILE_M + rl < n;   // (a dead ray's discriminants are all -1e30; never let it index anything)
+                    m0 = live_ray ? ~w0 : 0u; m1 = live_ray ? ~w1 : 0u;   // candidates: clear sign bits; column q of a word is bit 31 - q
                 }
                 TC_ACC(1, t1);
                 TC_T(t2);
                 const unsigned row0 = (unsigned)j * tc::TILE_N + cb * 64u;
+#ifdef RT_TC_CHECK
+                {   // the accumulator's sign bits against the same products summed in double from the operands in shared memory
+                    const unsigned char* Ab = reinterpret_cast<const unsigned char*>(S.A(s));
+                    const unsigned char* Bb = reinterpret_cast<const unsigned char*>(S.B) + (size_t)j * tc::B_TILE_BYTES;
+                    for (int q = 0; q < 64; ++q) {
+                        double acc = 0.0, mag = 0.0;
+                        for (int k = 0; k < tc::KTOT; ++k) {
+                            const double x = (double)*reinterpret_cast<const float*>(Ab + tc::canon_off(tc::TILE_M, (int)rl, k)) *
+                                             (double)*reinterpret_cast<const float*>(Bb + tc::canon_off(tc::TILE_N, (int)(cb * 64u) + q, k));
+                            acc += x; mag += fabs(x);
+                        }
+                        const unsigned culled = ((q < 32 ? ~m0 : ~m1) >> (31 - (q & 31))) & 1u;   // sign bit as collected
+                        if (acc > 1e-4 * mag && culled && mag < 1e20)
+                            printf("TMEM mismatch: tile %u ray %u col %u (row %u) double %g (mag %g) but sign bit set; block %u warp %u buffer %u g %u\n", tile, rl, (unsigned)q, row0 + q,
+                                   acc, mag, blockIdx.x, warp, b, g);
+                        if (acc < -1e-4 * mag && !culled)
+                            printf("TMEM mismatch: tile %u ray %u col %u (row %u) double %g (mag %g) but sign bit clear; block %u warp %u buffer %u g %u\n", tile, rl, (unsigned)q, row0 + q,
+                                   acc, mag, blockIdx.x, warp, b, g);
+                    }
+                }
+#endif
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     unsigned mm = h ? m1 : m0;
+#ifdef RT_TC_BALLOT_PUSH
+                    while (__any_sync(0xffffffffu, mm != 0u)) {
+                        const bool has = mm != 0u;
+                        const unsigned bal = __ballot_sync(0xffffffffu, has);
+                        const unsigned base = *cand_n;
+                        if (has) {
+                            const int bit = 31 - __clz((int)mm);
+                            mm &= ~(1u << bit);
+                            const unsigned pos = base + __popc(bal & ((1u << lane) - 1u));
+                            if (pos < (unsigned)tc::CAND_CAP) cand[pos] = (rl << 20) | (row0 + (unsigned)h * 32u + (unsigned)(31 - bit));
+                            else W.best_key[wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity)] = BEST_KEY_OVERFLOW;
+                        }
+                        __syncwarp();
+                        if (lane == 0) *cand_n = base + __popc(bal);
+                        __syncwarp();
+                    }
+#else
                     while (mm != 0u) {                          // lanes with candidates only (divergent; a shared-memory atomic hands out slots)
                         const int bit = 31 - __clz((int)mm);
                         mm &= ~(1u << bit);
@@ -484,12 +559,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
                         if (pos < (unsigned)tc::CAND_CAP) cand[pos] = (rl << 20) | (row0 + (unsigned)h * 32u + (unsigned)(31 - bit));
                         else W.best_key[wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity)] = BEST_KEY_OVERFLOW;   // list full: exact re-intersection downstream
                     }
+#endif
                 }
                 TC_ACC(2, t2);
             }
             __syncwarp();
             TC_T(t3);
             const unsigned ncand = min(*cand_n, (unsigned)tc::CAND_CAP);
+#ifdef RT_TC_CHECK
+            if (lane == 0 && ncand > 48u && n < 300u)
+                printf("big candidate list: block %u warp %u tile %u it %u ncand %u raw %u first %x %x %x %x last %x\n", blockIdx.x, warp, tile, it, ncand, *cand_n, cand[0], cand[1], cand[2], cand[3], cand[ncand - 1]);
+#endif
             if (ncand) {
                 tc::mbar_wait(&S.a_ready[s], a_ph);             // (long complete) the producers' writes of ray[s], acquired directly
                 tc_drain(W, S, (int)s, tile, n_g, n_p, cand, ncand, E, lane);
@@ -539,9 +619,27 @@ __global__ void tc_check_fill(const __grid_constant__ WaveParams W, int n, const
 }
 __global__ void tc_check_mark(const __grid_constant__ WaveParams W, unsigned* mask, int words) {
     const unsigned npairs = min(W.st->npairs, W.pair_cap);
+#ifdef RT_TC_CHECK
+    if (blockIdx.x == 0 && threadIdx.x == 0 && W.st->cnt[0][0] < 300u) {
+        // the harness filled the pair buffer with 0xDD bytes: a slot still holding them was never written
+        for (unsigned c0 = 0; c0 < npairs; c0 += 64) {
+            unsigned never = 0, real = 0, tag0 = 0xffffffffu, tags = 0;
+            for (unsigned i = c0; i < min(c0 + 64u, npairs); ++i) {
+                const uint2 pr = W.pairs[i];
+                if (pr.x == 0xddddddddu) ++never;
+                else if (pr.x == PAIR_NULL) { if (pr.y != tag0) { ++tags; tag0 = pr.y; } }
+                else ++real;
+            }
+            if (never || tags > 1 || real)
+                printf("chunk %u: never written %u, real %u, pad-tag changes %u (last tag block %u warp %u)  first entries (%x %x) (%x %x) (%x %x) ... (%x %x)\n", c0, never, real, tags,
+                       tag0 >> 8, tag0 & 255u, W.pairs[c0].x, W.pairs[c0].y, W.pairs[c0 + 1].x, W.pairs[c0 + 1].y, W.pairs[c0 + 2].x, W.pairs[c0 + 2].y, W.pairs[c0 + 63].x, W.pairs[c0 + 63].y);
+        }
+        printf("npairs %u pad counter %u\n", W.st->npairs, W.st->pad);
+    }
+#endif
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
         const uint2 pr = W.pairs[i];
-        if (pr.x != PAIR_NULL) atomicOr(&mask[(size_t)pr.x * words + (pr.y >> 5)], 1u << (pr.y & 31u));
+        if (pr.x != PAIR_NULL && pr.x < (unsigned)W.capacity) atomicOr(&mask[(size_t)pr.x * words + (pr.y >> 5)], 1u << (pr.y & 31u));
     }
 }
 __global__ void __launch_bounds__(128) tc_check_compare(const __grid_constant__ WaveParams W, int n, double tmin, double tmax, const unsigned* mask,
@@ -560,6 +658,9 @@ __global__ void __launch_bounds__(128) tc_check_compare(const __grid_constant__ 
             if (t < CUDART_INF) {
                 cand++;
                 lost += kept ? 0u : 1u;
+#ifdef RT_TC_CHECK
+                if (!kept) printf("lost pair: ray %d leaf %d t %.9g  o (%.9g %.9g %.9g) d (%.9g %.9g %.9g)\n", idx, k, t, a.x, a.y, a.z, b.x, b.y, b.z);
+#endif
             }
         }
     }

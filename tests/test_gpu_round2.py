@@ -592,3 +592,26 @@ def test_tensor_core_cull_gives_identical_paths(renderer, scene_name):
         renderer.set_option("cull_tc", 1)
     for a, b in zip(out[0][:3], out[1][:3]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("scene_name", ["sweep:100", "cornell", "random"])
+def test_tensor_core_cull_short_queues_and_partial_tiles(renderer, scene_name):
+    """Launches of a few rays: one ray tile per CTA, the last one mostly DEAD slots, and (scenes with few leaves) feature
+    tiles that are mostly padding rows.  Regression: dead ray x padding row used to come out as +0 = a candidate."""
+    import bench
+    flat, cam_type, cam = bench.build_scene(scene_name, 300, 300, 1)
+    renderer.set_scene(flat)
+    renderer.set_camera(cam_type, cam)
+    rng = np.random.default_rng(12)
+    try:
+        for n in (1, 7, 128, 129, 130, 257, 1000, 4000):
+            o = rng.uniform(-5, 5, size=(n, 3)).astype(np.float32) * (60.0 if scene_name == "cornell" else 1.0)
+            d = rng.normal(size=(n, 3)).astype(np.float32)
+            res = {}
+            for mode in (0, 1):
+                renderer.set_option("cull_tc", mode)
+                res[mode] = renderer.cull_check(o, d, None, 0.001, FMAX)
+                assert res[mode][0] == 0, f"{scene_name} n={n} cull_tc={mode}: lost {res[mode][0]} of {res[mode][2]}"
+            assert res[0][2] == res[1][2]
+    finally:
+        renderer.set_option("cull_tc", 1)

@@ -158,3 +158,18 @@ def test_selectivity_stays_close_to_the_exact_test():
     ref = exact_disc(oo, dd, ccs, rr).reshape(3000, 400)
     assert not ((ref >= 0) & (disc < 0)).any()
     assert (disc >= 0).sum() <= 1.10 * (ref >= 0).sum() + 5      # r = 0.2 at |o| ~ 17: the budget is ~10 % of r^2
+
+
+def test_dead_rays_and_padding_rows_never_survive():
+    """A dead ray (tile slot beyond the queue) and a padding row (feature row beyond the leaf list) must give a NEGATIVE
+    discriminant against anything — in particular against each other (0 x 0 = +0 reads as "candidate": the bug that made
+    the last, partial ray tile of a launch flood the candidate lists on scenes with few leaves)."""
+    DEAD = np.float32(-1.0e30)
+    dead = np.zeros(32, np.float32); dead[0] = DEAD; dead[2] = 1.0           # tc_produce_ray, dead branch
+    pad = np.zeros(32, np.float32); pad[0] = 1.0; pad[2] = DEAD              # tc::padding_slots
+    rng = np.random.default_rng(4)
+    o, d, c, r = tangent_pairs(rng, 500, 50.0, 50.0, 0.1, 30.0, 1e-3)
+    R = ray_slots(o, d).astype(np.float64); S = sphere_slots(c, r).astype(np.float64)
+    assert float(dead.astype(np.float64) @ pad) < -1e29
+    assert np.all(R @ pad.astype(np.float64) < -1e29)
+    assert np.all(S @ dead.astype(np.float64) < -1e29)
