@@ -382,7 +382,9 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     void (*k_bvh)(const WaveParams) = gen ? wf_bvh<true> : wf_bvh<false>;
     const bool tail_ok = tail_bps >= 1 && tail_entries > 0 && !ctx->profile && !bvh;
     // tensor-core cull (rt_cull_tc.cuh): one 544-thread CTA per SM, the whole sphere-feature list resident in shared memory
-    const bool use_tc = opt.cull_tc != 0 && ctx->tc_tiles > 0 && !bvh;
+    // (below ~160 leaves most of a 256-column feature tile is padding and the FP32 loop wins: C5-100 39.7 vs 48.0 ms, Cornell box
+    // 47.8 vs 64.0 ms; cull_tc = 3 forces the tensor-core kernel whatever the list length)
+    const bool use_tc = opt.cull_tc != 0 && ctx->tc_tiles > 0 && !bvh && (ctx->n_list >= tc::MIN_LEAVES || opt.cull_tc == 3);
     const int tc_slots = tc::slots_for(ctx->tc_tiles, 227 * 1024);
     const size_t tc_smem = tc::smem_bytes(ctx->tc_tiles, tc_slots);
     if (use_tc) RT_CUDA(ctx, cudaFuncSetAttribute(wf_cull_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
@@ -1868,7 +1870,7 @@ int rt_cull_check(rt_ctx* ctx, int n, const float* origins, const float* dirs, c
     RT_CUDA(ctx, cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, d.stream));
     if (times) RT_CUDA(ctx, cudaMemcpyAsync(d_tm, times, (size_t)n * 4, cudaMemcpyHostToDevice, d.stream));
     RT_CUDA(ctx, cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), d.stream));
-    if (ctx->opt.cull_tc && ctx->tc_tiles > 0) {
+    if (ctx->opt.cull_tc && ctx->tc_tiles > 0) {   // (whatever the list length: this is the diagnostic)
         // option cull_tc: check the tensor-core cull by running the PRODUCTION kernel over a queue of these rays
         const size_t cap = align_up((size_t)n, 128);
         if ((rc = ensure_lane(ctx, d, 0, cap))) return rc;

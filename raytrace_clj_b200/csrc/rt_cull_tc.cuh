@@ -36,6 +36,7 @@ constexpr int KTOT = 32;                       // K-slots (TF32) per pair: 4 MMA
 constexpr int A_BYTES = TILE_M * KTOT * 4;     // 16 KB per ray tile
 constexpr int B_TILE_BYTES = TILE_N * KTOT * 4;   // 32 KB per sphere tile
 constexpr int MAX_TILES = 4;                   // resident sphere tiles
+constexpr int MIN_LEAVES = 160;                // shorter lists stay on the FP32 loop (a 256-column tile would be mostly padding)
 constexpr int CAND_CAP = 256;                  // per-warp candidate list (one ray tile)
 constexpr int PAIR_CHUNK = 64;                 // pair slots a warp reserves at a time (one atomic)
 constexpr float RAY_DEFLATE = 1.0f - 5.0e-6f;  // 1 - 84 u: the ray's share of the rounding budget, taken off |o|^2

@@ -1232,6 +1232,7 @@ __global__ void __launch_bounds__(BLOCK, GEN ? 1 : 2) wf_tail(const __grid_const
             s_st.exhausted = 1;
             s_st.done = 0;
             s_st.mode = MODE_RUN;
+            s_st.pad = 0;
         }
         // this CTA's view of the lane's buffers
         const unsigned warps = BLOCK / 32;

