@@ -127,6 +127,7 @@ struct Options {
     int cull_tc = 1;                  // RT_CULL_TC: 0 = FP32 cull (wf_cull) always; 1 = the cull runs on the tensor cores (wf_cull_tc) when the list fits (<= 1024 leaves);
                                       //   2 = except a lane's first, all-camera-ray iteration when those rays share an origin
     int tc_tiles_per_cta = 0;         // RT_TC_TILES_PER_CTA: ray tiles a wf_cull_tc CTA takes before it retires (0 = one CTA per SM, persistent)
+    int tc_ctas = 0;                  // RT_TC_CTAS: persistent wf_cull_tc CTAs (0 = one per SM); fewer leaves whole SMs to the other lane's stage kernels
 };
 
 struct rt_ctx {
@@ -314,6 +315,7 @@ Options options_from_env() {
     o.tail_block = env_int("RT_TAIL_BLOCK", o.tail_block);
     o.cull_tc = env_int("RT_CULL_TC", o.cull_tc);
     o.tc_tiles_per_cta = env_int("RT_TC_TILES_PER_CTA", o.tc_tiles_per_cta);
+    o.tc_ctas = env_int("RT_TC_CTAS", o.tc_ctas);
     return o;
 }
 
@@ -389,6 +391,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     const size_t tc_smem = tc::smem_bytes(ctx->tc_tiles, tc_slots);
     if (use_tc) RT_CUDA(ctx, cudaFuncSetAttribute(wf_cull_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     const int tc_per_cta = std::max(0, opt.tc_tiles_per_cta);
+    const int tc_grid = opt.tc_ctas > 0 ? std::min(opt.tc_ctas, 4 * d.sm_count) : d.sm_count;
 
     const int light_block = std::max(64, std::min(256, opt.light_block / 32 * 32));   // <= a cull CTA in every resource
     const int light_grid = d.sm_count * 8 * 256 / light_block;
@@ -534,7 +537,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                         WaveParams Wt = W[l];
                         Wt.claims_per_warp = tc_per_cta;
                         Wt.tc_slots = tc_slots;
-                        const unsigned ctas = tc_per_cta ? (tiles + (unsigned)tc_per_cta - 1u) / (unsigned)tc_per_cta : (unsigned)d.sm_count;
+                        const unsigned ctas = tc_per_cta ? (tiles + (unsigned)tc_per_cta - 1u) / (unsigned)tc_per_cta : (unsigned)tc_grid;
                         wf_cull_tc<<<std::max(1u, ctas), tc::THREADS, tc_smem, st[l]>>>(Wt);
                     } else {
                     // every work item of the launch must find a warp: items <= n / (32 R) + 2 resident_warps + 8 (wf_cull_body)
@@ -562,7 +565,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                         WaveParams Wt = W[l];
                         Wt.claims_per_warp = 0;
                         Wt.tc_slots = tc_slots;
-                        wf_cull_tc<<<d.sm_count, tc::THREADS, tc_smem, st[l]>>>(Wt);
+                        wf_cull_tc<<<tc_grid, tc::THREADS, tc_smem, st[l]>>>(Wt);
                     } else {
                         cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
                     }
@@ -1510,6 +1513,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "tail_block") o.tail_block = (int)value;
     else if (k == "cull_tc") o.cull_tc = (int)value;
     else if (k == "tc_tiles_per_cta") o.tc_tiles_per_cta = (int)value;
+    else if (k == "tc_ctas") o.tc_ctas = (int)value;
     else return fail(ctx, RT_ERR_ARG, "unknown option: " + k);
     return RT_OK;
 }

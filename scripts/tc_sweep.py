@@ -21,10 +21,11 @@ def run(name, opts, reps=6):
         c = r.counters()
     print(f"{name:6s} {str(opts):90s} best {min(ts[1:])*1e3:8.3f} ms  device {c['kernel_ns']*1e-6:8.3f} ms", flush=True)
 
-base = {"cull_tc": 1}
-for name in ("c2", "c1", "c4"):
-    run(name, {"cull_tc": 0})
-    run(name, base)
-    for extra in ({"wave_lanes": 1}, {"wave_depth": 3}, {"light_block": 64}, {"light_block": 256}, {"tail_entries": 1 << 18}, {"tail_entries": 1 << 20},
-                  {"tail_entries": 1 << 17}, {"wave_capacity": 1 << 22}, {"wave_capacity": 1 << 23}):
-        o = dict(base); o.update(extra); run(name, o)
+if __name__ == "__main__":
+  base = {"cull_tc": 1}
+  for name in ("c2", "c1", "c4"):
+      run(name, {"cull_tc": 0})
+      run(name, base)
+      for extra in ({"wave_lanes": 1}, {"wave_depth": 3}, {"light_block": 64}, {"light_block": 256}, {"tail_entries": 1 << 18}, {"tail_entries": 1 << 20},
+                    {"tail_entries": 1 << 17}, {"wave_capacity": 1 << 22}, {"wave_capacity": 1 << 23}):
+          o = dict(base); o.update(extra); run(name, o)
