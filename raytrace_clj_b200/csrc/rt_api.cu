@@ -140,7 +140,7 @@ struct rt_ctx {
     int n_total = 0;              // + boundary primitives of media
     int n_list = 0, n_cull = 0;   // spheres in the cull list / cull records (padded)
     int cull_cap = 0, preloaded = 0;
-    int tc_tiles = 0;             // sphere tiles of the tensor-core cull (0: the list is too long for it: FP32 cull only)
+    int tc_tiles = 0;             // feature tiles (256 leaves each) of the tensor-core cull; over 4, an iteration takes several launches
     std::vector<std::vector<float>> tc_scratch_rows;   // build_cull_records: the leaves' feature rows before they are placed
     std::vector<int> tc_row_k;    // feature row -> cull index (-1 = padding): a fixed shuffle, so every 64-row block sees the same mix
     int generic = 0;              // some leaf is not a plain sphere (rt_set_scene_ex)
@@ -387,11 +387,25 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     // (below ~160 leaves most of a 256-column feature tile is padding and the FP32 loop wins: C5-100 39.7 vs 48.0 ms, Cornell box
     // 47.8 vs 64.0 ms; cull_tc = 3 forces the tensor-core kernel whatever the list length)
     const bool use_tc = opt.cull_tc != 0 && ctx->tc_tiles > 0 && !bvh && (ctx->n_list >= tc::MIN_LEAVES || opt.cull_tc == 3);
-    const int tc_slots = tc::slots_for(ctx->tc_tiles, 227 * 1024);
-    const size_t tc_smem = tc::smem_bytes(ctx->tc_tiles, tc_slots);
+    const int tc_launch_tiles = std::min(ctx->tc_tiles, (int)tc::MAX_TILES);
+    const int tc_slots = tc::slots_for(tc_launch_tiles, 227 * 1024);
+    const size_t tc_smem = tc::smem_bytes(tc_launch_tiles, tc_slots);
     if (use_tc) RT_CUDA(ctx, cudaFuncSetAttribute(wf_cull_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     const int tc_per_cta = std::max(0, opt.tc_tiles_per_cta);
     const int tc_grid = opt.tc_ctas > 0 ? std::min(opt.tc_ctas, 4 * d.sm_count) : d.sm_count;
+    // one launch per 1024 leaves of the list ("pass"): the pairs of all passes pile up in the same buffer
+    auto launch_tc = [&](const WaveParams& Wl, int per_cta, unsigned ctas, cudaStream_t s_) {
+        WaveParams Wt = Wl;
+        Wt.claims_per_warp = per_cta;
+        Wt.tc_slots = tc_slots;
+        for (int t0 = 0, pass = 0; t0 < ctx->tc_tiles; t0 += tc::MAX_TILES, ++pass) {
+            Wt.tc_tile0 = t0;
+            Wt.tc_launch_tiles = std::min((int)tc::MAX_TILES, ctx->tc_tiles - t0);
+            Wt.tc_pass = pass;
+            wf_cull_tc<<<ctas, tc::THREADS, tc_smem, s_>>>(Wt);
+            if (pass) ctx->n_launches += 1;
+        }
+    };
 
     const int light_block = std::max(64, std::min(256, opt.light_block / 32 * 32));   // <= a cull CTA in every resource
     const int light_grid = d.sm_count * 8 * 256 / light_block;
@@ -534,11 +548,8 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                     }
                     if (tc_now) {
                         const unsigned tiles = (n_bound[l] + tc::TILE_M - 1) / tc::TILE_M;
-                        WaveParams Wt = W[l];
-                        Wt.claims_per_warp = tc_per_cta;
-                        Wt.tc_slots = tc_slots;
                         const unsigned ctas = tc_per_cta ? (tiles + (unsigned)tc_per_cta - 1u) / (unsigned)tc_per_cta : (unsigned)tc_grid;
-                        wf_cull_tc<<<std::max(1u, ctas), tc::THREADS, tc_smem, st[l]>>>(Wt);
+                        launch_tc(W[l], tc_per_cta, std::max(1u, ctas), st[l]);
                     } else {
                     // every work item of the launch must find a warp: items <= n / (32 R) + 2 resident_warps + 8 (wf_cull_body)
                     const unsigned items = n_bound[l] / (32u * kR) + 2u * (unsigned)resident_warps + 8u;
@@ -562,10 +573,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
                 } else {
                     W[l].trace = trace_slot("cull", l, iter_no[l]);
                     if (tc_now) {
-                        WaveParams Wt = W[l];
-                        Wt.claims_per_warp = 0;
-                        Wt.tc_slots = tc_slots;
-                        wf_cull_tc<<<tc_grid, tc::THREADS, tc_smem, st[l]>>>(Wt);
+                        launch_tc(W[l], 0, (unsigned)tc_grid, st[l]);
                     } else {
                         cull<<<cull_grid, cull_block, smem, st[l]>>>(W[l]);
                     }
@@ -1328,7 +1336,7 @@ int rt_set_scene_ex(rt_ctx* ctx, const rt_scene_desc* s, const rt_scene_ext* x) 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + std::max<size_t>(bytes, 16), 256); return o; };
     size_t o_cull_a = take((size_t)(n_cull + n_direct) * 16);
-    const int tc_tiles = (n_list + tc::TILE_N - 1) / tc::TILE_N <= tc::MAX_TILES ? (n_list + tc::TILE_N - 1) / tc::TILE_N : 0;
+    const int tc_tiles = (n_list + tc::TILE_N - 1) / tc::TILE_N;   // (over MAX_TILES: several wf_cull_tc launches per iteration)
     ctx->tc_tiles = tc_tiles;
     size_t o_cull_tc = take((size_t)tc_tiles * tc::B_TILE_BYTES), o_tc_row = take((size_t)tc_tiles * tc::TILE_N * 4);
     {   // rows: the listed leaves dealt out over the 32-row words largest first (a leaf's share of the candidates grows with its
@@ -1876,7 +1884,7 @@ int rt_cull_check(rt_ctx* ctx, int n, const float* origins, const float* dirs, c
     RT_CUDA(ctx, cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), d.stream));
     if (ctx->opt.cull_tc && ctx->tc_tiles > 0) {   // (whatever the list length: this is the diagnostic)
         // option cull_tc: check the tensor-core cull by running the PRODUCTION kernel over a queue of these rays
-        const size_t cap = align_up((size_t)n, 128);
+        const size_t cap = align_up(std::max<size_t>((size_t)n, 1u << 18), 128);   // (room for the warps' 64-slot pair reservations of every pass)
         if ((rc = ensure_lane(ctx, d, 0, cap))) return rc;
         DeviceBuffers::WaveLane& L = d.lanes[0];
         L.best_clean = false;
@@ -1906,10 +1914,16 @@ int rt_cull_check(rt_ctx* ctx, int n, const float* origins, const float* dirs, c
         RT_CUDA(ctx, cudaMemsetAsync(L.pairs, 0xDD, (size_t)W.pair_cap * sizeof(uint2), d.stream));
 #endif
         tc_check_fill<<<(n + 127) / 128, 128, 0, d.stream>>>(W, n, d_o, d_d, times ? d_tm : nullptr);
-        W.tc_slots = tc::slots_for(ctx->tc_tiles, 227 * 1024);
-        const size_t tc_smem = tc::smem_bytes(ctx->tc_tiles, W.tc_slots);
+        const int launch_tiles = std::min(ctx->tc_tiles, (int)tc::MAX_TILES);
+        W.tc_slots = tc::slots_for(launch_tiles, 227 * 1024);
+        const size_t tc_smem = tc::smem_bytes(launch_tiles, W.tc_slots);
         RT_CUDA(ctx, cudaFuncSetAttribute(wf_cull_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-        wf_cull_tc<<<d.sm_count, tc::THREADS, tc_smem, d.stream>>>(W);
+        for (int t0 = 0, pass = 0; t0 < ctx->tc_tiles; t0 += tc::MAX_TILES, ++pass) {
+            W.tc_tile0 = t0;
+            W.tc_launch_tiles = std::min((int)tc::MAX_TILES, ctx->tc_tiles - t0);
+            W.tc_pass = pass;
+            wf_cull_tc<<<d.sm_count, tc::THREADS, tc_smem, d.stream>>>(W);
+        }
         tc_check_mark<<<d.sm_count * 4, 256, 0, d.stream>>>(W, d_mask, words);
         tc_check_compare<<<(n + 127) / 128, 128, 0, d.stream>>>(W, n, tmin, tmax, d_mask, words, d_out);
         cudaError_t e = cudaStreamSynchronize(d.stream);

@@ -20,8 +20,9 @@
 // <= 7 u sum|terms| by csrc/tcprobe.cu, budgeted at 16 u) <= u (32 |o|^2 + 48 |c|^2 + 16 R2).  The ray's share
 // (80 u |o|^2) is taken off Q, the sphere's (96 u c.c + 24 u R2) is added to W on the host (build_cull_records).
 //
-// CTA = 16 epilogue warps + 1 MMA-issuing warp, one CTA per SM (the two accumulator buffers take all 512 TMEM
-// columns).  Sphere features of the whole list stay resident in shared memory (<= 4 tiles of 256 = 1024 spheres).
+// CTA = 16 epilogue warps + 1 MMA-issuing warp + 4 producer warps, one CTA per SM (the two accumulator buffers take all
+// 512 TMEM columns).  The sphere features of a launch stay resident in shared memory (<= 4 tiles of 256 = 1024 leaves);
+// a longer list is covered by several launches per iteration, each over its own 1024 leaves (WaveParams::tc_tile0).
 
 namespace tc {
 
@@ -202,7 +203,11 @@ __device__ __forceinline__ void tc_produce_ray(const WaveParams& W, const tc::Sm
     if (live) {
         float4* qc = cur ? W.queue[1] : W.queue[0];
         float4 a, b;
-        if (v >= n_g) {
+        if (v >= n_g && W.tc_pass != 0) {                      // a fresh entry whose ray an earlier pass generated and stored
+            const size_t e = (size_t)(p0 + (v - n_g));
+            a = qc[3 * e];
+            b = qc[3 * e + 1];
+        } else if (v >= n_g) {
             float4 c;
             float4* q = qc + 3 * (size_t)(p0 + (v - n_g));
             TC_CHECK(p0 + (v - n_g) < (unsigned)W.capacity, "fresh entry", p0 + (v - n_g), W.capacity);
@@ -261,7 +266,8 @@ __device__ __forceinline__ void tc_produce_ray(const WaveParams& W, const tc::Sm
 // unused are padded with PAIR_NULL (wf_refine skips those)
 struct TcEmit {
     unsigned pos, end;                 // warp-uniform: next free slot / end of the current reservation
-    unsigned next;                     // lane 0: start of the reservation requested ahead
+    unsigned next;                     // lane 0: start of the reservation requested ahead (if `ahead`)
+    bool ahead;                        // a warp that never emits reserves nothing
     unsigned pads;                     // padding slots written so far (WaveState::pad: wf_refine takes them off the candidate count)
 };
 __device__ __forceinline__ void tc_pad(const WaveParams& W, TcEmit& E, unsigned from, unsigned to, unsigned lane) {
@@ -277,6 +283,7 @@ __device__ __forceinline__ void tc_request(const WaveParams& W, TcEmit& E, unsig
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(&W.st->npairs, (unsigned)tc::PAIR_CHUNK);
     E.next = b;
+    E.ahead = true;
 }
 
 // FP32 confirm + emission of this warp's candidate list (ray-local index << 20 | feature row)
@@ -289,7 +296,7 @@ __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S,
         if (idx < ncand) {
             const uint32_t c = cand[idx];
             const unsigned rl = c >> 20, row = c & 0xfffffu;
-            TC_CHECK(rl < 128u && row < (unsigned)W.base.sc.tc_tiles * 256u, "candidate", c, ncand);
+            TC_CHECK(rl < 128u && row < (unsigned)W.tc_launch_tiles * 256u, "candidate", c, ncand);
             const float4 r0 = S.ray((unsigned)slot)[2 * rl], r1 = S.ray((unsigned)slot)[2 * rl + 1];
             const float4 R = S.rec[row];
             const int kk = S.row_k[row];
@@ -319,6 +326,7 @@ __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S,
         if (total == 0) continue;
         if (E.pos + total > E.end) {   // move to the reservation requested ahead (the rest of the old one becomes padding), request another
             tc_pad(W, E, E.pos, E.end, lane);
+            if (!E.ahead) tc_request(W, E, lane);             // the warp's first pairs of this launch: the one atomic it waits for
             const unsigned b = __shfl_sync(0xffffffffu, E.next, 0);
             E.pos = min(b, W.pair_cap);
             E.end = min(b + (unsigned)tc::PAIR_CHUNK, W.pair_cap);
@@ -352,11 +360,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
     if (n == 0) return;
     const unsigned long long gen_base = W.st->gen_base[W.cur];
     const unsigned p0 = (unsigned)W.capacity - n_p;
-    const int tiles = P.sc.tc_tiles;
+    const int tiles = W.tc_launch_tiles;
     const unsigned slots = (unsigned)W.tc_slots;
     const tc::Smem S = tc::carve(tc_smem, tiles, (int)slots);
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
+    if (blockIdx.x == 0 && tid == 0 && W.tc_pass == 0) atomicAdd(&P.counters[DC_RAYS], (unsigned long long)n);
 
     // this CTA's ray tiles: a contiguous run
     const unsigned total_tiles = (n + tc::TILE_M - 1) / tc::TILE_M;
@@ -382,12 +390,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
     }
     if (tid < tc::EW) S.cand_n[tid] = 0u;
     {   // the sphere features of the whole list (already in the canonical layout) and their FP32 records: global (L2) -> shared
-        const float4* src = reinterpret_cast<const float4*>(P.sc.cull_tc);
+        const float4* src = reinterpret_cast<const float4*>(P.sc.cull_tc) + (size_t)W.tc_tile0 * (tc::B_TILE_BYTES / 16);
         float4* dst = reinterpret_cast<float4*>(S.B);
         const int n4 = tiles * (tc::B_TILE_BYTES / 16);
         for (int i = (int)tid; i < n4; i += tc::THREADS) dst[i] = __ldg(&src[i]);
         for (int i = (int)tid; i < tiles * tc::TILE_N; i += tc::THREADS) {
-            const int k = __ldg(&P.sc.tc_row_k[i]);
+            const int k = __ldg(&P.sc.tc_row_k[(size_t)W.tc_tile0 * tc::TILE_N + i]);
             S.row_k[i] = k;
             S.rec[i] = k >= 0 ? __ldg(&P.sc.cull_a[k]) : make_float4(0.f, 0.f, 0.f, -CUDART_INF_F);
         }
@@ -481,8 +489,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
         const uint32_t t_lane = ((warp & 3u) * 32u) << 16;
         uint32_t* cand = S.cand + warp * tc::CAND_CAP;
         unsigned* cand_n = S.cand_n + warp;
-        TcEmit E{0u, 0u, 0u, 0u};
-        tc_request(W, E, lane);
+        TcEmit E{0u, 0u, 0u, false, 0u};
         unsigned g = 0;
         for (unsigned it = 0; it < n_it; ++it) {
             const unsigned s = it % slots, a_ph = (it / slots) & 1u, tile = first + it;
@@ -536,31 +543,21 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     unsigned mm = h ? m1 : m0;
-#ifdef RT_TC_BALLOT_PUSH
-                    while (__any_sync(0xffffffffu, mm != 0u)) {
-                        const bool has = mm != 0u;
-                        const unsigned bal = __ballot_sync(0xffffffffu, has);
-                        const unsigned base = *cand_n;
-                        if (has) {
-                            const int bit = 31 - __clz((int)mm);
-                            mm &= ~(1u << bit);
-                            const unsigned pos = base + __popc(bal & ((1u << lane) - 1u));
-                            if (pos < (unsigned)tc::CAND_CAP) cand[pos] = (rl << 20) | (row0 + (unsigned)h * 32u + (unsigned)(31 - bit));
-                            else W.best_key[wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity)] = BEST_KEY_OVERFLOW;
-                        }
-                        __syncwarp();
-                        if (lane == 0) *cand_n = base + __popc(bal);
-                        __syncwarp();
-                    }
-#else
                     while (mm != 0u) {                          // lanes with candidates only (divergent; a shared-memory atomic hands out slots)
                         const int bit = 31 - __clz((int)mm);
                         mm &= ~(1u << bit);
                         const unsigned pos = atomicAdd(cand_n, 1u);
                         if (pos < (unsigned)tc::CAND_CAP) cand[pos] = (rl << 20) | (row0 + (unsigned)h * 32u + (unsigned)(31 - bit));
-                        else W.best_key[wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity)] = BEST_KEY_OVERFLOW;   // list full: exact re-intersection downstream
+                        else {                                  // list full (dozens of leaves along this warp's rays): straight to the pair
+                            const int kk = S.row_k[row0 + (unsigned)h * 32u + (unsigned)(31 - bit)];   // buffer, unconfirmed (the refine sorts it out)
+                            const unsigned entry = wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity);
+                            const unsigned w = kk >= 0 ? atomicAdd(&W.st->npairs, 1u) : 0u;
+                            if (kk >= 0) {
+                                if (w < W.pair_cap) W.pairs[w] = make_uint2(entry, (unsigned)kk);
+                                else W.best_key[entry] = BEST_KEY_OVERFLOW;   // pair buffer full too: wf_shade re-intersects this entry exactly
+                            }
+                        }
                     }
-#endif
                 }
                 TC_ACC(2, t2);
             }
@@ -584,7 +581,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
             TC_ACC(3, t3);
         }
         tc_pad(W, E, E.pos, E.end, lane);
-        {                              // the reservation requested ahead and never used
+        if (E.ahead) {                 // the reservation requested ahead and never used
             const unsigned b = __shfl_sync(0xffffffffu, E.next, 0);
             tc_pad(W, E, min(b, W.pair_cap), min(b + (unsigned)tc::PAIR_CHUNK, W.pair_cap), lane);
             if (lane == 0 && E.pads) atomicAdd(&W.st->pad, E.pads);

@@ -495,6 +495,9 @@ struct WaveParams {
     unsigned iter;                 // 1-based number of this iteration within the render (LaneStatus::seq after its wf_shade)
     TraceRec* trace;               // this launch's timeline record, or null
     int tc_slots;                  // wf_cull_tc: ray-tile buffers in shared memory (2 .. 4)
+    int tc_tile0, tc_launch_tiles; // wf_cull_tc: this launch tests feature tiles [tc_tile0, tc_tile0 + tc_launch_tiles) of the list (<= 4: they
+    int tc_pass;                   //   stay resident in shared memory); a longer list takes several launches ("passes") per iteration, and only
+                                   //   pass 0 generates the fresh entries' rays and counts the rays
 };
 __device__ __forceinline__ void publish_status(const WaveParams& W, unsigned n_next, unsigned n_fresh, unsigned exhausted, unsigned mode,
                                                unsigned seq) {

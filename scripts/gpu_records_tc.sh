@@ -15,3 +15,5 @@ run r02_bench_c4_tc --workload c4 --steps 10 --warmup 3 --no-cpu-baseline
 run r02_bench_c5_1k_tc --workload c5-1k --steps 5 --warmup 3 --no-cpu-baseline
 run r02_bench_c5_100_tc --workload c5-100 --steps 10 --warmup 3 --no-cpu-baseline
 run r02_bench_cornell_tc --workload cornell --steps 10 --warmup 3 --no-cpu-baseline
+run r02_bench_c5_10k_tc --workload c5-10k --steps 3 --warmup 3 --no-cpu-baseline
+run r02_bench_c5_100k_tc --workload c5-100k --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1

@@ -617,3 +617,33 @@ def test_tensor_core_cull_short_queues_and_partial_tiles(renderer, scene_name):
             assert res[0][2] == res[1][2]
     finally:
         renderer.set_option("cull_tc", 1)
+
+
+def test_tensor_core_cull_long_lists_take_several_passes(renderer):
+    """Over 1024 leaves the tensor-core cull covers the list in several launches per iteration (1024 leaves' features resident
+    in shared memory each): same contract, same paths as the FP32 loop."""
+    import bench
+    nx, ny = 320, 180
+    flat, cam_type, cam = bench.build_scene("sweep:3000", nx, ny, 5)
+    renderer.set_scene(flat)
+    renderer.set_camera(cam_type, cam)
+    rng = np.random.default_rng(8)
+    n = 20_000
+    side = math.sqrt(flat.n_spheres) / 2
+    o = rng.uniform(-side, side, size=(n, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(0, 3, n)                       # in and just above the layer of spheres: dozens of leaves along many rays
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    pix = rng.integers(0, nx * ny, 100_000).astype(np.int32)
+    smp = rng.integers(0, 16, 100_000).astype(np.int32)
+    res, out = {}, {}
+    try:
+        for mode in (0, 1):
+            renderer.set_option("cull_tc", mode)
+            res[mode] = renderer.cull_check(o, d, None, 0.001, FMAX)
+            assert res[mode][0] == 0
+            out[mode] = renderer.trace_paths(nx, ny, pix, smp, 50, seed=9)
+    finally:
+        renderer.set_option("cull_tc", 1)
+    assert res[0][2] == res[1][2] and res[1][1] <= res[0][1] * (1 + 1e-3) + 2
+    for a, b in zip(out[0][:3], out[1][:3]):
+        assert np.array_equal(a, b)
