@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
         unsigned g = 0;
         for (unsigned it = 0; it < n_it; ++it) {
             const unsigned s = it % slots, a_ph = (it / slots) & 1u, tile = first + it;
+            bool lost = false;
             for (int j = 0; j < tiles; ++j, ++g) {
                 const unsigned b = g & 1u;
                 TC_T(t0);
@@ -548,19 +549,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
                         mm &= ~(1u << bit);
                         const unsigned pos = atomicAdd(cand_n, 1u);
                         if (pos < (unsigned)tc::CAND_CAP) cand[pos] = (rl << 20) | (row0 + (unsigned)h * 32u + (unsigned)(31 - bit));
-                        else {                                  // list full (dozens of leaves along this warp's rays): straight to the pair
-                            const int kk = S.row_k[row0 + (unsigned)h * 32u + (unsigned)(31 - bit)];   // buffer, unconfirmed (the refine sorts it out)
-                            const unsigned entry = wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity);
-                            const unsigned w = kk >= 0 ? atomicAdd(&W.st->npairs, 1u) : 0u;
-                            if (kk >= 0) {
-                                if (w < W.pair_cap) W.pairs[w] = make_uint2(entry, (unsigned)kk);
-                                else W.best_key[entry] = BEST_KEY_OVERFLOW;   // pair buffer full too: wf_shade re-intersects this entry exactly
-                            }
-                        }
+                        else lost = true;                       // list full (dozens of leaves along this warp's rays): see below
                     }
                 }
                 TC_ACC(2, t2);
             }
+            // a ray that lost a candidate to a full list is re-intersected exactly downstream (wf_shade, BEST_KEY_OVERFLOW): rare —
+            // it takes more than 256 candidates among 32 rays x 256 leaves — and never wrong
+            if (lost) W.best_key[wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity)] = BEST_KEY_OVERFLOW;
             __syncwarp();
             TC_T(t3);
             const unsigned ncand = min(*cand_n, (unsigned)tc::CAND_CAP);
