@@ -386,7 +386,10 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
     // tensor-core cull (rt_cull_tc.cuh): one 544-thread CTA per SM, the whole sphere-feature list resident in shared memory
     // (below ~160 leaves most of a 256-column feature tile is padding and the FP32 loop wins: C5-100 39.7 vs 48.0 ms, Cornell box
     // 47.8 vs 64.0 ms; cull_tc = 3 forces the tensor-core kernel whatever the list length)
-    const bool use_tc = opt.cull_tc != 0 && ctx->tc_tiles > 0 && !bvh && (ctx->n_list >= tc::MIN_LEAVES || opt.cull_tc == 3);
+    // Scenes with generic leaves (rectangles, boxes, triangles, media: rt_set_scene_ex) stay on the FP32 loop too: their bounding
+    // spheres are loose, a ray's line meets dozens of them, the per-warp candidate lists overflow and the overflow path (exact
+    // re-intersection of the ray in wf_shade) takes over: make-final 1.47 s on the FP32 loop, 2.96 s on the tensor cores.
+    const bool use_tc = opt.cull_tc != 0 && ctx->tc_tiles > 0 && !bvh && ((ctx->n_list >= tc::MIN_LEAVES && !ctx->generic) || opt.cull_tc == 3);
     const int tc_launch_tiles = std::min(ctx->tc_tiles, (int)tc::MAX_TILES);
     const int tc_slots = tc::slots_for(tc_launch_tiles, 227 * 1024);
     const size_t tc_smem = tc::smem_bytes(tc_launch_tiles, tc_slots);

@@ -1,9 +1,7 @@
-# final round-2 evidence with the tensor-core cull: tests, smoke, records, launch list, ncu captures, timeline
+# final round-2 evidence with the tensor-core cull: launch list, ncu captures of wf_cull_tc, timeline, make-final record
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-bash scripts/gpu_records_tc.sh 2>&1 | tail -8
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-strong-c3 --e2e-steps 1"
+$CMD > gpurun_out/plain.log 2> gpurun_out/plain.err || { echo "plain run failed"; tail -5 gpurun_out/plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_ncu_launches_c2_tc.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 cuobjdump -xelf all raytrace_clj_b200/libraytrace_b200.so > /dev/null 2>&1; CUBIN=$(ls *.cubin | head -1)
 for skip in 0 3; do
@@ -16,4 +14,11 @@ for skip in 0 3; do
 done
 rm -f *.cubin
 timeout 100 python scripts/tc_trace.py gpurun_out/r02_timeline_c2_tc_two_lanes.txt 2 1
-head -12 gpurun_out/r02_ncu_wf_cull_tc_s3_summary.txt
+python bench.py --workload final --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_final_tc.json 2> gpurun_out/final.err; tail -2 gpurun_out/final.err
+python - <<P
+import json
+d=json.loads([l for l in open("gpurun_out/r02_bench_final_tc.json") if l.startswith("{")][-1])
+print("final", d["ms_per_step"], d["value"], d["roofline"]["frac"])
+P
+grep -E "duration|issue slots|ALU pipe|executed warp" gpurun_out/r02_ncu_wf_cull_tc_s3_summary.txt
+head -12 gpurun_out/r02_ncu_wf_cull_tc_s3_by_line.txt
