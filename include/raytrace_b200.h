@@ -219,7 +219,7 @@ int rt_set_accel(rt_ctx* ctx, int accel);
  * "wave_lanes", "wave_capacity", "cull_claims", "cull_ctas_per_sm", "light_block", "tail_entries", "tile_records",
  * "direct_spheres", "common_origin", "reduce" (0 peer loads in the resolve kernel, 1 ncclReduce), "rows" (multi-device
  * partition: 0 sample slices, 1 interleaved rows), "cull_tc" (1 = the brute-force cull runs on the tensor cores when the
- * list has 160 leaves or more (default), 0 = FP32 pipe only, 2 = FP32 for a lane's first all-camera-ray iteration, 3 = tensor
+ * list has 160 leaves or more, all spheres (default), 0 = FP32 pipe only, 2 = FP32 for a lane's first all-camera-ray iteration, 3 = tensor
  * cores whatever the list length),
  * "tc_tiles_per_cta", "wave_depth", "tail_rays", "tail_block", "cull_shape", "tail_ctas_per_sm", "mega_regcap".
  * Unknown name -> RT_ERR_ARG.                                                                                     */

@@ -286,6 +286,56 @@ __device__ __forceinline__ void tc_request(const WaveParams& W, TcEmit& E, unsig
     E.ahead = true;
 }
 
+// warp-converged: the lanes with `emit` append (entry, k) to the warp's pair reservation
+__device__ __forceinline__ void tc_emit(const WaveParams& W, TcEmit& E, bool emit, unsigned entry, unsigned k, unsigned lane) {
+    const unsigned bal = __ballot_sync(0xffffffffu, emit);
+    const unsigned total = __popc(bal);
+    if (total == 0) return;
+    if (E.pos + total > E.end) {   // move to the reservation requested ahead (the rest of the old one becomes padding), request another
+        tc_pad(W, E, E.pos, E.end, lane);
+        if (!E.ahead) tc_request(W, E, lane);             // the warp's first pairs of this launch: the one atomic it waits for
+        const unsigned b = __shfl_sync(0xffffffffu, E.next, 0);
+        E.pos = min(b, W.pair_cap);
+        E.end = min(b + (unsigned)tc::PAIR_CHUNK, W.pair_cap);
+        tc_request(W, E, lane);
+    }
+    if (emit) {
+        const unsigned w = E.pos + __popc(bal & ((1u << lane) - 1u));
+        TC_CHECK(entry < (unsigned)W.capacity && k < (unsigned)W.base.sc.n_list, "pair", entry, k);
+        if (w < E.end) W.pairs[w] = make_uint2(entry, k);
+        else W.best_key[entry] = BEST_KEY_OVERFLOW;       // pair buffer full: wf_shade re-intersects this entry exactly
+    }
+    E.pos = min(E.pos + total, E.end);
+}
+
+// The FP32 cull's own test of one (ray, feature row): Culler::key_bits, general form, on the constants the producers left
+__device__ __forceinline__ bool tc_confirm(const tc::Smem& S, float4 r0, float4 r1, unsigned row, int& kk) {
+    const float4 R = S.rec[row];
+    kk = S.row_k[row];
+    const float cc = fmaf(R.x, r0.x, fmaf(R.y, r0.y, fmaf(R.z, r0.z, r0.w)));
+    const float s = fmaf(R.x, r1.x, fmaf(R.y, r1.y, fmaf(R.z, r1.z, R.w)));
+    const float key = fmaf(-cc, fabsf(cc), fmaf(cc, cc, s - r1.w));
+    return (__float_as_uint(key) >> 31) == 0u && kk >= 0;     // (a padding row never gets here: W = DEAD)
+}
+
+// A warp whose candidate list overflowed (dozens of leaves along its rays' lines: loose bounding spheres, a dense layer)
+// drops the list and redoes its share of the tile — 32 rays x its 64 columns of every group — with the FP32 test itself:
+// as slow as the FP32 loop for that warp and tile, never a lost pair, no exact re-intersection downstream.
+__device__ __noinline__ void tc_redo_fp32(const WaveParams& W, const tc::Smem& S, int slot, unsigned tile, unsigned n, unsigned n_g, unsigned n_p,
+                                          int tiles, unsigned cb, unsigned rl) {
+    if (tile * tc::TILE_M + rl >= n) return;
+    const float4 r0 = S.ray((unsigned)slot)[2 * rl], r1 = S.ray((unsigned)slot)[2 * rl + 1];
+    const unsigned entry = wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity);
+    for (int j = 0; j < tiles; ++j)
+        for (unsigned q = 0; q < 64u; ++q) {
+            int kk;
+            if (!tc_confirm(S, r0, r1, (unsigned)j * tc::TILE_N + cb * 64u + q, kk)) continue;
+            const unsigned w = atomicAdd(&W.st->npairs, 1u);  // (single slots, outside the warp's reservation: nothing to pad; a rare path)
+            if (w < W.pair_cap) W.pairs[w] = make_uint2(entry, (unsigned)kk);
+            else W.best_key[entry] = BEST_KEY_OVERFLOW;       // pair buffer full: wf_shade re-intersects this entry exactly
+        }
+}
+
 // FP32 confirm + emission of this warp's candidate list (ray-local index << 20 | feature row)
 __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S, int slot, unsigned tile, unsigned n_g, unsigned n_p,
                                          const uint32_t* cand, unsigned ncand, TcEmit& E, unsigned lane) {
@@ -297,49 +347,12 @@ __device__ __forceinline__ void tc_drain(const WaveParams& W, const tc::Smem& S,
             const uint32_t c = cand[idx];
             const unsigned rl = c >> 20, row = c & 0xfffffu;
             TC_CHECK(rl < 128u && row < (unsigned)W.tc_launch_tiles * 256u, "candidate", c, ncand);
-            const float4 r0 = S.ray((unsigned)slot)[2 * rl], r1 = S.ray((unsigned)slot)[2 * rl + 1];
-            const float4 R = S.rec[row];
-            const int kk = S.row_k[row];
-            const float cc = fmaf(R.x, r0.x, fmaf(R.y, r0.y, fmaf(R.z, r0.z, r0.w)));
-            const float s = fmaf(R.x, r1.x, fmaf(R.y, r1.y, fmaf(R.z, r1.z, R.w)));
-            const float key = fmaf(-cc, fabsf(cc), fmaf(cc, cc, s - r1.w));       // Culler::key_bits, general form
-            emit = (__float_as_uint(key) >> 31) == 0u && kk >= 0;                 // (a padding row never gets here: W = DEAD)
+            int kk;
+            emit = tc_confirm(S, S.ray((unsigned)slot)[2 * rl], S.ray((unsigned)slot)[2 * rl + 1], row, kk);
             k = (unsigned)kk;
             entry = wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity);
-#ifdef RT_TC_CHECK
-            if (kk >= 0) {   // the candidate must be a line-sphere intersection of THIS entry's ray and THIS leaf's bounding sphere (with slack)
-                const float4* qc = W.cur ? W.queue[1] : W.queue[0];
-                const float4 qa = qc[3 * (size_t)entry], qb = qc[3 * (size_t)entry + 1];
-                const float4 Rg = W.base.sc.cull_a[kk];
-                const double cx = -(double)Rg.x, cy = -(double)Rg.y, cz = -(double)Rg.z, R2 = (double)Rg.w + cx * cx + cy * cy + cz * cz;
-                const double dn = sqrt((double)qb.x * qb.x + (double)qb.y * qb.y + (double)qb.z * qb.z);
-                const double ux = qb.x / dn, uy = qb.y / dn, uz = qb.z / dn, ox = qa.x - cx, oy = qa.y - cy, oz = qa.z - cz;
-                const double bb = ux * ox + uy * oy + uz * oz, disc = bb * bb - (ox * ox + oy * oy + oz * oz) + R2;
-                if (disc < -1e-3 * (R2 + ox * ox + oy * oy + oz * oz))
-                    printf("bogus candidate: tile %u rl %u row %u k %d entry %u disc %g (R2 %g |oc|2 %g) slot %d idx %u of %u block %u warp %u\n", tile, rl, row, kk, entry, disc, R2,
-                           ox * ox + oy * oy + oz * oz, slot, idx, ncand, blockIdx.x, threadIdx.x >> 5);
-            }
-#endif
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, emit);
-        const unsigned total = __popc(bal);
-        if (total == 0) continue;
-        if (E.pos + total > E.end) {   // move to the reservation requested ahead (the rest of the old one becomes padding), request another
-            tc_pad(W, E, E.pos, E.end, lane);
-            if (!E.ahead) tc_request(W, E, lane);             // the warp's first pairs of this launch: the one atomic it waits for
-            const unsigned b = __shfl_sync(0xffffffffu, E.next, 0);
-            E.pos = min(b, W.pair_cap);
-            E.end = min(b + (unsigned)tc::PAIR_CHUNK, W.pair_cap);
-            tc_request(W, E, lane);
-        }
-        if (emit) {
-            const unsigned w = E.pos + __popc(bal & ((1u << lane) - 1u));
-            TC_CHECK(entry < (unsigned)W.capacity && k < (unsigned)W.base.sc.n_list, "pair", entry, k);
-            TC_CHECK(w >= E.end || w < W.pair_cap, "pair slot", w, W.pair_cap);
-            if (w < E.end) W.pairs[w] = make_uint2(entry, k);
-            else W.best_key[entry] = BEST_KEY_OVERFLOW;       // pair buffer full: wf_shade re-intersects this entry exactly
-        }
-        E.pos = min(E.pos + total, E.end);
+        tc_emit(W, E, emit, entry, k, lane);
     }
 }
 
@@ -493,7 +506,6 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
         unsigned g = 0;
         for (unsigned it = 0; it < n_it; ++it) {
             const unsigned s = it % slots, a_ph = (it / slots) & 1u, tile = first + it;
-            bool lost = false;
             for (int j = 0; j < tiles; ++j, ++g) {
                 const unsigned b = g & 1u;
                 TC_T(t0);
@@ -548,21 +560,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1) wf_cull_tc(const __grid_consta
                         const int bit = 31 - __clz((int)mm);
                         mm &= ~(1u << bit);
                         const unsigned pos = atomicAdd(cand_n, 1u);
-                        if (pos < (unsigned)tc::CAND_CAP) cand[pos] = (rl << 20) | (row0 + (unsigned)h * 32u + (unsigned)(31 - bit));
-                        else lost = true;                       // list full (dozens of leaves along this warp's rays): see below
+                        if (pos < (unsigned)tc::CAND_CAP) cand[pos] = (rl << 20) | (row0 + (unsigned)h * 32u + (unsigned)(31 - bit));   // (a full list: see below)
                     }
                 }
                 TC_ACC(2, t2);
             }
-            // a ray that lost a candidate to a full list is re-intersected exactly downstream (wf_shade, BEST_KEY_OVERFLOW): rare —
-            // it takes more than 256 candidates among 32 rays x 256 leaves — and never wrong
-            if (lost) W.best_key[wf_entry(tile * tc::TILE_M + rl, n_g, n_p, (unsigned)W.capacity)] = BEST_KEY_OVERFLOW;
-            __syncwarp();
             TC_T(t3);
-            const unsigned ncand = min(*cand_n, (unsigned)tc::CAND_CAP);
+            __syncwarp();
+            const unsigned raw = *cand_n;                       // every push counted, also those that found the list full
+            const bool overflowed = raw > (unsigned)tc::CAND_CAP;   // then: drop the list, redo this warp's share of the tile in FP32
+            const unsigned ncand = overflowed ? 0u : raw;
+            if (overflowed) {
+                tc::mbar_wait(&S.a_ready[s], a_ph);
+                tc_redo_fp32(W, S, (int)s, tile, n, n_g, n_p, tiles, cb, rl);
+                __syncwarp();
+            }
 #ifdef RT_TC_CHECK
             if (lane == 0 && ncand > 48u && n < 300u)
-                printf("big candidate list: block %u warp %u tile %u it %u ncand %u raw %u first %x %x %x %x last %x\n", blockIdx.x, warp, tile, it, ncand, *cand_n, cand[0], cand[1], cand[2], cand[3], cand[ncand - 1]);
+                printf("big candidate list: block %u warp %u tile %u it %u ncand %u raw %u first %x %x %x %x last %x\n", blockIdx.x, warp, tile, it, ncand, raw, cand[0], cand[1], cand[2], cand[3], cand[ncand - 1]);
 #endif
             if (ncand) {
                 tc::mbar_wait(&S.a_ready[s], a_ph);             // (long complete) the producers' writes of ray[s], acquired directly
