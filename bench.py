@@ -289,7 +289,7 @@ def main():
     r.set_option("cull_tc", cull_tc)
     # the tensor-core cull keeps 1024 leaves' features in shared memory per launch; longer lists take several launches per iteration
     # (and lists below 160 leaves, where a 256-column feature tile would be mostly padding; up to 8 "direct" spheres are not listed)
-    tc_active = bool(cull_tc) and accel_id == 0 and args.variant == 1 and 160 + 8 <= flat.n_spheres and not flat.has_ext
+    tc_active = bool(cull_tc) and accel_id == 0 and args.variant == 1 and 160 + 8 <= flat.n_spheres and not flat.generic
     info = r.device_info()
 
     d_sum = torch.zeros(ny, nx, 3, device=dev, dtype=torch.float32)

@@ -92,6 +92,18 @@ class FlatScene:
         return self.prim_type is not None or self.tie_rule != RT_TIE_HITLIST or self.perlin_vectors is not None \
             or self.image_wh is not None
 
+    @property
+    def generic(self):
+        """Mirror of the library's `generic` flag (rt_set_scene_ex): some leaf is not a plain sphere, or a wrapper, an extended
+        texture (Perlin / image / flip) or an Isotropic material is in use — such scenes run the GEN kernels and the FP32 cull."""
+        g = self.perlin_vectors is not None
+        if self.prim_type is not None:
+            g = g or bool((np.asarray(self.prim_type)[: self.n_spheres] != RT_PRIM_SPHERE).any())
+        if self.prim_xform is not None:
+            g = g or bool((np.asarray(self.prim_xform) >= 0).any())
+        g = g or bool((np.asarray(self.tex_type) > RT_TEX_CHECKERBOARD).any()) or bool((np.asarray(self.mat_type) == RT_MAT_ISOTROPIC).any())
+        return g
+
     def copy(self):
         return FlatScene(**{k: (getattr(self, k).copy() if isinstance(getattr(self, k), np.ndarray) else getattr(self, k))
                             for k in self.__dataclass_fields__})
