@@ -83,8 +83,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 #define RT_TC_NBLK 1
 #endif
 constexpr int NBLK = RT_TC_NBLK;               // column blocks of an accumulator buffer that advance on their own (own full / empty barriers,
-constexpr int BLOCK_N = TILE_N / NBLK;         //   own MMAs of N = BLOCK_N): a block that met many candidates does not hold the others back, and
-constexpr int BLOCK_WARPS = EW / NBLK;         //   the blocks drift out of phase, so TMEM loads / funnel shifts / candidate handling overlap
+constexpr int BLOCK_N = TILE_N / NBLK;         //   own MMAs of N = BLOCK_N).  Kept as a compile-time experiment: with 4 blocks the epilogue's load
+constexpr int BLOCK_WARPS = EW / NBLK;         //   phase drops from 1250 to 800 cycles per tile (no collisions), but a tcgen05.mma costs ~128 cycles
+                                               //   whatever N <= 256, so the tensor pipe becomes the bottleneck (C2: 7.56 ms; 2 blocks 6.05; 1 block 5.76)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);   // f32 += tf32 x tf32, both K-major
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
