@@ -199,7 +199,22 @@ __global__ void __launch_bounds__(WARPS * 32 + 32) rate_probe(int mode, int iter
                     uint32_t v[32];
                     TMEM_LD32(tb + lane_base + (uint32_t)(cbase + c0), v);
                     tmem_wait_ld();
-                    if (mode == 1) {
+                    if (mode == 5) {                                  // half of the values by funnel shift (ALU pipe), half by FSET + FFMA (FMA pipe?)
+                        unsigned w = 0;
+                        float af = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) w = __funnelshift_l(v[j], w, 1);
+#pragma unroll
+                        for (int j = 16; j < 32; ++j) af = fmaf(af, 2.0f, !(__uint_as_float(v[j]) < 0.0f) ? 1.0f : 0.0f);
+                        acc ^= (w << 16) | (unsigned)__float2uint_rz(af);
+                    } else if (mode == 6) {                           // all values by FSET + FFMA
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) a0 = fmaf(a0, 2.0f, !(__uint_as_float(v[j]) < 0.0f) ? 1.0f : 0.0f);
+#pragma unroll
+                        for (int j = 16; j < 32; ++j) a1 = fmaf(a1, 2.0f, !(__uint_as_float(v[j]) < 0.0f) ? 1.0f : 0.0f);
+                        acc ^= ((unsigned)__float2uint_rz(a0) << 16) | (unsigned)__float2uint_rz(a1);
+                    } else if (mode == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) acc ^= v[j] ^ v[j + 1] ^ v[j + 2] ^ v[j + 3];   // LOP3s: ~0.4 per value
                     } else {
@@ -309,6 +324,8 @@ int main() {
     run_rate<16>("load + SHF per value", 2, 256);
     run_rate<8>("two loads + 2 FFMA + SHF per pair", 3, 256);
     run_rate<16>("two loads + 2 FFMA + SHF per pair", 3, 256);
+    run_rate<16>("load + 16 SHF + 16 (FSET, FFMA) per 32 values", 5, 256);
+    run_rate<16>("load + (FSET, FFMA) per value", 6, 256);
     run_rate<8>("load + SHF per value, MMAs running", 4, 256);
     run_rate<16>("load + SHF per value, MMAs running", 4, 256);
     printf("status: %s\n", cudaGetErrorString(cudaGetLastError()));
