@@ -498,6 +498,7 @@ struct WaveParams {
     int tc_tile0, tc_launch_tiles; // wf_cull_tc: this launch tests feature tiles [tc_tile0, tc_tile0 + tc_launch_tiles) of the list (<= 4: they
     int tc_pass;                   //   stay resident in shared memory); a longer list takes several launches ("passes") per iteration, and only
                                    //   pass 0 generates the fresh entries' rays and counts the rays
+    unsigned tail_solo;            // wf_tail: a slice that has shrunk to this many paths or fewer is finished one WARP per path (wf_solo_paths)
 };
 __device__ __forceinline__ void publish_status(const WaveParams& W, unsigned n_next, unsigned n_fresh, unsigned exhausted, unsigned mode,
                                                unsigned seq) {
@@ -1199,6 +1200,109 @@ __global__ void __launch_bounds__(128) trace_bvh_kernel(const __grid_constant__ 
     }
 }
 
+// The thin end of a tail slice: a handful of paths with up to max_depth bounces still to go.  Staged, every bounce of
+// those few paths costs the CTA four barriers and a chain of dependent global loads (pairs -> ray -> sphere ->
+// closest-hit words -> candidates -> queue record: ~9 us per bounce whatever the population); here every WARP takes
+// one path at a time and keeps it in registers until it ends.  All 32 lanes hold the same ray; the listed leaves are
+// dealt over the lanes (lane, lane + 32, ...: the same conservative FP32 test as the cull, then the exact FP64 test for what
+// passed, with the warp converged), the direct spheres likewise, the closest hit is the minimum over the lanes of (t bits, tie key) — the merge
+// rule of wf_refine + wf_tiebreak + wf_shade — and the shading runs on every lane with identical inputs (no divergence,
+// same Philox block); lane 0 owns the side effects.  Same arithmetic as the staged path: results equal bit for bit.
+template <bool GEN>
+__device__ __forceinline__ void wf_solo_paths(const WaveParams& W, const DevScene* scp, const float4* qc, unsigned n, unsigned* claim,
+                                              const float4* s_cull, unsigned* s_ctr) {
+    const RenderParams& P = W.base;
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned i = 0;
+        if (lane == 0) i = atomicAdd(claim, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) return;
+        float4 a = qc[3 * (size_t)i], b = qc[3 * (size_t)i + 1], c = qc[3 * (size_t)i + 2];
+        const uint32_t slot = __float_as_uint(b.w);
+        const uint32_t pix = rng_pixel(P, slot);
+        unsigned n_rays = 0, n_cand = 0, n_direct = 0;
+        int reason = TERM_NONE;
+        for (;;) {
+            const uint32_t sd = __float_as_uint(c.w), smp = sd >> 8;
+            const int depth = (int)(sd & 255u);
+            const uint32_t bounce = (uint32_t)(P.max_depth - depth + 1);
+            ++n_rays;
+            Culler<1, 32, false> K;
+            K.set_ray(0, a.x, a.y, a.z, b.x, b.y, b.z);
+            unsigned long long bt = BEST_T_INIT, bkey = BEST_KEY_MISS;
+            // 1024 leaves at a time: the cull key of this lane's 32 of them first (bit j = leaf base + 32 j + lane passed; a direct
+            // sphere always does), then the exact tests with the warp converged — as many rounds as the busiest lane has
+            // candidates (1 or 2), not one round per leaf position that saw a survivor
+            for (int base = 0; base < P.sc.n; base += 1024) {
+                unsigned mask = 0u;
+                const int jn = min(32, (P.sc.n - base + 31) >> 5);
+#pragma unroll 4
+                for (int j = 0; j < jn; ++j) {
+                    const int s = base + 32 * j + (int)lane;
+                    bool pass = s < P.sc.n;                       // beyond the list: a sphere that bypasses the cull
+                    if (s < P.sc.n_list) {
+                        const float4 S = P.preloaded ? s_cull[s] : __ldg(&P.sc.cull_a[s]);
+                        pass = (int)K.key_bits(S, 0) >= 0;        // sign bit clear = survived the cull
+                    }
+                    mask |= (pass ? 1u : 0u) << j;
+                }
+                while (__any_sync(0xffffffffu, mask != 0u)) {
+                    if (mask) {
+                        const int s = base + 32 * (__ffs(mask) - 1) + (int)lane;
+                        mask &= mask - 1u;
+                        if (s < P.sc.n_list) ++n_cand; else ++n_direct;
+                        const double t = refine_leaf<GEN>(scp, s, a.x, a.y, a.z, b.x, b.y, b.z, a.w, 0.001, (double)FLT_MAX, true, P.key, pix,
+                                                          smp, bounce);   // core.clj:25 t-range
+                        const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
+                        const unsigned long long kk = (((unsigned long long)__ldg(&P.sc.tie_hi[s])) << 32) | (unsigned)s;
+                        if (t < CUDART_INF && (tb < bt || (tb == bt && kk < bkey))) { bt = tb; bkey = kk; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int dlt = 16; dlt; dlt >>= 1) {           // t > 0: the order of the bit patterns is the order of the values
+                const unsigned long long ot = __shfl_xor_sync(0xffffffffu, bt, dlt), ok = __shfl_xor_sync(0xffffffffu, bkey, dlt);
+                if (ot < bt || (ot == bt && ok < bkey)) { bt = ot; bkey = ok; }
+            }
+            const bool hit = bkey != BEST_KEY_MISS;
+            const int k = (int)(unsigned)bkey;
+            const double td = __longlong_as_double((long long)bt);
+            if (P.path_pixel && lane == 0) path_log_ray(P, slot, (int)bounce - 1, a, b, hit ? k : -1, hit ? td : CUDART_INF);
+            if (!hit) {                                     // core.clj:40-41 miss -> accum (black)
+                reason = TERM_MISS;
+            } else {
+                float3 o = f3(a.x, a.y, a.z), d = f3(b.x, b.y, b.z);
+                float3 att, em;
+                float tmv = a.w;
+                ScatterRng rng{P.key, pix, smp, bounce, nullptr, nullptr};
+                const bool cont = shade_hit<GEN>(P.sc, scp, k, (float)td, o, d, tmv, depth > 0, rng, att, em, reason);
+                if (lane == 0 && (em.x != 0.f || em.y != 0.f || em.z != 0.f)) {   // accum += atten * emitted (core.clj:32-34,37-39)
+                    float* dst = P.sum + (size_t)slot * 3;
+                    atomicAdd(dst + 0, c.x * em.x);
+                    atomicAdd(dst + 1, c.y * em.y);
+                    atomicAdd(dst + 2, c.z * em.z);
+                }
+                if (cont) {
+                    a = make_float4(o.x, o.y, o.z, tmv);
+                    b = make_float4(d.x, d.y, d.z, b.w);
+                    c = make_float4(c.x * att.x, c.y * att.y, c.z * att.z, __uint_as_float((smp << 8) | (uint32_t)(depth - 1)));
+                    continue;
+                }
+            }
+            if (lane == 0) {
+                atomicAdd(&s_ctr[reason == TERM_MISS ? DC_TERM_MISS : reason == TERM_LIGHT ? DC_TERM_LIGHT
+                                 : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
+                if (P.path_pixel) path_log_end(P, slot, (int)bounce, reason);
+            }
+            break;
+        }
+        if (lane == 0) atomicAdd(&s_ctr[DC_RAYS], n_rays);
+        if (n_cand) atomicAdd(&s_ctr[DC_CANDIDATES], n_cand);
+        if (n_direct) atomicAdd(&s_ctr[DC_DIRECT], n_direct);
+    }
+}
+
 // Tail of a render: the work counter is exhausted and the queue is short (up to 50 more bounces of a shrinking
 // handful of paths).  ONE launch finishes the lane: the queue is cut into one slice per CTA, and every CTA runs
 // the wavefront stages on its own slice by itself — its queue counters live in shared memory, the stages are
@@ -1261,14 +1365,39 @@ __global__ void __launch_bounds__(BLOCK, GEN ? 1 : 2) wf_tail(const __grid_const
         for (;;) {
             __syncthreads();
             const unsigned n = *(volatile unsigned*)&s_st.cnt[cur][0];
-            if (n == 0) break;
+#ifdef RT_TAIL_DIAG
+            const bool diag = (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && threadIdx.x == 0;
+            unsigned long long dt0 = global_timer_ns();
+#endif
+            if (n <= W.tail_solo) {   // the thin end (or nothing): one warp per path, no more barriers (s_st.done: the claim counter)
+                if (n) wf_solo_paths<GEN>(L, &W.base.sc, cur ? L.queue[1] : L.queue[0], n, &s_st.done, s_cull, s_ctr);
+#ifdef RT_TAIL_DIAG
+                __syncthreads();
+                if (diag) printf("tail cta %u solo n %u: %llu ns\n", blockIdx.x, n, global_timer_ns() - dt0);
+#endif
+                break;
+            }
             wf_cull_body<TR, BLOCK>(L, solo, cur, n, 0u, 0ull, s_cull, nullptr, s_list);
             __syncthreads();
+#ifdef RT_TAIL_DIAG
+            unsigned long long dt1 = global_timer_ns();
+            const unsigned np_ = s_st.npairs;
+#endif
             wf_refine_body<GEN>(L, &W.base.sc, solo, cur);
             __syncthreads();
+#ifdef RT_TAIL_DIAG
+            unsigned long long dt2 = global_timer_ns();
+#endif
             wf_tiebreak_body(L, solo);
             __syncthreads();
+#ifdef RT_TAIL_DIAG
+            unsigned long long dt3 = global_timer_ns();
+#endif
             wf_shade_body<GEN>(L, &W.base.sc, solo, cur, s_ctr);
+#ifdef RT_TAIL_DIAG
+            __syncthreads();
+            if (diag) printf("tail cta %u n %u pairs %u: cull %llu refine %llu tie %llu shade %llu ns\n", blockIdx.x, n, np_, dt1 - dt0, dt2 - dt1, dt3 - dt2, global_timer_ns() - dt3);
+#endif
             cur ^= 1;
         }
         __syncthreads();

@@ -647,3 +647,35 @@ def test_tensor_core_cull_long_lists_take_several_passes(renderer):
     assert res[0][2] == res[1][2]      # (these rays skim the layer: some overflow their warp's candidate list and count as all-kept)
     for a, b in zip(out[0][:3], out[1][:3]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("scene_name", ["random", "cornell", "final", "sweep:3000"])
+def test_tail_warp_per_path_gives_identical_paths(renderer, scene_name):
+    """wf_tail finishes the thin end of its slices one warp per path (wf_solo_paths: leaves dealt over the lanes, closest hit by
+    a shuffle minimum, shading replicated on the lanes).  Same cull key, same exact FP64 tests, same merge rule, same Philox
+    blocks as the staged kernels: whole paths (radiance, bounce count, termination) and the bounce logs must be IDENTICAL
+    whether a slice goes solo never (0), at 16 paths or from the tail's first bounce on (1 << 20)."""
+    import bench
+    nx, ny = 320, 200
+    flat, cam_type, cam = bench.build_scene(scene_name, nx, ny, 1)
+    renderer.set_scene(flat)
+    renderer.set_camera(cam_type, cam)
+    rng = np.random.default_rng(5)
+    n = 120_000 if scene_name in ("random", "cornell") else 70_000
+    pix = rng.integers(0, nx * ny, n).astype(np.int32)
+    smp = rng.integers(0, 64, n).astype(np.int32)
+    out, ctr = {}, {}
+    try:
+        for solo in (0, 16, 1 << 20):
+            renderer.set_option("tail_solo", solo)
+            renderer.reset_counters()
+            out[solo] = renderer.trace_paths(nx, ny, pix, smp, 50, seed=21, log_bounces=6)
+            ctr[solo] = renderer.counters()
+    finally:
+        renderer.set_option("tail_solo", 24)
+    for solo in (16, 1 << 20):
+        for a, b in zip(out[0], out[solo]):
+            if isinstance(a, np.ndarray):
+                assert a.tobytes() == b.tobytes(), f"{scene_name}: tail_solo={solo} differs from the staged tail"
+        for key in ("rays", "samples", "term_light", "term_absorb", "term_depth", "term_miss"):
+            assert ctr[0][key] == ctr[solo][key], f"{scene_name}: counter {key} tail_solo={solo}: {ctr[solo][key]} != {ctr[0][key]}"
