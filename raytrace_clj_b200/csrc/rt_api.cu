@@ -122,7 +122,8 @@ struct Options {
     int rows = 0;                     // multi-device partition: 0 = sample slices, 1 = interleaved rows
     int tail_block = 256;             // RT_TAIL_BLOCK: CTA size of the tail kernel (32 | 64 | 128 | 256)
     int tail_rays = 1;                // RT_TAIL_RAYS: rays per thread of the tail kernel's cull while its slices are long (1 | 4)
-    int tail_solo = 24;               // RT_TAIL_SOLO: a tail slice of this many paths or fewer is finished one warp per path (0 = staged to the end)
+    int tail_solo = 24;               // RT_TAIL_SOLO: a tail slice of this many paths or fewer is finished one lane group per path (0 = staged to the end)
+    int tail_lpp = 32;                // RT_TAIL_LPP: lanes of such a group (8 | 16 | 32)
     int mega_regcap = 0;              // 1: the register-capped megakernel (128 registers, 2 CTAs / SM) instead of the uncapped one
     int wave_depth = 2;               // RT_WAVE_DEPTH: iterations the host keeps queued ahead of the GPU per lane
     int cull_tc = 1;                  // RT_CULL_TC: 0 = FP32 cull (wf_cull) always; 1 = the cull runs on the tensor cores (wf_cull_tc) when the list fits (<= 1024 leaves);
@@ -314,6 +315,7 @@ Options options_from_env() {
     o.wave_depth = env_int("RT_WAVE_DEPTH", o.wave_depth);
     o.tail_rays = env_int("RT_TAIL_RAYS", o.tail_rays);
     o.tail_solo = env_int("RT_TAIL_SOLO", o.tail_solo);
+    o.tail_lpp = env_int("RT_TAIL_LPP", o.tail_lpp);
     o.tail_block = env_int("RT_TAIL_BLOCK", o.tail_block);
     o.cull_tc = env_int("RT_CULL_TC", o.cull_tc);
     o.tc_tiles_per_cta = env_int("RT_TC_TILES_PER_CTA", o.tc_tiles_per_cta);
@@ -446,6 +448,7 @@ int launch_wave(rt_ctx* ctx, DeviceBuffers& d, const RenderParams& P, unsigned l
         W[l].claims_per_warp = claims;
         W[l].resident_warps = claims ? resident_warps : 0;
         W[l].tail_solo = (unsigned)std::max(0, opt.tail_solo);
+        W[l].tail_lpp = opt.tail_lpp == 8 ? 8u : (opt.tail_lpp == 16 ? 16u : 32u);
         st[l] = l == 0 ? stream : L.stream;
     }
     // RT_TRACE=<file>: device-side timeline of this render's kernels (dumped by the next rt_get_counters)
@@ -1525,6 +1528,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "mega_regcap") o.mega_regcap = (int)value;
     else if (k == "tail_rays") o.tail_rays = (int)value;
     else if (k == "tail_solo") o.tail_solo = (int)value;
+    else if (k == "tail_lpp") o.tail_lpp = (int)value;
     else if (k == "tail_block") o.tail_block = (int)value;
     else if (k == "cull_tc") o.cull_tc = (int)value;
     else if (k == "tc_tiles_per_cta") o.tc_tiles_per_cta = (int)value;

@@ -498,7 +498,8 @@ struct WaveParams {
     int tc_tile0, tc_launch_tiles; // wf_cull_tc: this launch tests feature tiles [tc_tile0, tc_tile0 + tc_launch_tiles) of the list (<= 4: they
     int tc_pass;                   //   stay resident in shared memory); a longer list takes several launches ("passes") per iteration, and only
                                    //   pass 0 generates the fresh entries' rays and counts the rays
-    unsigned tail_solo;            // wf_tail: a slice that has shrunk to this many paths or fewer is finished one WARP per path (wf_solo_paths)
+    unsigned tail_solo;            // wf_tail: a slice that has shrunk to this many paths or fewer is finished by groups of tail_lpp lanes,
+    unsigned tail_lpp;             //   each running one path at a time to its end (wf_solo_paths); tail_lpp = 8 | 16 | 32
 };
 __device__ __forceinline__ void publish_status(const WaveParams& W, unsigned n_next, unsigned n_fresh, unsigned exhausted, unsigned mode,
                                                unsigned seq) {
@@ -1200,84 +1201,96 @@ __global__ void __launch_bounds__(128) trace_bvh_kernel(const __grid_constant__ 
     }
 }
 
-// The thin end of a tail slice: a handful of paths with up to max_depth bounces still to go.  Staged, every bounce of
-// those few paths costs the CTA four barriers and a chain of dependent global loads (pairs -> ray -> sphere ->
-// closest-hit words -> candidates -> queue record: ~9 us per bounce whatever the population); here every WARP takes
-// one path at a time and keeps it in registers until it ends.  All 32 lanes hold the same ray; the listed leaves are
-// dealt over the lanes (lane, lane + 32, ...: the same conservative FP32 test as the cull, then the exact FP64 test for what
-// passed, with the warp converged), the direct spheres likewise, the closest hit is the minimum over the lanes of (t bits, tie key) — the merge
-// rule of wf_refine + wf_tiebreak + wf_shade — and the shading runs on every lane with identical inputs (no divergence,
-// same Philox block); lane 0 owns the side effects.  Same arithmetic as the staged path: results equal bit for bit.
+// The thin end of a tail slice: a few dozen paths with up to max_depth bounces still to go (on the random scene a late
+// bounce ends only ~8 % of the paths).  Staged, every bounce of those few paths costs the CTA four barriers and a chain of
+// dependent global loads (pairs -> ray -> sphere -> closest-hit words -> candidates -> queue record: ~12 us per bounce
+// whatever the population, RT_TAIL_DIAG); here a GROUP of `lpp` lanes (8 | 16 | 32: 4 | 2 | 1 paths per warp) takes one
+// path at a time and keeps it in registers until it ends.  All lanes of a group hold the same ray; the listed leaves are
+// dealt over the group's lanes (the same conservative FP32 key as the cull, then the exact FP64 test for what passed,
+// with the warp converged), the direct spheres likewise, the closest hit is the minimum over the group of (t bits, tie
+// key) — the merge rule of wf_refine + wf_tiebreak + wf_shade — and the shading runs on every lane of the group with
+// identical inputs (same Philox block); the group's first lane owns the side effects.  A group whose path has ended
+// claims the next one from the slice's shared counter.  Same arithmetic as the staged path: results equal bit for bit.
 template <bool GEN>
 __device__ __forceinline__ void wf_solo_paths(const WaveParams& W, const DevScene* scp, const float4* qc, unsigned n, unsigned* claim,
                                               const float4* s_cull, unsigned* s_ctr) {
     const RenderParams& P = W.base;
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned lpp = W.tail_lpp;                       // lanes per path: 8, 16 or 32
+    const unsigned sub = lane & (lpp - 1u), lead = lane & ~(lpp - 1u);
+    bool active = false;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+    uint32_t slot = 0u, pix = 0u;
+    unsigned n_rays = 0, n_cand = 0, n_direct = 0;
     for (;;) {
-        unsigned i = 0;
-        if (lane == 0) i = atomicAdd(claim, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= n) return;
-        float4 a = qc[3 * (size_t)i], b = qc[3 * (size_t)i + 1], c = qc[3 * (size_t)i + 2];
-        const uint32_t slot = __float_as_uint(b.w);
-        const uint32_t pix = rng_pixel(P, slot);
-        unsigned n_rays = 0, n_cand = 0, n_direct = 0;
-        int reason = TERM_NONE;
-        for (;;) {
-            const uint32_t sd = __float_as_uint(c.w), smp = sd >> 8;
-            const int depth = (int)(sd & 255u);
-            const uint32_t bounce = (uint32_t)(P.max_depth - depth + 1);
-            ++n_rays;
-            Culler<1, 32, false> K;
-            K.set_ray(0, a.x, a.y, a.z, b.x, b.y, b.z);
-            unsigned long long bt = BEST_T_INIT, bkey = BEST_KEY_MISS;
-            // 1024 leaves at a time: the cull key of this lane's 32 of them first (bit j = leaf base + 32 j + lane passed; a direct
-            // sphere always does), then the exact tests with the warp converged — as many rounds as the busiest lane has
-            // candidates (1 or 2), not one round per leaf position that saw a survivor
-            for (int base = 0; base < P.sc.n; base += 1024) {
-                unsigned mask = 0u;
-                const int jn = min(32, (P.sc.n - base + 31) >> 5);
+        // every collective below is executed by the whole warp; a group without a path just idles through the bounce
+        unsigned i = 0xffffffffu;
+        if (!active && sub == 0u) i = atomicAdd(claim, 1u);
+        i = __shfl_sync(0xffffffffu, i, (int)lead);
+        if (!active && i < n) {
+            a = qc[3 * (size_t)i]; b = qc[3 * (size_t)i + 1]; c = qc[3 * (size_t)i + 2];
+            slot = __float_as_uint(b.w);
+            pix = rng_pixel(P, slot);
+            active = true;
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        const uint32_t sd = __float_as_uint(c.w), smp = sd >> 8;
+        const int depth = (int)(sd & 255u);
+        const uint32_t bounce = (uint32_t)(P.max_depth - depth + 1);
+        Culler<1, 32, false> K;
+        K.set_ray(0, a.x, a.y, a.z, b.x, b.y, b.z);
+        if (active && sub == 0u) ++n_rays;
+        unsigned long long bt = BEST_T_INIT, bkey = BEST_KEY_MISS;
+        // 64 * lpp leaves at a time: the cull key of this lane's 64 of them first (bit j = leaf base + lpp j + sub passed; a
+        // direct sphere always does), then the exact tests with the warp converged — as many rounds as the busiest lane has
+        // candidates (1 or 2), not one round per leaf position that saw a survivor
+        for (int base = 0; base < P.sc.n; base += 64 * (int)lpp) {
+            unsigned long long mask = 0ull;
+            if (active) {
+                const int jn = min(64, (P.sc.n - base + (int)lpp - 1) / (int)lpp);
 #pragma unroll 4
                 for (int j = 0; j < jn; ++j) {
-                    const int s = base + 32 * j + (int)lane;
+                    const int s = base + (int)lpp * j + (int)sub;
                     bool pass = s < P.sc.n;                       // beyond the list: a sphere that bypasses the cull
                     if (s < P.sc.n_list) {
                         const float4 S = P.preloaded ? s_cull[s] : __ldg(&P.sc.cull_a[s]);
                         pass = (int)K.key_bits(S, 0) >= 0;        // sign bit clear = survived the cull
                     }
-                    mask |= (pass ? 1u : 0u) << j;
-                }
-                while (__any_sync(0xffffffffu, mask != 0u)) {
-                    if (mask) {
-                        const int s = base + 32 * (__ffs(mask) - 1) + (int)lane;
-                        mask &= mask - 1u;
-                        if (s < P.sc.n_list) ++n_cand; else ++n_direct;
-                        const double t = refine_leaf<GEN>(scp, s, a.x, a.y, a.z, b.x, b.y, b.z, a.w, 0.001, (double)FLT_MAX, true, P.key, pix,
-                                                          smp, bounce);   // core.clj:25 t-range
-                        const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
-                        const unsigned long long kk = (((unsigned long long)__ldg(&P.sc.tie_hi[s])) << 32) | (unsigned)s;
-                        if (t < CUDART_INF && (tb < bt || (tb == bt && kk < bkey))) { bt = tb; bkey = kk; }
-                    }
+                    mask |= (unsigned long long)(pass ? 1u : 0u) << j;
                 }
             }
-#pragma unroll
-            for (int dlt = 16; dlt; dlt >>= 1) {           // t > 0: the order of the bit patterns is the order of the values
-                const unsigned long long ot = __shfl_xor_sync(0xffffffffu, bt, dlt), ok = __shfl_xor_sync(0xffffffffu, bkey, dlt);
-                if (ot < bt || (ot == bt && ok < bkey)) { bt = ot; bkey = ok; }
+            while (__any_sync(0xffffffffu, mask != 0ull)) {
+                if (mask) {
+                    const int s = base + (int)lpp * (__ffsll((long long)mask) - 1) + (int)sub;
+                    mask &= mask - 1ull;
+                    if (s < P.sc.n_list) ++n_cand; else ++n_direct;
+                    const double t = refine_leaf<GEN>(scp, s, a.x, a.y, a.z, b.x, b.y, b.z, a.w, 0.001, (double)FLT_MAX, true, P.key, pix, smp,
+                                                      bounce);   // core.clj:25 t-range
+                    const unsigned long long tb = (unsigned long long)__double_as_longlong(t);
+                    const unsigned long long kk = (((unsigned long long)__ldg(&P.sc.tie_hi[s])) << 32) | (unsigned)s;
+                    if (t < CUDART_INF && (tb < bt || (tb == bt && kk < bkey))) { bt = tb; bkey = kk; }
+                }
             }
+        }
+        for (unsigned dlt = lpp >> 1; dlt; dlt >>= 1) {    // t > 0: the order of the bit patterns is the order of the values
+            const unsigned long long ot = __shfl_xor_sync(0xffffffffu, bt, (int)dlt), ok = __shfl_xor_sync(0xffffffffu, bkey, (int)dlt);
+            if (ot < bt || (ot == bt && ok < bkey)) { bt = ot; bkey = ok; }
+        }
+        if (active) {
             const bool hit = bkey != BEST_KEY_MISS;
             const int k = (int)(unsigned)bkey;
             const double td = __longlong_as_double((long long)bt);
-            if (P.path_pixel && lane == 0) path_log_ray(P, slot, (int)bounce - 1, a, b, hit ? k : -1, hit ? td : CUDART_INF);
-            if (!hit) {                                     // core.clj:40-41 miss -> accum (black)
-                reason = TERM_MISS;
-            } else {
+            if (P.path_pixel && sub == 0u) path_log_ray(P, slot, (int)bounce - 1, a, b, hit ? k : -1, hit ? td : CUDART_INF);
+            int reason = TERM_MISS;                         // core.clj:40-41 miss -> accum (black)
+            bool cont = false;
+            if (hit) {
                 float3 o = f3(a.x, a.y, a.z), d = f3(b.x, b.y, b.z);
                 float3 att, em;
                 float tmv = a.w;
                 ScatterRng rng{P.key, pix, smp, bounce, nullptr, nullptr};
-                const bool cont = shade_hit<GEN>(P.sc, scp, k, (float)td, o, d, tmv, depth > 0, rng, att, em, reason);
-                if (lane == 0 && (em.x != 0.f || em.y != 0.f || em.z != 0.f)) {   // accum += atten * emitted (core.clj:32-34,37-39)
+                reason = TERM_NONE;
+                cont = shade_hit<GEN>(P.sc, scp, k, (float)td, o, d, tmv, depth > 0, rng, att, em, reason);
+                if (sub == 0u && (em.x != 0.f || em.y != 0.f || em.z != 0.f)) {   // accum += atten * emitted (core.clj:32-34,37-39)
                     float* dst = P.sum + (size_t)slot * 3;
                     atomicAdd(dst + 0, c.x * em.x);
                     atomicAdd(dst + 1, c.y * em.y);
@@ -1287,20 +1300,21 @@ __device__ __forceinline__ void wf_solo_paths(const WaveParams& W, const DevScen
                     a = make_float4(o.x, o.y, o.z, tmv);
                     b = make_float4(d.x, d.y, d.z, b.w);
                     c = make_float4(c.x * att.x, c.y * att.y, c.z * att.z, __uint_as_float((smp << 8) | (uint32_t)(depth - 1)));
-                    continue;
                 }
             }
-            if (lane == 0) {
-                atomicAdd(&s_ctr[reason == TERM_MISS ? DC_TERM_MISS : reason == TERM_LIGHT ? DC_TERM_LIGHT
-                                 : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
-                if (P.path_pixel) path_log_end(P, slot, (int)bounce, reason);
+            if (!cont) {
+                if (sub == 0u) {
+                    atomicAdd(&s_ctr[reason == TERM_MISS ? DC_TERM_MISS : reason == TERM_LIGHT ? DC_TERM_LIGHT
+                                     : reason == TERM_ABSORB ? DC_TERM_ABSORB : DC_TERM_DEPTH], 1u);
+                    if (P.path_pixel) path_log_end(P, slot, (int)bounce, reason);
+                }
+                active = false;
             }
-            break;
         }
-        if (lane == 0) atomicAdd(&s_ctr[DC_RAYS], n_rays);
-        if (n_cand) atomicAdd(&s_ctr[DC_CANDIDATES], n_cand);
-        if (n_direct) atomicAdd(&s_ctr[DC_DIRECT], n_direct);
     }
+    if (n_rays) atomicAdd(&s_ctr[DC_RAYS], n_rays);
+    if (n_cand) atomicAdd(&s_ctr[DC_CANDIDATES], n_cand);
+    if (n_direct) atomicAdd(&s_ctr[DC_DIRECT], n_direct);
 }
 
 // Tail of a render: the work counter is exhausted and the queue is short (up to 50 more bounces of a shrinking

@@ -1,9 +1,11 @@
-"""wf_tail's warp-per-path threshold (option tail_solo) on C2 / C1 / C4: python scripts/tail_sweep.py"""
+"""wf_tail's lane-group-per-path phase (options tail_solo, tail_lpp) on C2 / C1 / C4: python scripts/tail_sweep.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from scripts.tc_sweep import run
 
 if __name__ == "__main__":
     for name in ("c2", "c1", "c4"):
-        for solo in (0, 8, 16, 24, 32, 48, 64, 128):
-            run(name, {"tail_solo": solo}, reps=8)
+        run(name, {"tail_solo": 0}, reps=8)
+        for lpp, solos in ((32, (24,)), (16, (24, 48, 96)), (8, (32, 64, 96, 128, 192, 256, 512))):
+            for solo in solos:
+                run(name, {"tail_solo": solo, "tail_lpp": lpp}, reps=8)

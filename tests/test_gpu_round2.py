@@ -649,12 +649,16 @@ def test_tensor_core_cull_long_lists_take_several_passes(renderer):
         assert np.array_equal(a, b)
 
 
+TAIL_SOLO_DEFAULT = (24, 32)   # rt_api.cu Options::tail_solo / tail_lpp
+
+
 @pytest.mark.parametrize("scene_name", ["random", "cornell", "final", "sweep:3000"])
 def test_tail_warp_per_path_gives_identical_paths(renderer, scene_name):
-    """wf_tail finishes the thin end of its slices one warp per path (wf_solo_paths: leaves dealt over the lanes, closest hit by
-    a shuffle minimum, shading replicated on the lanes).  Same cull key, same exact FP64 tests, same merge rule, same Philox
-    blocks as the staged kernels: whole paths (radiance, bounce count, termination) and the bounce logs must be IDENTICAL
-    whether a slice goes solo never (0), at 16 paths or from the tail's first bounce on (1 << 20)."""
+    """wf_tail finishes the thin end of its slices one lane group per path (wf_solo_paths: leaves dealt over the group's lanes,
+    closest hit by a shuffle minimum, shading replicated on the lanes).  Same cull key, same exact FP64 tests, same merge rule,
+    same Philox blocks as the staged kernels: whole paths (radiance, bounce count, termination) and the bounce logs must be
+    IDENTICAL whether a slice goes solo never (tail_solo = 0), at a few dozen paths, or from the tail's first bounce on
+    (1 << 20), and whatever the group size (tail_lpp = 8 | 16 | 32 lanes per path)."""
     import bench
     nx, ny = 320, 200
     flat, cam_type, cam = bench.build_scene(scene_name, nx, ny, 1)
@@ -665,17 +669,20 @@ def test_tail_warp_per_path_gives_identical_paths(renderer, scene_name):
     pix = rng.integers(0, nx * ny, n).astype(np.int32)
     smp = rng.integers(0, 64, n).astype(np.int32)
     out, ctr = {}, {}
+    modes = [(0, 32), (24, 32), (1 << 20, 32), (1 << 20, 8), (64, 16), (96, 8)]
     try:
-        for solo in (0, 16, 1 << 20):
+        for solo, lpp in modes:
             renderer.set_option("tail_solo", solo)
+            renderer.set_option("tail_lpp", lpp)
             renderer.reset_counters()
-            out[solo] = renderer.trace_paths(nx, ny, pix, smp, 50, seed=21, log_bounces=6)
-            ctr[solo] = renderer.counters()
+            out[solo, lpp] = renderer.trace_paths(nx, ny, pix, smp, 50, seed=21, log_bounces=6)
+            ctr[solo, lpp] = renderer.counters()
     finally:
-        renderer.set_option("tail_solo", 24)
-    for solo in (16, 1 << 20):
-        for a, b in zip(out[0], out[solo]):
+        renderer.set_option("tail_solo", TAIL_SOLO_DEFAULT[0])
+        renderer.set_option("tail_lpp", TAIL_SOLO_DEFAULT[1])
+    for mode in modes[1:]:
+        for a, b in zip(out[modes[0]], out[mode]):
             if isinstance(a, np.ndarray):
-                assert a.tobytes() == b.tobytes(), f"{scene_name}: tail_solo={solo} differs from the staged tail"
+                assert a.tobytes() == b.tobytes(), f"{scene_name}: (tail_solo, tail_lpp) = {mode} differs from the staged tail"
         for key in ("rays", "samples", "term_light", "term_absorb", "term_depth", "term_miss"):
-            assert ctr[0][key] == ctr[solo][key], f"{scene_name}: counter {key} tail_solo={solo}: {ctr[solo][key]} != {ctr[0][key]}"
+            assert ctr[modes[0]][key] == ctr[mode][key], f"{scene_name}: counter {key} at {mode}: {ctr[mode][key]} != {ctr[modes[0]][key]}"
