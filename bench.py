@@ -197,8 +197,8 @@ CULL_TC = 1   # set by main() from --cull
 def in_library_run(rt, device_ids, flat, cam_type, cam, nx, ny, spp, depth, variant, steps, warmup, reduce_mode, rows, seed0=600, accel=0):
     """ONE process driving len(device_ids) GPUs through the C ABI with host buffers — what the JVM caller would do
     (core.clj:99-108): rt_set_scene + rt_set_camera + rt_render per step, wall clock.  Returns a record."""
-    out_img = np.empty((ny, nx, 3), np.uint8)
     with rt.native.Renderer(device_ids) as r:
+        out_img = r.host_empty((ny, nx, 3), np.uint8)   # page-locked result buffer (rt_host_alloc): the D2H read lands in it directly
         r.set_option("reduce", reduce_mode)
         r.set_option("rows", rows)
         r.set_option("cull_tc", CULL_TC)

@@ -199,12 +199,17 @@
     (try
       (let [scene (marshal-world world)                       ; keep the Memory blocks reachable during the call
             [cam-type cam-mem] (marshal-camera camera)
-            rgb (Memory. (* 3 nx ny))]
-        (check ctx (.invokeInt (f "rt_set_scene_ex") (to-array [ctx (scene-desc scene) (scene-ext scene)])) "rt_set_scene_ex")
-        (check ctx (.invokeInt (f "rt_set_camera") (to-array [ctx (int cam-type) cam-mem])) "rt_set_camera")
-        (check ctx (.invokeInt (f "rt_render") (to-array [ctx (int nx) (int ny) (int nr) (int depth) (long seed)
-                                                          (int variant) Pointer/NULL rgb])) "rt_render")
-        (.getByteArray rgb 0 (* 3 nx ny)))
+            ;; page-locked result buffer (rt_host_alloc): the device writes the 8-bit image into it directly
+            prgb (PointerByReference.)
+            _ (check ctx (.invokeInt (f "rt_host_alloc") (to-array [ctx (long (* 3 nx ny)) prgb])) "rt_host_alloc")
+            rgb (.getValue prgb)]
+        (try
+          (check ctx (.invokeInt (f "rt_set_scene_ex") (to-array [ctx (scene-desc scene) (scene-ext scene)])) "rt_set_scene_ex")
+          (check ctx (.invokeInt (f "rt_set_camera") (to-array [ctx (int cam-type) cam-mem])) "rt_set_camera")
+          (check ctx (.invokeInt (f "rt_render") (to-array [ctx (int nx) (int ny) (int nr) (int depth) (long seed)
+                                                            (int variant) Pointer/NULL rgb])) "rt_render")
+          (.getByteArray rgb 0 (* 3 nx ny))
+          (finally (.invokeInt (f "rt_host_free") (to-array [ctx rgb])))))
       (finally (.invokeVoid (f "rt_destroy") (to-array [ctx]))))))
 
 (defn write-ppm

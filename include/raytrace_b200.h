@@ -28,6 +28,7 @@
 #ifndef RAYTRACE_B200_H
 #define RAYTRACE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -238,6 +239,14 @@ int rt_set_camera(rt_ctx* ctx, int cam_type, const float cam[24]);
  *                 (reference writes row ny-1-j, core.clj:105); may be NULL.                      */
 int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t seed,
               int variant, float* out_linear_rgb, uint8_t* out_rgb8);
+
+/* Page-locked host memory for rt_render's outputs (what the reference holds in its BufferedImage, core.clj:100-108).
+ * rt_render recognises a page-locked destination — from here, or any buffer the caller registered with the CUDA runtime —
+ * and has the device write the result into it directly; into ordinary pageable memory the result goes through the
+ * context's own page-locked staging buffer plus one host copy.  A JNA / JNI caller wraps the pointer as a direct
+ * ByteBuffer.  ctx may be NULL (the memory is usable with every context of the process).        */
+int rt_host_alloc(rt_ctx* ctx, size_t bytes, void** out);
+int rt_host_free(rt_ctx* ctx, void* p);
 
 /* Same render, device-resident: accumulate samples [sample_begin, sample_begin+sample_count)
  * of every pixel whose row j satisfies j % row_stride == row_offset into d_sum (DEVICE pointer on

@@ -1690,6 +1690,11 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
     RT_CUDA(ctx, cudaGetLastError());
     ctx->n_launches += 1;
     // results: D2H into pinned staging at link speed, then one host memcpy into the caller's (pageable) buffer
+    auto host_pinned = [](const void* p) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
     const size_t b_lin = out_linear_rgb ? align_up(px * 3 * sizeof(float), 256) : 0, b_rgb = out_rgb8 ? px * 3 : 0;
     if (b_lin + b_rgb) {
         if ((rc = ensure_stage(ctx, root, b_lin + b_rgb))) return rc;
@@ -1701,6 +1706,10 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
                                {(char*)out_rgb8, (const char*)root.d_rgb8, (char*)root.h_stage + b_lin, b_rgb}};
         for (const Part& pt : parts) {
             if (!pt.bytes) continue;
+            if (host_pinned(pt.dst)) {   // the caller's buffer is page-locked (rt_host_alloc / registered): the device writes it directly
+                RT_CUDA(ctx, cudaMemcpyAsync(pt.dst, pt.src, pt.bytes, cudaMemcpyDeviceToHost, root.stream));
+                continue;
+            }
             const size_t step = align_up((pt.bytes + NCH - 1) / NCH, 4096);
             for (int c = 0; c < NCH; ++c) {
                 const size_t off = std::min(pt.bytes, (size_t)c * step), len = std::min(pt.bytes - off, step);
@@ -1724,6 +1733,28 @@ int rt_render(rt_ctx* ctx, int nx, int ny, int nsamples, int max_depth, uint64_t
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, root.ev_r0, root.ev_r1) == cudaSuccess) ctx->reduce_ms += ms;
         cudaGetLastError();
+    }
+    return RT_OK;
+}
+
+int rt_host_alloc(rt_ctx* ctx, size_t bytes, void** out) {
+    if (!out || bytes == 0) return ctx ? fail(ctx, RT_ERR_ARG, "rt_host_alloc: bad arguments") : RT_ERR_ARG;
+    *out = nullptr;
+    if (ctx && !ctx->devs.empty()) cudaSetDevice(ctx->devs[0].dev);
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, RT_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    }
+    return RT_OK;
+}
+
+int rt_host_free(rt_ctx* ctx, void* p) {
+    if (!p) return RT_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, RT_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
     }
     return RT_OK;
 }

@@ -379,7 +379,7 @@ ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_abi_version", "rt_set_scene", "rt_set_camera", "rt_render",
     "rt_render_accumulate_device", "rt_resolve_device", "rt_trace_primary", "rt_generate_rays", "rt_shade_batch",
     "rt_measure_fp32_peak", "rt_get_counters", "rt_reset_counters", "rt_set_profile", "rt_device_info", "rt_cull_check",
-    "rt_set_scene_ex", "rt_trace_paths", "rt_set_accel", "rt_set_option", "rt_sample_device",
+    "rt_set_scene_ex", "rt_trace_paths", "rt_set_accel", "rt_set_option", "rt_sample_device", "rt_host_alloc", "rt_host_free",
 ]
 
 _lib = None
@@ -423,6 +423,8 @@ def load_library():
     L.rt_measure_fp32_peak.argtypes = [C.c_void_p, _f64p, _f64p]
     L.rt_get_counters.argtypes = [C.c_void_p, _u64p]
     L.rt_device_info.argtypes = [C.c_void_p, _i32p, _i32p, C.c_char_p]
+    L.rt_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.rt_host_free.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -465,6 +467,18 @@ class Renderer:
         if rc != 0:
             msg = self.L.rt_last_error(self.h)
             raise NativeError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+    def host_empty(self, shape, dtype):
+        """rt_host_alloc: a numpy array over page-locked host memory (rt_render has the device write such a buffer directly).
+        The memory is returned by rt_host_free when the array (and every view of it) is gone."""
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        ptr = C.c_void_p()
+        self._check(self.L.rt_host_alloc(self.h, C.c_size_t(max(nbytes, 1)), C.byref(ptr)), "rt_host_alloc")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+        weakref.finalize(buf, self.L.rt_host_free, None, C.c_void_p(ptr.value))
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def set_scene(self, flat: FlatScene):
         self.flat = flat

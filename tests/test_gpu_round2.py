@@ -686,3 +686,26 @@ def test_tail_warp_per_path_gives_identical_paths(renderer, scene_name):
                 assert a.tobytes() == b.tobytes(), f"{scene_name}: (tail_solo, tail_lpp) = {mode} differs from the staged tail"
         for key in ("rays", "samples", "term_light", "term_absorb", "term_depth", "term_miss"):
             assert ctr[modes[0]][key] == ctr[mode][key], f"{scene_name}: counter {key} at {mode}: {ctr[mode][key]} != {ctr[modes[0]][key]}"
+
+
+def test_render_into_page_locked_buffers(renderer, random_scene_flat):
+    """rt_host_alloc: rt_render has the device write page-locked destinations directly (no staging copy); pageable ones go
+    through the context's staging buffer.  Same frame either way (same seed: the float sums only differ by the order of the
+    atomic adds), and a VIEW into the middle of a page-locked block is recognised too."""
+    flat, cam_type, cam = random_scene_flat
+    renderer.set_scene(flat)
+    nx, ny = 240, 160
+    sc = rt.scene.make_random_scene(nx, ny, 11, True, random.Random(1))
+    cam_type, cam = rt.native.marshal_camera(sc["camera"])
+    renderer.set_camera(cam_type, cam)
+    lin0, img0 = renderer.render(nx, ny, 8, 50, seed=5)
+    block = renderer.host_empty((2, ny, nx, 3), np.uint8)
+    block[:] = 7
+    plin = renderer.host_empty((ny, nx, 3), np.float32)
+    plin[:] = -1.0
+    renderer.render(nx, ny, 8, 50, seed=5, out_linear=plin, out_rgb8=block[1])
+    assert np.all(block[0] == 7)
+    assert (block[1] != img0).mean() < 1e-4
+    assert np.allclose(plin, lin0, rtol=1e-5, atol=1e-6)
+    _, only_img = renderer.render(nx, ny, 8, 50, seed=5, linear=False, out_rgb8=block[0])
+    assert np.shares_memory(only_img, block[0]) and (block[0] != img0).mean() < 1e-4
