@@ -431,3 +431,140 @@ def test_generic_leaves_and_wrapper_chains_against_interpreter():
             assert np.allclose(pnuv[i][3:6], want[2], rtol=1e-8, atol=1e-8), f"case {case} {chain} ray {i}: normal"
             assert np.allclose(pnuv[i][6:8], want[3], rtol=1e-7, atol=1e-8), f"case {case} {chain} ray {i}: uv"
     assert n_hits > 0.2 * n_cases and len(kinds_hit) > 25, (n_hits, n_cases, len(kinds_hit))
+
+
+# ---- `pixel` + `color` (core.clj:17-57) as a plain Python loop over the numpy pieces above, on the oracle's replay stream -----------
+def _replay_block(seed, pixel, sample, bounce, blk):
+    """The four uniforms of Philox block (pixel, sample, bounce << 16 | blk, "RTB2") under key = seed (replay mode)."""
+    from helpers import RNG_DOMAIN, philox4x32_10
+
+    ctr = np.array([[pixel, sample, (bounce << 16) | blk, RNG_DOMAIN]], np.uint32)
+    key = np.array([[seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]], np.uint32)
+    return (philox4x32_10(ctr, key)[0] >> np.uint32(8)).astype(np.float64) / 16777216.0
+
+
+def np_color_of_sample(flat, cam_type, cam, nx, ny, pix, smp, seed, max_depth=50):
+    """One (pixel, sample): jitter + get-ray (core.clj:49-50, camera.clj:35-48), then `color` (core.clj:17-41) with the
+    Hitlist closest hit (hitable.clj:15-26) by brute force over every sphere.  Returns (radiance, rays, termination)."""
+    cam = np.asarray(cam, np.float32).astype(np.float64)
+    origin, lleft, horiz, vert, cu, cv = (cam[3 * k:3 * k + 3] for k in range(6))
+    i, j = pix % nx, pix // nx
+    u0 = _replay_block(seed, pix, smp, 0, 0)
+    s, t = (float(np.float32(i)) + u0[0]) / nx, (float(np.float32(j)) + u0[1]) / ny
+    if cam_type == 1:
+        ud = _replay_block(seed, pix, smp, 0, 1)
+        rd = (cam[21] / 2.0) * np.array([np.sqrt(ud[0]) * np.cos(2 * np.pi * ud[1]), np.sqrt(ud[0]) * np.sin(2 * np.pi * ud[1])])
+        off = cu * rd[0] + cv * rd[1]
+        o, d, time = origin + off, lleft + s * horiz + t * vert - origin - off, cam[22] + (cam[23] - cam[22]) * u0[2]
+    else:
+        o, d, time = origin, lleft + s * horiz + t * vert - origin, 0.0
+    ns = flat.n_spheres
+    c0r = flat.center0_r[:ns].astype(np.float64)
+    c1 = flat.center1[:ns, :3].astype(np.float64)
+    tt = flat.t0t1[:ns].astype(np.float64)
+    moving = (flat.sphere_flags[:ns] & RT_SPHERE_MOVING) != 0
+    is_uv = (flat.sphere_flags[:ns] & RT_SPHERE_UV) != 0
+    rad = np.abs(c0r[:, 3])
+    atten, accum = np.ones(3), np.zeros(3)
+    depth, rays = max_depth, 0
+    while True:
+        rays += 1
+        with np.errstate(invalid="ignore", divide="ignore"):
+            f = np.where(moving, (time - tt[:, 0]) / np.where(moving, tt[:, 1] - tt[:, 0], 1.0), 0.0)[:, None]
+        cen = np.where(moving[:, None], c0r[:, :3] * (1.0 - f) + c1 * f, c0r[:, :3])
+        hit, th, ph, nh = np_sphere_hit(cen, rad, o[None, :], d[None, :], 0.001, FMAX)
+        if not hit.any():
+            return accum, rays, 4                                        # miss -> accum (core.clj:40-41)
+        k = int(np.argmin(np.where(hit, th, np.inf)))                    # closest; the FIRST of equal hits (hitable.clj:17-26)
+        p, n = ph[k], nh[k]
+        uu, vv = np_sphere_uv(n) if is_uv[k] else (0.0, 0.0)
+        m = int(flat.material_id[k])
+        ty, param, mt = int(flat.mat_type[m]), float(flat.mat_param[m]), int(flat.mat_tex[m])
+        emitted = np_tex_sample(flat, mt, uu, vv, p) if ty == RT_MAT_DIFFUSE_LIGHT else np.zeros(3)
+        scat, why = None, 3                                              # why: 1 light, 2 absorbed, 3 depth
+        if depth > 0:                                                    # (and (pos? depth) (scatter ...)), core.clj:26-27
+            ub = _replay_block(seed, pix, smp, rays, 1)
+            br, bz = np.cbrt(ub[0]), 1.0 - 2.0 * ub[1]
+            bs = np.sqrt(max(0.0, 1.0 - bz * bz)) * br
+            ball = np.array([bs * np.cos(2 * np.pi * ub[2]), bs * np.sin(2 * np.pi * ub[2]), bz * br])
+            if ty == RT_MAT_LAMBERTIAN:
+                scat = (p, (p + n + ball) - p, np_tex_sample(flat, mt, uu, vv, p))
+            elif ty == RT_MAT_METAL:
+                sd = np_reflect(normalise(d), n) + param * ball
+                scat, why = ((p, sd, np_tex_sample(flat, mt, uu, vv, p)), 0) if dot(sd, n) > 0 else (None, 2)
+            elif ty == RT_MAT_DIELECTRIC:
+                rdn, mag = dot(d, n), np.sqrt(dot(d, d))
+                outward, nint, cosine = (-n, param, param * (rdn / mag)) if rdn > 0 else (n, 1.0 / param, -(rdn / mag))
+                can, refr = np_refract(d, outward, np.float64(nint))
+                scat = (p, np_reflect(d, n) if (not can or ub[3] < np_schlick(cosine, param)) else refr, np.ones(3))
+            else:
+                why = 1                                                  # DiffuseLight: scatter -> nil
+        if scat is None:
+            return accum + atten * emitted, rays, why
+        accum = accum + atten * emitted                                  # with the OLD attenuation, core.clj:32-34
+        atten = atten * scat[2]
+        o, d = scat[0], scat[1]                                          # the ray keeps its time (shader.clj:34, 54, 96)
+        depth -= 1
+
+
+@pytest.mark.parametrize("aperture", [0.0, 0.4])
+def test_pixel_and_color_loop_against_numpy(random_scene_flat, aperture):
+    """core.clj:17-57 end to end on the benchmark scene: the oracle's replay of chosen (pixel, sample) pairs against the
+    plain-Python loop above fed the same Philox uniforms — same number of rays, same termination, same radiance, at depth 50 and
+    at depth cutoffs 0 / 1 / 3 (the `(pos? depth)` gate and the emitted-only return)."""
+    flat, cam_type, cam = random_scene_flat
+    nx, ny = 1200, 800
+    if aperture > 0:                                                       # a real lens: the disk sample and the shutter time matter
+        cam = oracle.thin_lens_camera([13, 2, 3], [0, 0, 0], [0, 1, 0], 20.0, nx / ny, aperture, 10.0, 0.0, 1.0).astype(np.float32)
+        cam_type = 1
+    S = oracle.Scene(flat)
+    rng = np.random.default_rng(16)
+    n = 160
+    pix = rng.integers(0, nx * ny, n).astype(np.int32)
+    pix[:40] = (rng.integers(300, 500, 40) * nx + rng.integers(300, 900, 40)).astype(np.int32)   # the middle of the frame: the big spheres
+    smp = rng.integers(0, 1000, n).astype(np.int32)
+    terms = set()
+    for depth in (50, 0, 1, 3):
+        rad, nr, term, _ = S.trace_paths(cam_type, cam, nx, ny, pix, smp, depth, seed=77)
+        for q in range(n if depth == 50 else 40):
+            w_rad, w_nr, w_term = np_color_of_sample(flat, cam_type, cam, nx, ny, int(pix[q]), int(smp[q]), 77, depth)
+            assert (nr[q], term[q]) == (w_nr, w_term), f"depth {depth} path {q}: rays / termination {nr[q], term[q]} vs {w_nr, w_term}"
+            assert np.allclose(rad[q], w_rad, rtol=1e-9, atol=1e-12), f"depth {depth} path {q}"
+            terms.add(w_term)
+    assert {1, 3} <= terms                                                 # light (the sky dome encloses the scene: no miss) and depth cutoff
+
+
+def test_color_loop_on_an_open_scene_misses_and_lights():
+    """The same comparison on a scene WITHOUT an enclosing sky: paths end by missing everything (accum, core.clj:40-41), on a
+    DiffuseLight sphere, by Metal absorption, or at the depth cutoff — every way `color` can return."""
+    import raytrace_clj_b200 as rt
+    from raytrace_clj_b200 import hitable as H
+    from raytrace_clj_b200 import shader as shad
+    from raytrace_clj_b200 import texture as tex
+    from raytrace_clj_b200.util import vec3
+
+    const = lambda r, g, b: tex.constant(color=vec3(r, g, b))  # noqa: E731
+    items = [H.sphere(center=vec3(0, -100.5, -1), radius=100.0, material=shad.lambertian(albedo=tex.checkerboard(
+                 tex0=const(.2, .3, .1), tex1=const(.9, .9, .9), scale=10.0))),
+             H.sphere(center=vec3(0, 0, -1), radius=0.5, material=shad.lambertian(albedo=const(.8, .3, .3))),
+             H.sphere(center=vec3(1, 0, -1), radius=0.5, material=shad.metal(albedo=const(.8, .6, .2), fuzz=0.9)),
+             H.sphere(center=vec3(-1, 0, -1), radius=0.5, material=shad.dielectric(ri=1.5)),
+             H.sphere(center=vec3(-1, 0, -1), radius=-0.45, material=shad.dielectric(ri=1.5)),     # the book's hollow glass
+             H.moving_sphere(center0=vec3(0, 1.2, -1), t0=0.0, center1=vec3(0.3, 1.4, -1), t1=1.0, radius=0.3,
+                             material=shad.diffuse_light(tex=const(4, 4, 4)))]
+    flat = rt.native.marshal_world(H.hitlist(items=items))
+    S = oracle.Scene(flat)
+    nx, ny = 200, 100
+    cam = oracle.thin_lens_camera([3, 1.5, 2], [0, 0, -1], [0, 1, 0], 35.0, nx / ny, 0.1, 4.0, 0.0, 1.0).astype(np.float32)
+    rng = np.random.default_rng(17)
+    n = 220
+    pix = rng.integers(0, nx * ny, n).astype(np.int32)
+    smp = rng.integers(0, 64, n).astype(np.int32)
+    rad, nr, term, _ = S.trace_paths(1, cam, nx, ny, pix, smp, 50, seed=5)
+    seen = set()
+    for q in range(n):
+        w_rad, w_nr, w_term = np_color_of_sample(flat, 1, cam, nx, ny, int(pix[q]), int(smp[q]), 5, 50)
+        assert (nr[q], term[q]) == (w_nr, w_term), f"path {q}: rays / termination {nr[q], term[q]} vs {w_nr, w_term}"
+        assert np.allclose(rad[q], w_rad, rtol=1e-9, atol=1e-12), f"path {q}"
+        seen.add(w_term)
+    assert {1, 4} <= seen, seen
