@@ -568,3 +568,128 @@ def test_color_loop_on_an_open_scene_misses_and_lights():
         assert np.allclose(rad[q], w_rad, rtol=1e-9, atol=1e-12), f"path {q}"
         seen.add(w_term)
     assert {1, 4} <= seen, seen
+
+
+# ---- Perlin noise, procedural / image textures, the constant medium ----------------------------------------------------------------
+def np_perlin_noise(flat, p):
+    """perlin.clj:19-50 on the MARSHALLED tables (random-vectors, perm-x / -y / -z)."""
+    vec = flat.perlin_vectors.astype(np.float64)
+    perm = flat.perlin_perm
+    p = np.asarray(p, np.float64)
+    ijk = np.floor(p).astype(np.int64)
+    uvw = p - ijk
+    hh = uvw * uvw * (3 - 2 * uvw)                                       # the Hermite-smoothed blend weights (perlin-interp)
+    acc = 0.0
+    for i in range(2):
+        for j in range(2):
+            for k in range(2):
+                c = vec[perm[0][(ijk[0] + i) & 255] ^ perm[1][(ijk[1] + j) & 255] ^ perm[2][(ijk[2] + k) & 255]]
+                w = uvw - np.array([i, j, k], np.float64)
+                acc += ((i * hh[0] + (1.0 - i) * (1.0 - hh[0])) * (j * hh[1] + (1.0 - j) * (1.0 - hh[1])) *
+                        (k * hh[2] + (1.0 - k) * (1.0 - hh[2])) * float(np.dot(w, c)))
+    return acc
+
+
+def np_turbulence(flat, p, depth):
+    """perlin.clj:52-64."""
+    acc, pt, w = 0.0, np.asarray(p, np.float64), 1.0
+    for _ in range(depth):
+        acc += w * np_perlin_noise(flat, pt)
+        pt = 2.0 * pt
+        w = w / 2.0
+    return abs(acc)
+
+
+def test_perlin_and_procedural_textures_against_numpy():
+    import raytrace_clj_b200 as rt
+    from raytrace_clj_b200 import hitable as H
+    from raytrace_clj_b200 import shader as shad
+    from raytrace_clj_b200 import texture as tex
+    from raytrace_clj_b200.util import vec3
+
+    mats = [shad.lambertian(albedo=t) for t in (tex.perlin_noise(scale=3.0), tex.perlin_turbulence(scale=4.0, depth=7),
+                                               tex.marble(scale=5.0, depth=6))]
+    flat = rt.native.marshal_world(H.hitlist(items=[H.sphere(center=vec3(3 * i, 0, 0), radius=1, material=m) for i, m in enumerate(mats)]))
+    S = oracle.Scene(flat)
+    rng = np.random.default_rng(18)
+    tid = {int(t): i for i, t in enumerate(flat.tex_type)}
+    for p in np.concatenate([rng.uniform(-40, 40, (300, 3)), rng.uniform(-1, 1, (100, 3)), [[-0.25, 300.5, -513.75]]]):
+        assert S.perlin_noise(p) == pytest.approx(np_perlin_noise(flat, p), rel=1e-10, abs=1e-13)
+    for p in rng.uniform(-6, 6, (60, 3)):
+        assert S.perlin_turbulence(p, 7) == pytest.approx(np_turbulence(flat, p, 7), rel=1e-10, abs=1e-13)
+        # texture.clj:60-98: 0.5 (1 + noise(scale p)), 0.5 (1 + turbulence(scale p, depth)), 0.5 (1 + sin(scale z + 10 turbulence(p, depth)))
+        assert np.allclose(S.tex_sample(tid[rt.native.RT_TEX_PERLIN_NOISE], 0, 0, p), 0.5 * (1 + np_perlin_noise(flat, 3.0 * p)), rtol=1e-10)
+        assert np.allclose(S.tex_sample(tid[rt.native.RT_TEX_PERLIN_TURB], 0, 0, p), 0.5 * (1 + np_turbulence(flat, 4.0 * p, 7)), rtol=1e-10)
+        assert np.allclose(S.tex_sample(tid[rt.native.RT_TEX_MARBLE], 0, 0, p),
+                           0.5 * (1 + np.sin(5.0 * p[2] + 10.0 * np_turbulence(flat, p, 6))), rtol=1e-9, atol=1e-12)
+
+
+def test_image_map_and_flips_against_numpy():
+    """texture.clj:103-133: (int (* u width)), (int (* v height)), components / 255, under FlipTextureU / FlipTextureV."""
+    import raytrace_clj_b200 as rt
+    from raytrace_clj_b200 import hitable as H
+    from raytrace_clj_b200 import shader as shad
+    from raytrace_clj_b200 import texture as tex
+    from raytrace_clj_b200.util import vec3
+
+    rng = np.random.default_rng(19)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)              # height 37, width 53
+    base = tex.image_map(image=img)
+    flat = rt.native.marshal_world(H.hitlist(items=[
+        H.uv_sphere(center=vec3(0, 0, 0), radius=1, material=shad.lambertian(albedo=tex.flip_texture_v(tex=base))),
+        H.uv_sphere(center=vec3(3, 0, 0), radius=1, material=shad.lambertian(albedo=tex.flip_texture_u(tex=base)))]))
+    S = oracle.Scene(flat)
+    tid = {int(t): i for i, t in enumerate(flat.tex_type)}
+    for u, v in rng.uniform(0, 0.999999, (400, 2)):
+        px = lambda uu, vv: img[int(vv * 37), int(uu * 53)] / 255.0      # noqa: E731   (get-pixel image i j): column i, row j
+        assert np.allclose(S.tex_sample(tid[rt.native.RT_TEX_IMAGE_MAP], u, v, [0, 0, 0]), px(u, v), atol=1e-15)
+        assert np.allclose(S.tex_sample(tid[rt.native.RT_TEX_FLIP_V], u, v, [0, 0, 0]), px(u, 1.0 - v), atol=1e-15)
+        assert np.allclose(S.tex_sample(tid[rt.native.RT_TEX_FLIP_U], u, v, [0, 0, 0]), px(1.0 - u, v), atol=1e-15)
+
+
+def test_constant_medium_hit_against_numpy():
+    """hitable.clj:516-543 with its `rand` fixed at 0.5 (what the oracle draws without a path context): entry / exit through the
+    boundary over (-MAX, MAX) and (t1 + 0.0001, MAX), clamps to [t-min, t-max] and to 0, distance in units of |direction|."""
+    import math
+
+    import raytrace_clj_b200 as rt
+    from raytrace_clj_b200 import hitable as H
+    from raytrace_clj_b200 import shader as shad
+    from raytrace_clj_b200 import texture as tex
+    from raytrace_clj_b200.util import vec3
+
+    rng = np.random.default_rng(20)
+    n_hit = n_all = 0
+    for case in range(12):
+        c = rng.uniform(-2, 2, 3).astype(np.float32).astype(np.float64)
+        r = float(np.float32(rng.uniform(0.5, 2.0)))
+        rho = float(np.float32(rng.uniform(0.2, 3.0)))
+        ball = H.sphere(center=vec3(*c), radius=r, material=shad.dielectric(ri=1.5))
+        flat = rt.native.marshal_world(H.hitlist(items=[H.constant_medium(boundary=ball, density=rho, albedo=tex.constant(color=vec3(1, 1, 1)))]))
+        S = oracle.Scene(flat)
+        m = 60
+        o = (c + rng.normal(size=(m, 3)) * r * rng.uniform(0.0, 2.5, (m, 1))).astype(np.float32)       # inside and outside the boundary
+        d = ((c + rng.normal(size=(m, 3)) * r * 0.6 - o) * rng.uniform(0.2, 2.0, (m, 1))).astype(np.float32)
+        t_min = np.where(rng.random(m) < 0.3, rng.uniform(0, 2, m), 0.001)
+        t_max = np.where(rng.random(m) < 0.3, rng.uniform(0.5, 4, m), FMAX)
+        for i in range(m):
+            oi, di = o[i].astype(np.float64), d[i].astype(np.float64)
+            got_t, got_id = S.hit(o[i:i + 1], d[i:i + 1], None, float(t_min[i]), float(t_max[i]))
+            h1, t1, _, _ = np_sphere_hit(c, r, oi, di, -FMAX, FMAX)
+            want = None
+            if h1:
+                h2, t2, _, _ = np_sphere_hit(c, r, oi, di, t1 + 0.0001, FMAX)
+                if h2:
+                    a, b = (t_min[i] if t1 < t_min[i] else t1), (t_max[i] if t2 > t_max[i] else t2)
+                    if a < b:
+                        a = 0.0 if a < 0 else a
+                        mag = math.sqrt(float(np.dot(di, di)))
+                        hd = -(math.log(0.5) / rho)
+                        if hd < (b - a) * mag:
+                            want = a + hd / mag
+            n_all += 1
+            assert (got_id[0] >= 0) == (want is not None), f"case {case} ray {i}"
+            if want is not None:
+                n_hit += 1
+                assert got_t[0] == pytest.approx(want, rel=1e-10, abs=1e-12)
+    assert 0.2 * n_all < n_hit < 0.95 * n_all
