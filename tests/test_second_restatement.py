@@ -693,3 +693,44 @@ def test_constant_medium_hit_against_numpy():
                 n_hit += 1
                 assert got_t[0] == pytest.approx(want, rel=1e-10, abs=1e-12)
     assert 0.2 * n_all < n_hit < 0.95 * n_all
+
+
+def test_aabb_and_bvh_world_against_numpy(random_scene_flat):
+    """AABB.hit? (hitable.clj:36-48: slabs by min / max of (v - o) / d, `(> tmax tmin)`) on random boxes and rays, and the whole
+    bvh-node world (hitable.clj:97-106) — the oracle's reference-style BVH traversal must return the brute-force numpy closest
+    hit on the benchmark scene (its boxes can only cull: a wrong box or child order would lose hits)."""
+    rng = np.random.default_rng(21)
+    n_true = 0
+    for _ in range(3000):
+        lo = rng.uniform(-3, 2, 3)
+        hi = lo + rng.uniform(0.1, 3, 3)
+        o = rng.uniform(-6, 6, 3)
+        d = rng.normal(size=3) * rng.uniform(0.2, 3) if rng.random() < 0.4 else (lo + (hi - lo) * rng.uniform(-0.3, 1.3, 3) - o) * rng.uniform(0.2, 2)
+        t_min, t_max = (0.001, FMAX) if rng.random() < 0.6 else (rng.uniform(0, 3), rng.uniform(3, 12))
+        m, nn = (lo - o) / d, (hi - o) / d
+        want = min(np.maximum(m, nn).min(), t_max) > max(np.minimum(m, nn).max(), t_min)
+        assert oracle.aabb_hit(lo, hi, o, d, t_min, t_max) == bool(want)
+        n_true += bool(want)
+    assert 300 < n_true < 2700
+    flat, cam_type, cam = random_scene_flat
+    S = oracle.Scene(flat)
+    S.build_bvh(0.0, 1.0, seed=3)
+    ns = flat.n_spheres
+    c0r = flat.center0_r[:ns].astype(np.float64)
+    c1 = flat.center1[:ns, :3].astype(np.float64)
+    tt = flat.t0t1[:ns].astype(np.float64)
+    moving = (flat.sphere_flags[:ns] & RT_SPHERE_MOVING) != 0
+    m = 400
+    o = rng.uniform(-12, 12, (m, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(0.05, 4, m)
+    d = rng.normal(size=(m, 3)).astype(np.float32)
+    tm = rng.random(m).astype(np.float32)
+    t_bvh, id_bvh = S.hit(o, d, tm, 0.001, FMAX, use_bvh=True)
+    for i in range(m):
+        f = np.where(moving, (float(tm[i]) - tt[:, 0]) / np.where(moving, tt[:, 1] - tt[:, 0], 1.0), 0.0)[:, None]
+        cen = np.where(moving[:, None], c0r[:, :3] * (1.0 - f) + c1 * f, c0r[:, :3])
+        hit, th, _, _ = np_sphere_hit(cen, np.abs(c0r[:, 3]), o[i].astype(np.float64)[None], d[i].astype(np.float64)[None], 0.001, FMAX)
+        assert hit.any() == (id_bvh[i] >= 0)
+        if hit.any():
+            k = int(np.argmin(np.where(hit, th, np.inf)))
+            assert id_bvh[i] == k and t_bvh[i] == pytest.approx(th[k], rel=1e-12)
