@@ -709,3 +709,30 @@ def test_render_into_page_locked_buffers(renderer, random_scene_flat):
     assert np.allclose(plin, lin0, rtol=1e-5, atol=1e-6)
     _, only_img = renderer.render(nx, ny, 8, 50, seed=5, linear=False, out_rgb8=block[0])
     assert np.shares_memory(only_img, block[0]) and (block[0] != img0).mean() < 1e-4
+
+
+@pytest.mark.parametrize("variant", [rt.native.RT_VARIANT_WAVEFRONT, rt.native.RT_VARIANT_MEGAKERNEL])
+def test_trace_paths_against_the_plain_python_loop(renderer, random_scene_flat, variant):
+    """The PRODUCTION kernels against the second, independent restatement (tests/test_second_restatement.py: `pixel` + `color` as a
+    plain Python loop over numpy float64 pieces transcribed from the Clojure, fed the same Philox uniforms) — no oracle in between.
+    FP32 shading against float64: the same bounce count and termination for nearly every path, radiance to 1e-3."""
+    from test_second_restatement import np_color_of_sample
+
+    flat, cam_type, cam = random_scene_flat
+    nx, ny = 1200, 800
+    renderer.set_scene(flat)
+    renderer.set_camera(cam_type, cam)
+    rng = np.random.default_rng(31)
+    n = 400
+    pix = rng.integers(0, nx * ny, n).astype(np.int32)
+    pix[:150] = (rng.integers(250, 550, 150) * nx + rng.integers(200, 1000, 150)).astype(np.int32)   # the spheres in the middle of the frame
+    smp = rng.integers(0, 4096, n).astype(np.int32)
+    g_rad, g_nr, g_term, _ = renderer.trace_paths(nx, ny, pix, smp, 50, seed=123, variant=variant)
+    same = close = 0
+    for q in range(n):
+        w_rad, w_nr, w_term = np_color_of_sample(flat, cam_type, cam, nx, ny, int(pix[q]), int(smp[q]), 123, 50)
+        if (g_nr[q], g_term[q]) == (w_nr, w_term):
+            same += 1
+            close += bool(np.abs(g_rad[q] - w_rad).max() <= 1e-3 * max(np.abs(w_rad).max(), 1e-2))
+    assert same >= 0.985 * n, f"only {same} of {n} paths take the same bounces to the same end"
+    assert close >= 0.99 * same, f"radiance differs on {same - close} of {same} paths"
