@@ -222,7 +222,9 @@ int rt_set_accel(rt_ctx* ctx, int accel);
  * partition: 0 sample slices, 1 interleaved rows), "cull_tc" (1 = the brute-force cull runs on the tensor cores when the
  * list has 160 leaves or more, all spheres (default), 0 = FP32 pipe only, 2 = FP32 for a lane's first all-camera-ray iteration, 3 = tensor
  * cores whatever the list length),
- * "tc_tiles_per_cta", "wave_depth", "tail_rays", "tail_solo", "tail_lpp", "tail_block", "cull_shape", "tail_ctas_per_sm", "mega_regcap".
+ * "tc_tiles_per_cta", "tc_ctas", "wave_depth", "tail_rays", "tail_solo" (a tail slice of this many paths or fewer runs one warp per
+ * path, default 24; 0 = staged to the end), "tail_lpp" (lanes per such path: 8 | 16 | 32), "tail_block", "cull_shape",
+ * "tail_ctas_per_sm", "mega_regcap".
  * Unknown name -> RT_ERR_ARG.                                                                                     */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_set_camera(rt_ctx* ctx, int cam_type, const float cam[24]);

@@ -176,3 +176,18 @@ def test_no_kernel_spills_registers():
     assert len(kernels) >= 20                      # every kernel reported
     spilling = {k: v for k, v in kernels.items() if v != (0, 0)}
     assert all("mega_kernel<4, 256, 2, false>" in k for k in spilling), spilling
+
+
+def test_documented_options_are_the_implemented_ones():
+    """Every knob rt_set_option accepts (rt_api.cu) is named in the header's comment, and nothing else is."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    api = open(os.path.join(root, "raytrace_clj_b200", "csrc", "rt_api.cu")).read()
+    body = api[api.index("int rt_set_option("):]
+    body = body[:body.index("\n}\n")]
+    implemented = set(re.findall(r'k == "([a-z_0-9]+)"', body))
+    header = open(os.path.join(root, "include", "raytrace_b200.h")).read()
+    doc = header[header.index("Per-context tuning knob"):header.index("int rt_set_option(")]
+    documented = set(re.findall(r'"([a-z_0-9]+)"', doc))
+    assert implemented and implemented == documented, implemented ^ documented
