@@ -652,13 +652,14 @@ def test_tensor_core_cull_long_lists_take_several_passes(renderer):
 TAIL_SOLO_DEFAULT = (24, 32)   # rt_api.cu Options::tail_solo / tail_lpp
 
 
-@pytest.mark.parametrize("scene_name", ["random", "cornell", "final", "sweep:3000"])
+@pytest.mark.parametrize("scene_name", ["random", "cornell", "final", "sweep:3000", "sweep:5000"])
 def test_tail_warp_per_path_gives_identical_paths(renderer, scene_name):
     """wf_tail finishes the thin end of its slices one lane group per path (wf_solo_paths: leaves dealt over the group's lanes,
     closest hit by a shuffle minimum, shading replicated on the lanes).  Same cull key, same exact FP64 tests, same merge rule,
     same Philox blocks as the staged kernels: whole paths (radiance, bounce count, termination) and the bounce logs must be
     IDENTICAL whether a slice goes solo never (tail_solo = 0), at a few dozen paths, or from the tail's first bounce on
-    (1 << 20), and whatever the group size (tail_lpp = 8 | 16 | 32 lanes per path)."""
+    (1 << 20), and whatever the group size (tail_lpp = 8 | 16 | 32 lanes per path).  (sweep:5000: over 4096 leaves the list is
+    streamed through shared memory in tiles, and wf_solo_paths reads the cull records from global memory.)"""
     import bench
     nx, ny = 320, 200
     flat, cam_type, cam = bench.build_scene(scene_name, nx, ny, 1)
