@@ -6,7 +6,8 @@ spheres scene (make-random-scene n=11 moving=true, scene seed 1, ~486 spheres), 
 pixel, depth 50 (BASELINE.json configs[1]).  `value` = samples/s with the scene resident in HBM
 (kernels + reduce + resolve timed with CUDA events on the launching stream); `e2e` = the same
 metric through the C-ABI calls a front end makes (rt_set_scene + rt_set_camera + rt_render with
-HOST buffers), host<->device copies inside the timed region.
+HOST buffers: the scene arrays are ordinary numpy memory, the 8-bit frame lands in a page-locked
+buffer from rt_host_alloc), host<->device copies inside the timed region.
 
 N > 1 (torchrun, one rank per GPU): every rank renders its own 10-spp sample slice of the same
 frame (weak scaling: global spp = 10 N), the float sums are combined with one NCCL reduce over
@@ -475,7 +476,7 @@ def main():
             },
             "e2e": {"value": e2e_rec["value"], "unit": "samples/s", "h2d_bytes_per_step": flat.nbytes() + 24 * 4,
                     "d2h_bytes_per_step": nx * ny * 3, "steps": e2e_steps, "ms_per_step": e2e_rec["ms_per_step"],
-                    "path": ("rt_set_scene + rt_set_camera + rt_render, host buffers" if world == 1 else
+                    "path": ("rt_set_scene + rt_set_camera + rt_render, host buffers (8-bit frame into a page-locked rt_host_alloc buffer)" if world == 1 else
                              f"ONE process, rt_create over {world} devices + rt_set_scene + rt_set_camera + rt_render, host buffers; "
                              f"{e2e_rec['partition']}, {e2e_rec['reduce']}"),
                     "reduce_ms_per_step": e2e_rec["reduce_ms_per_step"],
