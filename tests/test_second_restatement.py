@@ -327,6 +327,24 @@ def interp_hit(obj, o, d, t_min, t_max):
         if not (t >= t_min and t <= t_max):
             return None
         return t, o + t * d, np.cross(e1, e2), (u, v)
+    if isinstance(obj, (H.Sphere, H.MovingSphere)):                       # hitable.clj:141-251 (H.UVSphere is a Sphere)
+        time = interp_hit.time
+        c = np_center_at_time(obj.center0, np.float64(obj.t0), obj.center1, np.float64(obj.t1), np.float64(time)) \
+            if isinstance(obj, H.MovingSphere) else np.asarray(obj.center, np.float64)
+        hit, t, p, n = np_sphere_hit(c, float(obj.radius), o, d, t_min, t_max)
+        if not hit:
+            return None
+        uv = tuple(float(x) for x in np_sphere_uv(n)) if isinstance(obj, H.UVSphere) else (0.0, 0.0)
+        return float(t), p, n, uv
+    if isinstance(obj, H.Hitlist):                                        # hitable.clj:15-26: shrinking t-max, later equal hits lose
+        best, far = None, t_max
+        for item in obj.items:
+            h = interp_hit(item, o, d, t_min, far)
+            if h is not None:
+                best, far = h, h[0]
+        return best
+    if isinstance(obj, H.Box):                                            # hitable.clj:491-497: the six sides
+        return interp_hit(obj.sides, o, d, t_min, t_max)
     if isinstance(obj, H.FlipNormals):                                    # hitable.clj:375-381
         h = interp_hit(obj.item, o, d, t_min, t_max)
         return None if h is None else (h[0], h[1], -h[2], h[3])
@@ -344,6 +362,9 @@ def interp_hit(obj, o, d, t_min, t_max):
         return (h[0], np.array([c * p[0] + s * p[2], p[1], -(s * p[0]) + c * p[2]]),
                 np.array([c * n[0] + s * n[2], n[1], -(s * n[0]) + c * n[2]]), h[3])
     raise TypeError(type(obj))
+
+
+interp_hit.time = 0.0          # the ray's time (only moving spheres look at it); set by the caller
 
 
 def test_generic_leaves_and_wrapper_chains_against_interpreter():
