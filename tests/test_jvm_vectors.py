@@ -83,3 +83,24 @@ def test_oracle_reproduces_the_reference_vectors():
         img = oracle.resolve(np.array(gm["mean"], np.float64).reshape(1, 1, 3), 1)
         assert img.reshape(3).tolist() == gm["rgb8"]
     assert len(J["scatter"]) > 0
+    mats = {"lambertian": shad.lambertian(albedo=tex.checkerboard(tex0=tex.constant(color=vec3(0.2, 0.3, 0.1)),
+                                                                  tex1=tex.constant(color=vec3(0.9, 0.9, 0.9)), scale=10)),
+            "metal": shad.metal(albedo=tex.constant(color=vec3(0.7, 0.6, 0.5)), fuzz=0.3),
+            "dielectric": shad.dielectric(ri=1.5),
+            "light": shad.diffuse_light(tex=tex.uv_gradient(co=vec3(1, 1, 1), cu=vec3(1, 1, 1), cv=vec3(0.5, 0.7, 1.0), cuv=vec3(0.5, 0.7, 1.0))),
+            "isotropic": shad.isotropic(albedo=tex.constant(color=vec3(0.2, 0.4, 0.9)))}
+    scenes = {k: oracle.Scene(rt.native.marshal_world(hit.hitlist(items=[hit.uv_sphere(center=vec3(0, 1, 0), radius=1, material=m)])))
+              for k, m in mats.items()}
+    for c in J["scatter"]:
+        r = c["ray"]
+        got = scenes[c["material"]].shade_batch([r["o"]], [r["d"]], [r["time"]], [0], [c["ball"]], [c["rand"]])
+        assert got["flags"][0] == (1 if c["scattered"] is not None else 0), c
+        # the ray and the fixed draws travel as float32 into the oracle: 2e-6 unless they are exactly representable
+        exact = all(float(np.float32(x)) == x for x in r["o"] + r["d"] + [r["time"], c["rand"]] + c["ball"])
+        tol = 1e-10 if exact else 5e-6
+        assert got["t"][0] == pytest.approx(c["hit"]["t"], rel=tol)
+        assert np.allclose(got["emitted"][0], c["emitted"], rtol=tol, atol=tol)
+        if c["scattered"] is not None:
+            assert np.allclose(got["origin"][0], c["scattered"]["o"], rtol=tol, atol=tol), c
+            assert np.allclose(got["dir"][0], c["scattered"]["d"], rtol=tol, atol=10 * tol), c
+            assert np.allclose(got["atten"][0], c["scattered"]["attenuation"], rtol=tol, atol=tol), c

@@ -12,7 +12,7 @@ import math
 import numpy as np
 
 import test_jvm_vectors as ingest
-from test_second_restatement import FMAX, interp_hit, normalise, np_reflect
+from test_second_restatement import FMAX, interp_hit, interp_scatter, normalise
 
 RAYS = [([13, 2, 3], [-13, -1, -3]), ([13, 2, 3], [-12.5, -1.7, -2.4]), ([0, 5, 0], [0.1, -1, 0.05]), ([0.5, 0.5, -10], [0, 0, 2]),
         ([278, 278, -800], [0.1, -0.2, 1]), ([278, 278, -800], [-0.3, 0.4, 1]), ([4, 1.3, 0.2], [-1, -0.2, 0.1]),
@@ -80,11 +80,38 @@ def test_ingest_of_a_stand_in_vector_file(tmp_path, monkeypatch):
                              "hit": bool(min(t1.min(), FMAX) > max(t0.max(), 0.001))})
     gamma = [{"mean": c, "rgb8": [int(min(255.99, 255.99 * math.sqrt(x))) for x in c]}
              for c in ([0.0, 0.25, 1.0], [0.5, 2.0, 7.0], [1e-6, 0.999, 0.1234])]
-    # one Metal scatter with fixed draws (the ingest test only requires the section to be present)
-    n = normalise(np.array([0.3, 0.5, -0.2]))
-    dirn = np.array([-1.0, -0.2, 0.1])
-    scat = [{"material": "metal", "ball": [0.1, -0.2, 0.3], "rand": 0.5,
-             "scattered": {"d": list(map(float, np_reflect(normalise(dirn), n) + 0.3 * np.array([0.1, -0.2, 0.3])))}}]
+    # dump_vectors.clj `scat`: every material on a uv-sphere (0 1 0) r = 1, every ray that hits it, rand-in-unit-sphere = ball, rand = rnd
+    from raytrace_clj_b200 import hitable as H
+    from raytrace_clj_b200 import shader as shad
+    from raytrace_clj_b200 import texture as tex
+    from raytrace_clj_b200.util import vec3
+
+    mats = {"lambertian": shad.lambertian(albedo=tex.checkerboard(tex0=tex.constant(color=vec3(0.2, 0.3, 0.1)),
+                                                                  tex1=tex.constant(color=vec3(0.9, 0.9, 0.9)), scale=10)),
+            "metal": shad.metal(albedo=tex.constant(color=vec3(0.7, 0.6, 0.5)), fuzz=0.3),
+            "dielectric": shad.dielectric(ri=1.5),
+            "light": shad.diffuse_light(tex=tex.uv_gradient(co=vec3(1, 1, 1), cu=vec3(1, 1, 1), cv=vec3(0.5, 0.7, 1.0), cuv=vec3(0.5, 0.7, 1.0))),
+            "isotropic": shad.isotropic(albedo=tex.constant(color=vec3(0.2, 0.4, 0.9)))}
+    ball = [0.1, -0.2, 0.3]
+    scat = []
+    for mk, m in mats.items():
+        sph = H.uv_sphere(center=vec3(0, 1, 0), radius=1, material=m)
+        for (o, d) in RAYS:
+            for time in (0.0, 0.37):
+                for rnd in (0.01, 0.5, 0.99):
+                    o64, d64 = np.array(o, np.float64), np.array(d, np.float64)
+                    interp_hit.time = time
+                    h = interp_hit(sph, o64, d64, 0.001, FMAX)
+                    if h is None:
+                        continue
+                    sc, em = interp_scatter(m, o64, d64, time, h, ball, rnd)
+                    scat.append({"material": mk, "ray": {"o": o, "d": d, "time": time}, "ball": ball, "rand": rnd,
+                                 "hit": {"t": float(h[0]), "p": list(map(float, h[1])), "normal": list(map(float, h[2])), "uv": list(map(float, h[3]))},
+                                 "scattered": None if sc is None else {"o": list(map(float, sc[0])), "d": list(map(float, sc[1])), "time": float(sc[2]),
+                                                                       "attenuation": list(map(float, sc[3]))},
+                                 "emitted": list(map(float, em))})
+    interp_hit.time = 0.0
+    assert len(scat) > 60 and any(c["scattered"] is None for c in scat)
     J = {"reference": "gonewest818/raytrace-clj", "hits": hits, "aabb": aabb, "scatter": scat, "get_ray": _camera_records(), "gamma": gamma}
     path = tmp_path / "jvm_vectors.json"
     path.write_text(json.dumps(J).replace(str(FMAX), repr(FMAX)))

@@ -755,3 +755,44 @@ def test_aabb_and_bvh_world_against_numpy(random_scene_flat):
         if hit.any():
             k = int(np.argmin(np.where(hit, th, np.inf)))
             assert id_bvh[i] == k and t_bvh[i] == pytest.approx(th[k], rel=1e-12)
+
+
+# ---- materials and textures as a tree-walking interpreter of the mirror's records (for the JVM-vector stand-in) -----------------------
+def interp_tex(t, u, v, p):
+    """texture.clj:14-50 on the records of raytrace_clj_b200/texture.py."""
+    from raytrace_clj_b200 import texture as T
+
+    if isinstance(t, T.Constant):
+        return np.asarray(t.color, np.float64)
+    if isinstance(t, T.UVGradient):
+        co, cu, cv, cuv = (np.asarray(x, np.float64) for x in (t.co, t.cu, t.cv, t.cuv))
+        return (cuv * (1 - u) + cv * u) * (1 - v) + (cu * (1 - u) + co * u) * v
+    if isinstance(t, T.Checkerboard):
+        return interp_tex(t.tex0 if np.prod(np.sin(t.scale * np.asarray(p, np.float64))) < 0 else t.tex1, u, v, p)
+    raise TypeError(type(t))
+
+
+def interp_scatter(m, o, d, time, h, ball, rnd):
+    """shader.clj:29-143 on the records of raytrace_clj_b200/shader.py; h = (t, p, normal, (u, v)).  Returns
+    (scattered (o, d, time, attenuation) | None, emitted)."""
+    from raytrace_clj_b200 import shader as M
+
+    t, p, n, (u, v) = h
+    ball = np.asarray(ball, np.float64)
+    zero = np.zeros(3)
+    if isinstance(m, M.Lambertian):
+        return (p, (p + n + ball) - p, time, interp_tex(m.albedo, u, v, p)), zero
+    if isinstance(m, M.Metal):
+        sd = np_reflect(normalise(d), n) + m.fuzz * ball
+        return ((p, sd, time, interp_tex(m.albedo, u, v, p)) if dot(sd, n) > 0 else None), zero
+    if isinstance(m, M.Dielectric):
+        rdn, mag = dot(d, n), np.sqrt(dot(d, d))
+        outward, nint, cosine = (-n, m.ri, m.ri * (rdn / mag)) if rdn > 0 else (n, 1.0 / m.ri, -(rdn / mag))
+        can, refr = np_refract(d, outward, np.float64(nint))
+        sd = np_reflect(d, n) if (not can or rnd < np_schlick(cosine, m.ri)) else refr
+        return (p, sd, time, np.ones(3)), zero
+    if isinstance(m, M.DiffuseLight):
+        return None, interp_tex(m.tex, u, v, p)
+    if isinstance(m, M.Isotropic):             # shader.clj:129-138: direction = the ball sample, TIME = the hit's t
+        return (p, ball, t, interp_tex(m.albedo, u, v, p)), zero
+    raise TypeError(type(m))
