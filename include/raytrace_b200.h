@@ -36,6 +36,7 @@ extern "C" {
 #endif
 
 #define RT_ABI_VERSION 2   /* 2: + rt_set_scene_ex / rt_scene_ext, rt_trace_paths, rt_set_accel, rt_set_option, rt_sample_device (additive) */
+                           /* (rt_host_alloc / rt_host_free joined version 2 later: additive, optional — an older library simply lacks the symbols) */
 
 typedef struct rt_ctx rt_ctx;
 
