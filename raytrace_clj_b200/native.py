@@ -481,38 +481,57 @@ class Renderer:
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def set_scene(self, flat: FlatScene):
+        """rt_set_scene / rt_set_scene_ex with the scene's host arrays (the C side marshals and uploads them on EVERY call).
+        The ctypes descriptors of a FlatScene whose arrays already have the ABI's dtypes and layout (no converted copies) are
+        kept, so that calling this once per frame costs the C call, not eleven numpy conversions; the descriptors point at the
+        caller's own arrays, so values changed in place are seen by the next call."""
         self.flat = flat
-        k = dict(
-            c0=np.ascontiguousarray(flat.center0_r, np.float32), c1=np.ascontiguousarray(flat.center1, np.float32),
-            tt=np.ascontiguousarray(flat.t0t1, np.float32), fl=np.ascontiguousarray(flat.sphere_flags, np.uint32),
-            mi=np.ascontiguousarray(flat.material_id, np.int32), mt=np.ascontiguousarray(flat.mat_type, np.int32),
-            mp=np.ascontiguousarray(flat.mat_param, np.float32), mx=np.ascontiguousarray(flat.mat_tex, np.int32),
-            tt2=np.ascontiguousarray(flat.tex_type, np.int32), tp=np.ascontiguousarray(flat.tex_params, np.float32),
-            tc=np.ascontiguousarray(flat.tex_children, np.int32))
-        d = _SceneDesc(flat.n_spheres, _p(k["c0"], _f32p), _p(k["c1"], _f32p), _p(k["tt"], _f32p), _p(k["fl"], _u32p),
-                       _p(k["mi"], _i32p), len(k["mt"]), _p(k["mt"], _i32p), _p(k["mp"], _f32p), _p(k["mx"], _i32p),
-                       len(k["tt2"]), _p(k["tt2"], _i32p), _p(k["tp"], _f32p), _p(k["tc"], _i32p))
-        if not flat.has_ext:
+        names = ("center0_r", "center1", "t0t1", "sphere_flags", "material_id", "mat_type", "mat_param", "mat_tex", "tex_type",
+                 "tex_params", "tex_children", "prim_type", "prim_params", "prim_aux", "prim_xform", "xform_ops", "xform_params",
+                 "perlin_vectors", "perlin_perm", "image_wh", "image_offset", "image_rgb")
+        sig = (tuple(id(getattr(flat, a)) for a in names), int(flat.n_boundary), int(flat.tie_rule))
+        cached = getattr(self, "_scene_desc", None)
+        if cached is not None and cached[0] is flat and cached[1] == sig:
+            _, _, _keep, d, x = cached
+        else:
+            c = np.ascontiguousarray
+            k = dict(
+                c0=c(flat.center0_r, np.float32), c1=c(flat.center1, np.float32), tt=c(flat.t0t1, np.float32),
+                fl=c(flat.sphere_flags, np.uint32), mi=c(flat.material_id, np.int32), mt=c(flat.mat_type, np.int32),
+                mp=c(flat.mat_param, np.float32), mx=c(flat.mat_tex, np.int32), tt2=c(flat.tex_type, np.int32),
+                tp=c(flat.tex_params, np.float32), tc=c(flat.tex_children, np.int32))
+            d = _SceneDesc(flat.n_spheres, _p(k["c0"], _f32p), _p(k["c1"], _f32p), _p(k["tt"], _f32p), _p(k["fl"], _u32p),
+                           _p(k["mi"], _i32p), len(k["mt"]), _p(k["mt"], _i32p), _p(k["mp"], _f32p), _p(k["mx"], _i32p),
+                           len(k["tt2"]), _p(k["tt2"], _i32p), _p(k["tp"], _f32p), _p(k["tc"], _i32p))
+            x, e = None, {}
+            if flat.has_ext:
+                e = dict(pt=None if flat.prim_type is None else c(flat.prim_type, np.int32),
+                         pp=None if flat.prim_params is None else c(flat.prim_params, np.float32),
+                         pa=None if flat.prim_aux is None else c(flat.prim_aux, np.int32),
+                         px=None if flat.prim_xform is None else c(flat.prim_xform, np.int32),
+                         xo=None if flat.xform_ops is None else c(flat.xform_ops, np.int32),
+                         xp=None if flat.xform_params is None else c(flat.xform_params, np.float32),
+                         pv=None if flat.perlin_vectors is None else c(flat.perlin_vectors, np.float32),
+                         pm=None if flat.perlin_perm is None else c(flat.perlin_perm, np.int32),
+                         iw=None if flat.image_wh is None else c(flat.image_wh, np.int32),
+                         io=None if flat.image_offset is None else c(flat.image_offset, np.int64),
+                         ir=None if flat.image_rgb is None else c(flat.image_rgb, np.uint8))
+                x = _SceneExt(C.sizeof(_SceneExt), int(flat.n_boundary), _p(e["pt"], _i32p), _p(e["pp"], _f32p), _p(e["pa"], _i32p),
+                              _p(e["px"], _i32p), 0 if e["xo"] is None else len(e["xo"]), _p(e["xo"], _i32p), _p(e["xp"], _f32p),
+                              int(flat.tie_rule), _p(e["pv"], _f32p), _p(e["pm"], _i32p),
+                              0 if e["iw"] is None else len(e["iw"]), _p(e["iw"], _i32p), _p(e["io"], C.POINTER(C.c_int64)),
+                              _p(e["ir"], _u8p))
+            src = {"c0": "center0_r", "c1": "center1", "tt": "t0t1", "fl": "sphere_flags", "mi": "material_id", "mt": "mat_type",
+                   "mp": "mat_param", "mx": "mat_tex", "tt2": "tex_type", "tp": "tex_params", "tc": "tex_children", "pt": "prim_type",
+                   "pp": "prim_params", "pa": "prim_aux", "px": "prim_xform", "xo": "xform_ops", "xp": "xform_params",
+                   "pv": "perlin_vectors", "pm": "perlin_perm", "iw": "image_wh", "io": "image_offset", "ir": "image_rgb"}
+            held = {**k, **e}
+            no_copies = all(v is None or v is getattr(flat, src[key]) for key, v in held.items())
+            self._scene_desc = (flat, sig, held, d, x) if no_copies else None
+        if x is None:
             self._check(self.L.rt_set_scene(self.h, C.byref(d)), "rt_set_scene")
-            return
-        c = np.ascontiguousarray
-        e = dict(pt=None if flat.prim_type is None else c(flat.prim_type, np.int32),
-                 pp=None if flat.prim_params is None else c(flat.prim_params, np.float32),
-                 pa=None if flat.prim_aux is None else c(flat.prim_aux, np.int32),
-                 px=None if flat.prim_xform is None else c(flat.prim_xform, np.int32),
-                 xo=None if flat.xform_ops is None else c(flat.xform_ops, np.int32),
-                 xp=None if flat.xform_params is None else c(flat.xform_params, np.float32),
-                 pv=None if flat.perlin_vectors is None else c(flat.perlin_vectors, np.float32),
-                 pm=None if flat.perlin_perm is None else c(flat.perlin_perm, np.int32),
-                 iw=None if flat.image_wh is None else c(flat.image_wh, np.int32),
-                 io=None if flat.image_offset is None else c(flat.image_offset, np.int64),
-                 ir=None if flat.image_rgb is None else c(flat.image_rgb, np.uint8))
-        x = _SceneExt(C.sizeof(_SceneExt), int(flat.n_boundary), _p(e["pt"], _i32p), _p(e["pp"], _f32p), _p(e["pa"], _i32p),
-                      _p(e["px"], _i32p), 0 if e["xo"] is None else len(e["xo"]), _p(e["xo"], _i32p), _p(e["xp"], _f32p),
-                      int(flat.tie_rule), _p(e["pv"], _f32p), _p(e["pm"], _i32p),
-                      0 if e["iw"] is None else len(e["iw"]), _p(e["iw"], _i32p), _p(e["io"], C.POINTER(C.c_int64)),
-                      _p(e["ir"], _u8p))
-        self._check(self.L.rt_set_scene_ex(self.h, C.byref(d), C.byref(x)), "rt_set_scene_ex")
+        else:
+            self._check(self.L.rt_set_scene_ex(self.h, C.byref(d), C.byref(x)), "rt_set_scene_ex")
 
     def set_accel(self, accel):
         """RT_ACCEL_BRUTE_FORCE (the roofline path) or RT_ACCEL_BVH (flattened GPU BVH, hitable.clj:97-123's role)."""
