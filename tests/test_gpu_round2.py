@@ -737,3 +737,41 @@ def test_trace_paths_against_the_plain_python_loop(renderer, random_scene_flat, 
             close += bool(np.abs(g_rad[q] - w_rad).max() <= 1e-3 * max(np.abs(w_rad).max(), 1e-2))
     assert same >= 0.985 * n, f"only {same} of {n} paths take the same bounces to the same end"
     assert close >= 0.99 * same, f"radiance differs on {same - close} of {same} paths"
+
+
+def test_set_scene_descriptor_cache_sees_in_place_changes(random_scene_flat):
+    """native.Renderer keeps the ctypes descriptors of an unchanged FlatScene object between rt_set_scene calls; they point at the
+    caller's own arrays, so a value changed IN PLACE (and an array replaced by a new one) must reach the next upload."""
+    import copy
+
+    flat0, cam_type, cam = random_scene_flat
+    flat = copy.deepcopy(flat0)
+    rng = np.random.default_rng(41)
+    n = 4000
+    o = np.tile(np.array([[13.0, 2.0, 3.0]], np.float32), (n, 1))
+    d = (rng.normal(size=(n, 3)) * 0.15 + np.array([-13.0, -2.0, -3.0])).astype(np.float32)
+    with rt.native.Renderer([0]) as r:
+        r.set_camera(cam_type, cam)
+        r.set_scene(flat)
+        assert r._scene_desc is not None                               # this scene needs no converted copies: descriptors kept
+        t0, id0 = r.trace_primary(o, d, None, 0.001)
+        k = int(np.bincount(id0[id0 >= 0]).argmax())                   # the sphere most of these rays hit (the big one at (4, 1, 0))
+        r.set_scene(flat)
+        t1, id1 = r.trace_primary(o, d, None, 0.001)
+        assert np.array_equal(t0, t1) and np.array_equal(id0, id1)
+        flat.center0_r[k, 1] += 0.75                                   # in place: same array object, same descriptors
+        r.set_scene(flat)
+        t2, id2 = r.trace_primary(o, d, None, 0.001)
+        flat.center0_r = flat.center0_r.copy()                         # a NEW array object: the descriptors are rebuilt
+        flat.center0_r[k, 1] -= 0.75
+        r.set_scene(flat)
+        t3, id3 = r.trace_primary(o, d, None, 0.001)
+    with rt.native.Renderer([0]) as fresh:
+        moved = copy.deepcopy(flat0)
+        moved.center0_r[k, 1] += 0.75
+        fresh.set_camera(cam_type, cam)
+        fresh.set_scene(moved)
+        t_ref, id_ref = fresh.trace_primary(o, d, None, 0.001)
+    assert not np.array_equal(id0, id2)                                # the move changed which rays hit what
+    assert np.array_equal(t2, t_ref) and np.array_equal(id2, id_ref)
+    assert np.array_equal(t3, t0) and np.array_equal(id3, id0)
